@@ -1,0 +1,636 @@
+// HBM-bound kernels of the Dino U-Net forward: LayerNorm, casts, patchify, stem conv, pooling, depthwise conv,
+// InstanceNorm, adapter tail, FiLM, squeeze-excitation, segmentation head.  All tensors are channels-last; every thread
+// moves 16-byte vectors (8 x 16-bit or 4 x fp32) along the channel dim so warps issue fully coalesced 128 B lines.
+#include "common.cuh"
+#include "../../include/dinounet_b200.h"
+#include "host_util.h"
+
+namespace b2u {
+
+template <typename T> struct Vec8 {
+  uint4 u;
+  __device__ __forceinline__ void load(const T* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(T* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), d = T16<T>::unpack2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  __device__ __forceinline__ void from_float(const float (&f)[8]) {
+    u.x = T16<T>::pack2(f[0], f[1]); u.y = T16<T>::pack2(f[2], f[3]);
+    u.z = T16<T>::pack2(f[4], f[5]); u.w = T16<T>::pack2(f[6], f[7]);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+#define B2U_DISPATCH_T(dtype, ...)                          \
+  if ((dtype) == B2U_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else { using T = __half; __VA_ARGS__; }
+
+static inline int blocks_for(long long n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// one warp per row; three passes over the (L1-resident) row: mean, centred variance, normalise.
+template <typename T, bool OUT32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, void* __restrict__ out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int rows, int D, float eps, int rows_in, int rows_out,
+                                                        int row_off) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  long long ir = r;
+  if (rows_out > 0) ir = static_cast<long long>(r / rows_out) * rows_in + row_off + (r % rows_out);
+  const float4* x = reinterpret_cast<const float4*>(in + ir * D);
+  const int nv = D >> 2;
+  float s = 0.f;
+  for (int i = lane; i < nv; i += 32) { const float4 v = x[i]; s += (v.x + v.y) + (v.z + v.w); }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = x[i];
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = x[i], g = g4[i], b = b4[i];
+    const float y0 = (v.x - mean) * rstd * g.x + b.x, y1 = (v.y - mean) * rstd * g.y + b.y;
+    const float y2 = (v.z - mean) * rstd * g.z + b.z, y3 = (v.w - mean) * rstd * g.w + b.w;
+    if (OUT32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<long long>(r) * D)[i] = make_float4(y0, y1, y2, y3);
+    } else {
+      uint2 pk = make_uint2(T16<T>::pack2(y0, y1), T16<T>::pack2(y2, y3));
+      reinterpret_cast<uint2*>(reinterpret_cast<T*>(out) + static_cast<long long>(r) * D)[i] = pk;
+    }
+  }
+}
+
+extern "C" int b2u_layernorm(const float* in, void* out, const float* gamma, const float* beta, int32_t rows, int32_t D,
+                             float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32,
+                             int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (D % 4) return set_error(-1, "b2u_layernorm: D %% 4 != 0");
+  const int grid = blocks_for(rows, 8);
+  B2U_DISPATCH_T(dtype, {
+    if (out_fp32) layernorm_kernel<T, true><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+    else layernorm_kernel<T, false><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+  });
+  return check_launch("layernorm");
+}
+
+// ------------------------------------------------------------------------------------------------ cast rows
+template <typename T>
+__global__ void cast_rows_kernel(const float* __restrict__ in, T* __restrict__ out, long long total8, int D8,
+                                 int rows_in, int rows_out, int row_off) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const long long r = i / D8;
+  const int c8 = static_cast<int>(i - r * D8);
+  long long ir = r;
+  if (rows_out > 0) ir = (r / rows_out) * rows_in + row_off + (r % rows_out);
+  const float4* p = reinterpret_cast<const float4*>(in + (ir * D8 + c8) * 8);
+  const float4 a = p[0], b = p[1];
+  const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  Vec8<T> v;
+  v.from_float(f);
+  v.store(out + i * 8);
+}
+
+extern "C" int b2u_cast_rows(const float* in, void* out, int32_t rows, int32_t D, int32_t rows_in, int32_t rows_out,
+                             int32_t row_off, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (D % 8) return set_error(-1, "b2u_cast_rows: D %% 8 != 0");
+  const long long total8 = static_cast<long long>(rows) * (D / 8);
+  B2U_DISPATCH_T(dtype, (cast_rows_kernel<T><<<blocks_for(total8, 256), 256, 0, stream>>>(
+                             in, static_cast<T*>(out), total8, D / 8, rows_in, rows_out, row_off)));
+  return check_launch("cast_rows");
+}
+
+// ------------------------------------------------------------------------------------------------ patchify
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int S) {
+  // one thread per (patch, c, ky, half) -> 8 consecutive kx
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int w = S / 16;
+  const long long total = static_cast<long long>(B) * w * w * 96;  // 768 / 8
+  if (i >= total) return;
+  const long long patch = i / 96;
+  const int k8 = static_cast<int>(i - patch * 96);
+  const int c = k8 >> 5, ky = (k8 >> 1) & 15, half = k8 & 1;
+  const int b = static_cast<int>(patch / (w * w));
+  const int pr = static_cast<int>(patch - static_cast<long long>(b) * w * w);
+  const int py = pr / w, px = pr - py * w;
+  const float* src = x + ((static_cast<long long>(b) * 3 + c) * S + (py * 16 + ky)) * S + px * 16 + half * 8;
+  const float4 a = reinterpret_cast<const float4*>(src)[0], d = reinterpret_cast<const float4*>(src)[1];
+  const float f[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+  Vec8<T> v;
+  v.from_float(f);
+  v.store(out + patch * 768 + k8 * 8);
+}
+
+extern "C" int b2u_patchify(const float* x, void* out, int32_t B, int32_t S, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (S % 16) return set_error(-1, "b2u_patchify: S %% 16 != 0");
+  const long long total = static_cast<long long>(B) * (S / 16) * (S / 16) * 96;
+  B2U_DISPATCH_T(dtype, (patchify_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(x, static_cast<T*>(out), B, S)));
+  return check_launch("patchify");
+}
+
+__global__ void write_prefix_kernel(float* __restrict__ X, const float* __restrict__ prefix, int B, int ntok,
+                                    int n_prefix, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = B * n_prefix * D;
+  if (i >= total) return;
+  const int d = i % D, t = (i / D) % n_prefix, b = i / (D * n_prefix);
+  X[(static_cast<long long>(b) * ntok + t) * D + d] = prefix[t * D + d];
+}
+
+extern "C" int b2u_write_prefix(float* X, const float* prefix, int32_t B, int32_t ntok, int32_t n_prefix, int32_t D,
+                                b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  write_prefix_kernel<<<blocks_for(static_cast<long long>(B) * n_prefix * D, 256), 256, 0, stream>>>(X, prefix, B, ntok, n_prefix, D);
+  return check_launch("write_prefix");
+}
+
+// ------------------------------------------------------------------------------------------------ SPM stem conv0
+// Conv2d(3,64,k3,s2,p1) + folded BN + ReLU: thread = (output pixel, 8 channels); weights staged in smem as [27][64].
+template <typename T>
+__global__ void __launch_bounds__(256) stem_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         T* __restrict__ out, int B, int S) {
+  __shared__ float sw[27 * 64];
+  __shared__ float ssc[64], ssh[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) {
+    const int co = i & 63, k = i >> 6;  // w is [64][3][3][3] -> k = ci*9 + ky*3 + kx
+    sw[i] = w[co * 27 + k];
+  }
+  if (threadIdx.x < 64) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
+  __syncthreads();
+  const int So = S / 2;
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long total = static_cast<long long>(B) * So * So * 8;
+  if (i >= total) return;
+  const int cg = static_cast<int>(i & 7);
+  const long long pix = i >> 3;
+  const int b = static_cast<int>(pix / (So * So));
+  const int pr = static_cast<int>(pix - static_cast<long long>(b) * So * So);
+  const int oy = pr / So, ox = pr - oy * So;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy + ky - 1;
+      if (iy < 0 || iy >= S) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox + kx - 1;
+        if (ix < 0 || ix >= S) continue;
+        const float xv = __ldg(x + ((static_cast<long long>(b) * 3 + ci) * S + iy) * S + ix);
+        const float* wp = sw + (ci * 9 + ky * 3 + kx) * 64 + cg * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wp[j], acc[j]);
+      }
+    }
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float r16 = T16<T>::to_f(T16<T>::from_f(acc[j]));  // conv output is 16-bit under autocast
+    f[j] = fmaxf(r16 * ssc[cg * 8 + j] + ssh[cg * 8 + j], 0.f);
+  }
+  Vec8<T> v;
+  v.from_float(f);
+  v.store(out + pix * 64 + cg * 8);
+}
+
+extern "C" int b2u_stem_conv0(const float* x, const float* w, const float* scale, const float* shift, void* out,
+                              int32_t B, int32_t S, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long total = static_cast<long long>(B) * (S / 2) * (S / 2) * 8;
+  B2U_DISPATCH_T(dtype, (stem_conv0_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(x, w, scale, shift, static_cast<T*>(out), B, S)));
+  return check_launch("stem_conv0");
+}
+
+// ------------------------------------------------------------------------------------------------ maxpool 3x3 s2 p1
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Ho * Wo * C8;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % C8);
+  const long long pix = i / C8;
+  const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho), b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = 2 * oy + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = 2 * ox + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      Vec8<T> v;
+      v.load(in + ((static_cast<long long>(b) * H + iy) * W + ix) * C8 * 8 + c8 * 8);
+      float f[8];
+      v.to_float(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+  }
+  Vec8<T> o;
+  o.from_float(m);
+  o.store(out + pix * C8 * 8 + c8 * 8);
+}
+
+extern "C" int b2u_maxpool3x3s2(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t dtype,
+                                b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (C % 8) return set_error(-1, "b2u_maxpool3x3s2: C %% 8 != 0");
+  const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+  B2U_DISPATCH_T(dtype, (maxpool_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(in), static_cast<T*>(out), B, H, W, C / 8)));
+  return check_launch("maxpool3x3s2");
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise 3x3
+// w9 is [9][C] fp32 (tap-major) so a thread reads its 8 channels of each tap as two float4.
+template <typename T>
+__global__ void dwconv_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ w9,
+                              const float* __restrict__ bias, int B, int H, int W, int C8, int planes, int act) {
+  const long long rows_per_img = planes == 3 ? (static_cast<long long>(H) * W * 21) / 4 : static_cast<long long>(H) * W;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * rows_per_img * C8;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % C8);
+  const long long row = i / C8;
+  const int b = static_cast<int>(row / rows_per_img);
+  long long t = row - static_cast<long long>(b) * rows_per_img;
+  int ph = H, pw = W;
+  long long poff = 0;
+  if (planes == 3) {
+    const long long n0 = static_cast<long long>(H) * W * 4, n1 = static_cast<long long>(H) * W;
+    if (t < n0) { ph = 2 * H; pw = 2 * W; }
+    else if (t < n0 + n1) { poff = n0; t -= n0; }
+    else { poff = n0 + n1; t -= n0 + n1; ph = H / 2; pw = W / 2; }
+  }
+  const int y = static_cast<int>(t / pw), x = static_cast<int>(t - static_cast<long long>(y) * pw);
+  const T* base = in + (static_cast<long long>(b) * rows_per_img + poff) * C8 * 8 + c8 * 8;
+  const int C = C8 * 8;
+  float acc[8];
+  {
+    const float4 b0 = reinterpret_cast<const float4*>(bias + c8 * 8)[0], b1 = reinterpret_cast<const float4*>(bias + c8 * 8)[1];
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = y + ky - 1;
+    if (iy < 0 || iy >= ph) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = x + kx - 1;
+      if (ix < 0 || ix >= pw) continue;
+      Vec8<T> v;
+      v.load(base + (static_cast<long long>(iy) * pw + ix) * C);
+      float f[8];
+      v.to_float(f);
+      const float4 w0 = reinterpret_cast<const float4*>(w9 + (ky * 3 + kx) * C + c8 * 8)[0];
+      const float4 w1 = reinterpret_cast<const float4*>(w9 + (ky * 3 + kx) * C + c8 * 8)[1];
+      acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+      acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+      acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+      acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+    }
+  }
+  if (act == B2U_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = gelu_erf(T16<T>::to_f(T16<T>::from_f(acc[j])));
+  }
+  Vec8<T> o;
+  o.from_float(acc);
+  o.store(out + row * C + c8 * 8);
+}
+
+extern "C" int b2u_dwconv3x3(const void* in, void* out, const float* w, const float* bias, int32_t B, int32_t H,
+                             int32_t W, int32_t C, int32_t planes, int32_t act, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (C % 8) return set_error(-1, "b2u_dwconv3x3: C %% 8 != 0");
+  if (planes != 1 && planes != 3) return set_error(-1, "b2u_dwconv3x3: planes must be 1 or 3");
+  const long long rows = planes == 3 ? (static_cast<long long>(H) * W * 21) / 4 : static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(B) * rows * (C / 8);
+  B2U_DISPATCH_T(dtype, (dwconv_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(in), static_cast<T*>(out), w, bias, B, H, W, C / 8, planes, act)));
+  return check_launch("dwconv3x3");
+}
+
+// ------------------------------------------------------------------------------------------------ adapter tail
+template <typename T>
+__global__ void tail_fuse_kernel(const void* __restrict__ base, int base_fp32, long long base_bstride,
+                                 const float* __restrict__ tap, T* __restrict__ out, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, int B, int H, int W, int Ht, int Wt, int D8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * D8;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % D8);
+  const long long pix = i / D8;
+  const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const int D = D8 * 8;
+  // bilinear source (align_corners=False), PyTorch upsample_bilinear2d index rule
+  const float sy = fmaxf((y + 0.5f) * (static_cast<float>(Ht) / H) - 0.5f, 0.f);
+  const float sx = fmaxf((x + 0.5f) * (static_cast<float>(Wt) / W) - 0.5f, 0.f);
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = y0 + (y0 < Ht - 1 ? 1 : 0), x1 = x0 + (x0 < Wt - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const float* tb = tap + static_cast<long long>(b) * Ht * Wt * D + c8 * 8;
+  float f[8];
+  if (base_fp32) {
+    const float* bp = reinterpret_cast<const float*>(base) + static_cast<long long>(b) * base_bstride + (static_cast<long long>(y) * W + x) * D + c8 * 8;
+    const float4 a = reinterpret_cast<const float4*>(bp)[0], c = reinterpret_cast<const float4*>(bp)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = c.x; f[5] = c.y; f[6] = c.z; f[7] = c.w;
+  } else {
+    Vec8<T> v;
+    v.load(reinterpret_cast<const T*>(base) + static_cast<long long>(b) * base_bstride + (static_cast<long long>(y) * W + x) * D + c8 * 8);
+    v.to_float(f);
+  }
+  const float* p00 = tb + (static_cast<long long>(y0) * Wt + x0) * D;
+  const float* p01 = tb + (static_cast<long long>(y0) * Wt + x1) * D;
+  const float* p10 = tb + (static_cast<long long>(y1) * Wt + x0) * D;
+  const float* p11 = tb + (static_cast<long long>(y1) * Wt + x1) * D;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = reinterpret_cast<const float4*>(p00)[h], c = reinterpret_cast<const float4*>(p01)[h];
+    const float4 d = reinterpret_cast<const float4*>(p10)[h], e = reinterpret_cast<const float4*>(p11)[h];
+    f[4 * h + 0] += w00 * a.x + w01 * c.x + w10 * d.x + w11 * e.x;
+    f[4 * h + 1] += w00 * a.y + w01 * c.y + w10 * d.y + w11 * e.y;
+    f[4 * h + 2] += w00 * a.z + w01 * c.z + w10 * d.z + w11 * e.z;
+    f[4 * h + 3] += w00 * a.w + w01 * c.w + w10 * d.w + w11 * e.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = f[j] * __ldg(scale + c8 * 8 + j) + __ldg(shift + c8 * 8 + j);
+  Vec8<T> o;
+  o.from_float(f);
+  o.store(out + pix * D + c8 * 8);
+}
+
+extern "C" int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_batch_stride, const float* tap, void* out,
+                             const float* scale, const float* shift, int32_t B, int32_t H, int32_t W, int32_t Ht,
+                             int32_t Wt, int32_t D, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (D % 8) return set_error(-1, "b2u_tail_fuse: D %% 8 != 0");
+  const long long total = static_cast<long long>(B) * H * W * (D / 8);
+  B2U_DISPATCH_T(dtype, (tail_fuse_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, H, W, Ht, Wt, D / 8)));
+  return check_launch("tail_fuse");
+}
+
+// ------------------------------------------------------------------------------------------------ InstanceNorm
+// stats: block = (image b, row chunk); thread = (row lane, 8-channel group); smem tree over row lanes; atomics to [B,C,2].
+template <typename T>
+__global__ void __launch_bounds__(256) in_stats_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ sums,
+                                                       int rows, int C8, int chunk) {
+  extern __shared__ float red[];  // [rows_par][C8*16]
+  const int b = blockIdx.y;
+  const int cg = threadIdx.x % C8, rl = threadIdx.x / C8;
+  const int rows_par = 256 / C8;
+  const int r0 = blockIdx.x * chunk;
+  const int r1 = min(rows, r0 + chunk);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < rows_par) {
+    for (int r = r0 + rl; r < r1; r += rows_par) {
+      Vec8<T> v;
+      v.load(x + (static_cast<long long>(b) * rows + r) * ldx + cg * 8);
+      float f[8];
+      v.to_float(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    }
+    float* my = red + (rl * C8 + cg) * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my[j] = s[j]; my[8 + j] = q[j]; }
+  }
+  __syncthreads();
+  // C8*16 outputs, each summed over rows_par partials
+  for (int o = threadIdx.x; o < C8 * 16; o += 256) {
+    float t = 0.f;
+    for (int p = 0; p < rows_par; ++p) t += red[p * C8 * 16 + o];
+    const int g = o / 16, j = o % 16;
+    const int c = g * 8 + (j & 7);
+    atomicAdd(sums + (static_cast<long long>(b) * C8 * 8 + c) * 2 + (j >> 3), t);
+  }
+}
+
+extern "C" int b2u_in_stats(const void* x, int64_t ldx, float* sums, int32_t B, int32_t rows, int32_t C, int32_t dtype,
+                            b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (C % 8 || C > 2048 || (256 % (C / 8))) return set_error(-1, "b2u_in_stats: C must be 8*2^k <= 2048");
+  const int C8 = C / 8;
+  const int chunk = rows >= 8192 ? 2048 : (rows >= 1024 ? 256 : 64);
+  dim3 grid((rows + chunk - 1) / chunk, B);
+  const size_t smem = static_cast<size_t>(256 / C8) * C8 * 16 * sizeof(float);
+  B2U_DISPATCH_T(dtype, (in_stats_kernel<T><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), ldx, sums, rows, C8, chunk)));
+  return check_launch("in_stats");
+}
+
+template <typename T>
+__global__ void in_apply_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, long long ldy,
+                                const float* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int B, int rows, int C8, float eps) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * rows * C8;
+  if (i >= total) return;
+  const int cg = static_cast<int>(i % C8);
+  const long long row = i / C8;
+  const int b = static_cast<int>(row / rows);
+  Vec8<T> v;
+  v.load(x + row * ldx + cg * 8);
+  float f[8];
+  v.to_float(f);
+  const float inv = 1.f / rows;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    const float2 sq = *reinterpret_cast<const float2*>(sums + (static_cast<long long>(b) * C8 * 8 + c) * 2);
+    const float mean = sq.x * inv;
+    const float var = fmaxf(sq.y * inv - mean * mean, 0.f);
+    const float t = (f[j] - mean) * rsqrtf(var + eps) * __ldg(gamma + c) + __ldg(beta + c);
+    f[j] = t > 0.f ? t : 0.01f * t;
+  }
+  Vec8<T> o;
+  o.from_float(f);
+  o.store(y + row * ldy + cg * 8);
+}
+
+extern "C" int b2u_in_apply(const void* x, int64_t ldx, void* y, int64_t ldy, const float* sums, const float* gamma,
+                            const float* beta, int32_t B, int32_t rows, int32_t C, float eps, int32_t dtype,
+                            b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (C % 8) return set_error(-1, "b2u_in_apply: C %% 8 != 0");
+  const long long total = static_cast<long long>(B) * rows * (C / 8);
+  B2U_DISPATCH_T(dtype, (in_apply_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(x), ldx, static_cast<T*>(y), ldy, sums, gamma, beta, B, rows, C / 8, eps)));
+  return check_launch("in_apply");
+}
+
+// ------------------------------------------------------------------------------------------------ FiLM
+template <typename T>
+__global__ void film_kernel(const T* __restrict__ gb, const T* __restrict__ zz, long long ldzz, int zoff,
+                            T* __restrict__ z, long long rows, int R8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * R8) return;
+  const int c8 = static_cast<int>(i % R8);
+  const long long r = i / R8;
+  const int R = R8 * 8;
+  Vec8<T> g, bt, zs;
+  g.load(gb + r * 2 * R + c8 * 8);
+  bt.load(gb + r * 2 * R + R + c8 * 8);
+  zs.load(zz + r * ldzz + zoff + c8 * 8);
+  float fg[8], fb[8], fz[8];
+  g.to_float(fg); bt.to_float(fb); zs.to_float(fz);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) fz[j] = fg[j] * fz[j] + fb[j];
+  Vec8<T> o;
+  o.from_float(fz);
+  o.store(z + r * R + c8 * 8);
+}
+
+extern "C" int b2u_film(const void* gb, const void* zz, int64_t ldzz, int32_t zoff, void* z, int32_t rows, int32_t R,
+                        int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (R % 8) return set_error(-1, "b2u_film: R %% 8 != 0");
+  const long long total = static_cast<long long>(rows) * (R / 8);
+  B2U_DISPATCH_T(dtype, (film_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(gb), static_cast<const T*>(zz), ldzz, zoff, static_cast<T*>(z), rows, R / 8)));
+  return check_launch("film");
+}
+
+// ------------------------------------------------------------------------------------------------ squeeze-excitation
+__global__ void se_gate_kernel(const float* __restrict__ sums, const float* __restrict__ w1, const float* __restrict__ b1,
+                               const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gate,
+                               int C, int Cr, int rows) {
+  extern __shared__ float sm[];  // pooled[C] + hidden[Cr]
+  float* pooled = sm;
+  float* hidden = sm + C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) pooled[c] = sums[(static_cast<long long>(b) * C + c) * 2] / rows;
+  __syncthreads();
+  for (int h = threadIdx.x; h < Cr; h += blockDim.x) {
+    float a = b1[h];
+    for (int c = 0; c < C; ++c) a = fmaf(w1[h * C + c], pooled[c], a);
+    hidden[h] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int h = 0; h < Cr; ++h) a = fmaf(w2[c * Cr + h], hidden[h], a);
+    gate[static_cast<long long>(b) * C + c] = 1.f / (1.f + __expf(-a));
+  }
+}
+
+extern "C" int b2u_se_gate(const float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+                           float* gate, int32_t B, int32_t C, int32_t Cr, int32_t rows, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  se_gate_kernel<<<B, 256, (C + Cr) * sizeof(float), stream>>>(sums, w1, b1, w2, b2, gate, C, Cr, rows);
+  return check_launch("se_gate");
+}
+
+template <typename T>
+__global__ void se_apply_kernel(const T* __restrict__ t, const T* __restrict__ sc, long long ldsc,
+                                const float* __restrict__ gate, T* __restrict__ out, int B, int rows, int C8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * rows * C8;
+  if (i >= total) return;
+  const int cg = static_cast<int>(i % C8);
+  const long long row = i / C8;
+  const int b = static_cast<int>(row / rows);
+  Vec8<T> a, s;
+  a.load(t + row * C8 * 8 + cg * 8);
+  s.load(sc + row * ldsc + cg * 8);
+  float fa[8], fs[8];
+  a.to_float(fa); s.to_float(fs);
+  const float* g = gate + static_cast<long long>(b) * C8 * 8 + cg * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) fa[j] = fa[j] * __ldg(g + j) + fs[j];
+  Vec8<T> o;
+  o.from_float(fa);
+  o.store(out + row * C8 * 8 + cg * 8);
+}
+
+extern "C" int b2u_se_apply(const void* t, const void* sc, int64_t ldsc, const float* gate, void* out, int32_t B,
+                            int32_t rows, int32_t C, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (C % 8) return set_error(-1, "b2u_se_apply: C %% 8 != 0");
+  const long long total = static_cast<long long>(B) * rows * (C / 8);
+  B2U_DISPATCH_T(dtype, (se_apply_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(t), static_cast<const T*>(sc), ldsc, gate, static_cast<T*>(out), B, rows, C / 8)));
+  return check_launch("se_apply");
+}
+
+// ------------------------------------------------------------------------------------------------ seg head
+// thread per pixel: InstanceNorm + LeakyReLU on C (<= 64) channels, 1x1 conv to ncls (<= 8), NCHW fp32 logits, argmax.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, const float* __restrict__ sums,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ logits, uint8_t* __restrict__ labels,
+                                                       int rows, int ncls) {
+  __shared__ float s_a[C], s_b[C];       // per-image affine: y = x*a + b
+  __shared__ float s_w[8 * C], s_bias[8];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float mean = sums[(static_cast<long long>(b) * C + c) * 2] / rows;
+    const float var = fmaxf(sums[(static_cast<long long>(b) * C + c) * 2 + 1] / rows - mean * mean, 0.f);
+    const float a = rsqrtf(var + eps) * gamma[c];
+    s_a[c] = a;
+    s_b[c] = beta[c] - mean * a;
+  }
+  for (int i = threadIdx.x; i < ncls * C; i += 256) s_w[i] = w[i];
+  if (threadIdx.x < ncls) s_bias[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= rows) return;
+  const T* xp = x + (static_cast<long long>(b) * rows + p) * C;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = k < ncls ? s_bias[k] : -INFINITY;
+#pragma unroll
+  for (int g = 0; g < C / 8; ++g) {
+    Vec8<T> v;
+    v.load(xp + g * 8);
+    float f[8];
+    v.to_float(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = f[j] * s_a[g * 8 + j] + s_b[g * 8 + j];
+      t = t > 0.f ? t : 0.01f * t;
+      t = T16<T>::to_f(T16<T>::from_f(t));  // the normalised activation is a 16-bit tensor in the reference regime
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < ncls) acc[k] = fmaf(t, s_w[k * C + g * 8 + j], acc[k]);
+    }
+  }
+  int best = 0;
+  float bv = acc[0];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < ncls) {
+      logits[(static_cast<long long>(b) * ncls + k) * rows + p] = acc[k];
+      if (acc[k] > bv) { bv = acc[k]; best = k; }
+    }
+  }
+  if (labels) labels[static_cast<long long>(b) * rows + p] = static_cast<uint8_t>(best);
+}
+
+extern "C" int b2u_seg_head(const void* x, const float* sums, const float* gamma, const float* beta, float eps,
+                            const float* w, const float* b, float* logits, uint8_t* labels, int32_t B, int32_t rows,
+                            int32_t C, int32_t ncls, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (C != 32) return set_error(-1, "b2u_seg_head: C must be 32 (plans features_per_stage[0])");
+  if (ncls < 1 || ncls > 8) return set_error(-1, "b2u_seg_head: 1 <= ncls <= 8");
+  dim3 grid((rows + 255) / 256, B);
+  B2U_DISPATCH_T(dtype, (seg_head_kernel<T, 32><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
+  return check_launch("seg_head");
+}
+
+}  // namespace b2u

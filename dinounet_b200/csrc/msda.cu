@@ -1,0 +1,150 @@
+// MultiScaleDeformableAttention forward for sm_100a.
+//
+// b2u_msda_forward — the hot-path kernel: one warp per query, lane = (head = lane/2, channel half = lane&1).  The
+//   per-head prologue the reference runs as separate torch ops (softmax over the points, reference point + offset /
+//   (W,H), ms_deform_attn.py:185-197) is fused: each lane loads its head's 8 offsets + 4 logits as three float4.
+//   The value map of one image (Hv*Wv x D/2, 16-bit, <= 1 MB for ViT-L) stays L2/L1 resident; the kernel is bound by
+//   the streaming read of the offset/logit rows and the write of the sampled rows.
+// b2u_msda_forward_f32 — signature-compatible (in meaning) with the reference pybind op `ms_deform_attn_forward`
+//   (ops/src/vision.cpp:18, ms_deform_attn_cuda.cu:25-85, ms_deform_im2col_cuda.cuh:242-304): fp32, multi-level.
+#include "common.cuh"
+#include "../../include/dinounet_b200.h"
+#include "host_util.h"
+
+namespace b2u {
+
+template <typename T, int HALF>  // HALF = channels per lane (dh / 2), even
+__global__ void __launch_bounds__(256) msda_fwd_kernel(const T* __restrict__ value, const float* __restrict__ offaw,
+                                                       T* __restrict__ out, int B, int Hv, int Wv, int heads) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = Hv * Wv;
+  const int Lq = (HW * 21) / 4;
+  const long long qg = static_cast<long long>(blockIdx.x) * 8 + warp;  // global query index in [0, B*Lq)
+  if (qg >= static_cast<long long>(B) * Lq) return;
+  const int b = static_cast<int>(qg / Lq);
+  int q = static_cast<int>(qg - static_cast<long long>(b) * Lq);
+  // reference point = cell centre of the query in its own pyramid level (dinov3_adapter.py:40-53,65-68)
+  int gh = 2 * Hv, gw = 2 * Wv;
+  if (q >= 4 * HW) { q -= 4 * HW; gh = Hv; gw = Wv; if (q >= HW) { q -= HW; gh = Hv / 2; gw = Wv / 2; } }
+  const int qy = q / gw, qx = q - qy * gw;
+  const float refx = (qx + 0.5f) / gw, refy = (qy + 0.5f) / gh;
+
+  const int head = lane >> 1, half = lane & 1;
+  const int dh = 2 * HALF;
+  const float* row = offaw + qg * (heads * 12);
+  const float4 o0 = *reinterpret_cast<const float4*>(row + head * 8);
+  const float4 o1 = *reinterpret_cast<const float4*>(row + head * 8 + 4);
+  const float4 lg = *reinterpret_cast<const float4*>(row + heads * 8 + head * 4);
+  // softmax over the 4 points (fp32, ms_deform_attn.py:189-190)
+  const float mx = fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w));
+  float w[4] = {__expf(lg.x - mx), __expf(lg.y - mx), __expf(lg.z - mx), __expf(lg.w - mx)};
+  const float inv = 1.f / (w[0] + w[1] + w[2] + w[3]);
+  const float ox[4] = {o0.x, o0.z, o1.x, o1.z}, oy[4] = {o0.y, o0.w, o1.y, o1.w};
+
+  float acc[HALF];
+#pragma unroll
+  for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+  const T* vb = value + (static_cast<long long>(b) * HW * heads + head) * dh + half * HALF;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float aw = w[p] * inv;
+    // loc = ref + off / (W, H);  pixel = loc * (W, H) - 0.5   (grid_sample align_corners=False)
+    const float px = (refx + ox[p] / Wv) * Wv - 0.5f;
+    const float py = (refy + oy[p] / Hv) * Hv - 0.5f;
+    const float fx = floorf(px), fy = floorf(py);
+    const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+    const float lx = px - fx, ly = py - fy;
+    const float cw[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int yy = y0 + (c >> 1), xx = x0 + (c & 1);
+      if (yy < 0 || yy >= Hv || xx < 0 || xx >= Wv) continue;  // zero padding
+      const float wt = aw * cw[c];
+      const T* src = vb + static_cast<long long>(yy * Wv + xx) * heads * dh;
+#pragma unroll
+      for (int j = 0; j < HALF; j += 2) {
+        const float2 v2 = T16<T>::unpack2(*reinterpret_cast<const uint32_t*>(src + j));
+        acc[j] = fmaf(wt, v2.x, acc[j]);
+        acc[j + 1] = fmaf(wt, v2.y, acc[j + 1]);
+      }
+    }
+  }
+  T* dst = out + qg * (heads * dh) + head * dh + half * HALF;
+#pragma unroll
+  for (int j = 0; j < HALF; j += 2) *reinterpret_cast<uint32_t*>(dst + j) = T16<T>::pack2(acc[j], acc[j + 1]);
+}
+
+extern "C" int b2u_msda_forward(const void* value, const float* offaw, void* out, int32_t B, int32_t Hv, int32_t Wv,
+                                int32_t heads, int32_t dh, int32_t points, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (heads != 16 || points != 4) return set_error(-1, "b2u_msda_forward: built for 16 heads x 4 points (dinounet_training.py:758-759)");
+  if ((Hv & 1) || (Wv & 1)) return set_error(-1, "b2u_msda_forward: value map must have even size");
+  const long long nq = static_cast<long long>(B) * ((Hv * Wv * 21) / 4);
+  const int grid = static_cast<int>((nq + 7) / 8);
+#define B2U_MSDA(HALF_)                                                                                               \
+  case 2 * HALF_:                                                                                                     \
+    if (dtype == B2U_BF16)                                                                                            \
+      msda_fwd_kernel<__nv_bfloat16, HALF_><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(value), offaw,  \
+                                                                      static_cast<__nv_bfloat16*>(out), B, Hv, Wv, heads); \
+    else                                                                                                              \
+      msda_fwd_kernel<__half, HALF_><<<grid, 256, 0, stream>>>(static_cast<const __half*>(value), offaw,               \
+                                                               static_cast<__half*>(out), B, Hv, Wv, heads);          \
+    break;
+  switch (dh) {
+    B2U_MSDA(6) B2U_MSDA(12) B2U_MSDA(16) B2U_MSDA(64)
+    default: return set_error(-1, "b2u_msda_forward: per-head dim %d not in {12,24,32,128}", dh);
+  }
+#undef B2U_MSDA
+  return check_launch("msda_forward");
+}
+
+// ------------------------------------------------------------------------------------------------ reference-op drop-in
+__global__ void msda_f32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                                const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                                const float* __restrict__ attw, float* __restrict__ out, int B, int S, int Lq, int M,
+                                int D, int L, int P) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Lq * M * D;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % D);
+  const int m = static_cast<int>((i / D) % M);
+  const int q = static_cast<int>((i / (static_cast<long long>(D) * M)) % Lq);
+  const int b = static_cast<int>(i / (static_cast<long long>(D) * M * Lq));
+  const long long wbase = ((static_cast<long long>(b) * Lq + q) * M + m) * L * P;
+  float acc = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const float* vl = value + ((static_cast<long long>(b) * S + lsi[l]) * M + m) * D + c;
+    for (int p = 0; p < P; ++p) {
+      const float lx = loc[(wbase + l * P + p) * 2], ly = loc[(wbase + l * P + p) * 2 + 1];
+      const float aw = attw[wbase + l * P + p];
+      const float px = lx * W - 0.5f, py = ly * H - 0.5f;
+      if (py > -1 && px > -1 && py < H && px < W) {
+        const float fx = floorf(px), fy = floorf(py);
+        const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+        const float ax = px - fx, ay = py - fy;
+        float v = 0.f;
+        if (y0 >= 0 && x0 >= 0) v += (1.f - ay) * (1.f - ax) * vl[static_cast<long long>(y0 * W + x0) * M * D];
+        if (y0 >= 0 && x0 + 1 < W) v += (1.f - ay) * ax * vl[static_cast<long long>(y0 * W + x0 + 1) * M * D];
+        if (y0 + 1 < H && x0 >= 0) v += ay * (1.f - ax) * vl[static_cast<long long>((y0 + 1) * W + x0) * M * D];
+        if (y0 + 1 < H && x0 + 1 < W) v += ay * ax * vl[static_cast<long long>((y0 + 1) * W + x0 + 1) * M * D];
+        acc += aw * v;
+      }
+    }
+  }
+  out[i] = acc;
+}
+
+extern "C" int b2u_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                    const float* loc, const float* attw, float* out, int32_t B, int32_t S, int32_t Lq,
+                                    int32_t heads, int32_t dh, int32_t levels, int32_t points, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!value || !spatial_shapes || !level_start_index || !loc || !attw || !out)
+    return set_error(-1, "b2u_msda_forward_f32: null pointer");
+  const long long total = static_cast<long long>(B) * Lq * heads * dh;
+  msda_f32_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(value, spatial_shapes, level_start_index, loc,
+                                                                            attw, out, B, S, Lq, heads, dh, levels, points);
+  return check_launch("msda_forward_f32");
+}
+
+}  // namespace b2u

@@ -1,0 +1,620 @@
+"""Host-side mirror of the reference's Dino U-Net module surface (drop-in boundary).
+
+Same class names, constructor signatures, attribute names and `state_dict()` keys (including the reference's duplicated
+keys: `decoder.encoder.*` and `...convs.N.all_modules.M.*`) as
+
+  dinounet_training.py            DinoUNet :632, DINOv3EncoderAdapter :444, FAPM :355, SqueezeExcitation :210,
+                                  DepthwiseSeparableConv :228, LearnableUpsampleBlock :249, UNetDecoder :517
+  dinov3/eval/segmentation/models/backbone/dinov3_adapter.py
+                                  DINOv3_Adapter :305, SpatialPriorModule :234, InteractionBlockWithCls :159,
+                                  Extractor :112, ConvFFN :73, DWConv :94
+  dinov3/eval/segmentation/models/utils/ms_deform_attn.py      MSDeformAttn :101
+  dinov3/models/vision_transformer.py                           DinoVisionTransformer :55
+  dinov3/layers/*                 SelfAttentionBlock, SelfAttention, LinearKMaskedBias, Mlp, SwiGLUFFN, LayerScale,
+                                  PatchEmbed, RopePositionEmbedding
+  dynamic_network_architectures   StackedConvBlocks / ConvDropoutNormReLU (third party, restated)
+
+These classes OWN the parameters (so checkpoints, optimizers, `.to()`, `.eval()` behave as with the reference) but hold
+no PyTorch compute: the only `forward` is `DinoUNet.forward`, which runs the sm_100a kernel plan of
+`dinounet_b200.engine.ForwardEngine` over packed copies of these parameters (re-packed after `load_state_dict` / `.to`).
+"""
+from __future__ import annotations
+
+import math
+import os
+import pydoc
+import warnings
+from functools import partial
+from typing import List, Optional, Sequence, Tuple, Type, Union
+
+import torch
+from torch import nn
+
+from .. import config as cfg
+
+
+class _NoForward(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError(f"{type(self).__name__} is a parameter container; run the model through DinoUNet.forward "
+                           "(hand-written sm_100a kernels) - there is no PyTorch fallback path")
+
+
+# ----------------------------------------------------------------------------------------------- DINOv3 ViT
+class LayerScale(_NoForward):
+    def __init__(self, dim: int, init_values: float = 1e-5, inplace: bool = False, device=None):
+        super().__init__()
+        self.inplace = inplace
+        self.init_values = init_values
+        self.gamma = nn.Parameter(torch.full((dim,), float(init_values), device=device))
+
+
+class LinearKMaskedBias(nn.Linear):
+    """attention.py:30-40: bias * bias_mask; bias_mask is NaN until a checkpoint fills it (reference quirk, kept)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.bias is not None:
+            self.register_buffer("bias_mask", torch.full_like(self.bias, fill_value=math.nan))
+
+
+class SelfAttention(_NoForward):
+    def __init__(self, dim, num_heads=8, qkv_bias=False, proj_bias=True, mask_k_bias=False, device=None):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        linear_class = LinearKMaskedBias if mask_k_bias else nn.Linear
+        self.qkv = linear_class(dim, dim * 3, bias=qkv_bias, device=device)
+        self.proj = nn.Linear(dim, dim, bias=proj_bias, device=device)
+
+
+class Mlp(_NoForward):
+    def __init__(self, in_features, hidden_features=None, out_features=None, bias=True, device=None, **_):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features or in_features, bias=bias, device=device)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features, bias=bias, device=device)
+
+
+class SwiGLUFFN(_NoForward):
+    def __init__(self, in_features, hidden_features=None, out_features=None, bias=True, align_to=8, device=None, **_):
+        super().__init__()
+        d = int((hidden_features or in_features) * 2 / 3)
+        hid = d + (-d % align_to)
+        self.w1 = nn.Linear(in_features, hid, bias=bias, device=device)
+        self.w2 = nn.Linear(in_features, hid, bias=bias, device=device)
+        self.w3 = nn.Linear(hid, out_features or in_features, bias=bias, device=device)
+
+
+class SelfAttentionBlock(_NoForward):
+    def __init__(self, dim, num_heads, ffn_ratio=4.0, qkv_bias=False, proj_bias=True, ffn_bias=True, init_values=None,
+                 drop_path=0.0, norm_layer=nn.LayerNorm, ffn_layer=Mlp, mask_k_bias=False, device=None):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = SelfAttention(dim, num_heads, qkv_bias, proj_bias, mask_k_bias, device)
+        self.ls1 = LayerScale(dim, init_values, device=device) if init_values else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = ffn_layer(in_features=dim, hidden_features=int(dim * ffn_ratio), bias=ffn_bias, device=device)
+        self.ls2 = LayerScale(dim, init_values, device=device) if init_values else nn.Identity()
+        self.sample_drop_ratio = drop_path
+
+
+class PatchEmbed(_NoForward):
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, flatten_embedding=False):
+        super().__init__()
+        self.img_size, self.patch_size = (img_size, img_size), (patch_size, patch_size)
+        self.in_chans, self.embed_dim = in_chans, embed_dim
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = nn.Identity()
+
+
+class RopePositionEmbedding(_NoForward):
+    def __init__(self, embed_dim, *, num_heads, base=100.0, dtype=torch.float32, device=None, **_):
+        super().__init__()
+        d_head = embed_dim // num_heads
+        self.base, self.D_head, self.dtype = base, d_head, dtype
+        periods = base ** (2 * torch.arange(d_head // 4, device=device, dtype=dtype) / (d_head // 2))
+        self.register_buffer("periods", periods, persistent=True)
+
+
+class DinoVisionTransformer(_NoForward):
+    """Parameter container for the frozen DINOv3 backbone; sizes from cfg.VARIANTS (hub/backbones.py)."""
+
+    def __init__(self, *, embed_dim=768, depth=12, num_heads=12, ffn_ratio=4.0, qkv_bias=True, layerscale_init=1e-5,
+                 ffn_layer="mlp", n_storage_tokens=4, mask_k_bias=True, untie_global_and_local_cls_norm=False,
+                 patch_size=16, drop_path_rate=0.0, device=None, **_ignored):
+        super().__init__()
+        self.num_features = self.embed_dim = embed_dim
+        self.n_blocks, self.num_heads, self.patch_size = depth, num_heads, patch_size
+        self.n_storage_tokens = n_storage_tokens
+        norm = partial(nn.LayerNorm, eps=cfg.LN_EPS_VIT)
+        ffn = Mlp if ffn_layer == "mlp" else partial(SwiGLUFFN, align_to=64)
+        self.patch_embed = PatchEmbed(224, patch_size, 3, embed_dim)
+        self.cls_token = nn.Parameter(torch.empty(1, 1, embed_dim, device=device))
+        self.storage_tokens = nn.Parameter(torch.empty(1, n_storage_tokens, embed_dim, device=device))
+        self.rope_embed = RopePositionEmbedding(embed_dim, num_heads=num_heads, base=cfg.ROPE_BASE, device=device)
+        self.blocks = nn.ModuleList([
+            SelfAttentionBlock(embed_dim, num_heads, ffn_ratio, qkv_bias, True, True, layerscale_init, drop_path_rate,
+                               norm, ffn, mask_k_bias, device) for _ in range(depth)])
+        self.chunked_blocks = False
+        self.norm = norm(embed_dim)
+        self.cls_norm = None
+        self.local_cls_norm = norm(embed_dim) if untie_global_and_local_cls_norm else None
+        self.head = nn.Identity()
+        self.mask_token = nn.Parameter(torch.empty(1, embed_dim, device=device))
+        self.init_weights()
+
+    def init_weights(self):
+        """vision_transformer.py:178-184 + init_weights_vit :41-52."""
+        nn.init.normal_(self.cls_token, std=0.02)
+        nn.init.normal_(self.storage_tokens, std=0.02)
+        nn.init.zeros_(self.mask_token)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        k = 1 / (3 * self.patch_size ** 2)
+        nn.init.uniform_(self.patch_embed.proj.weight, -math.sqrt(k), math.sqrt(k))
+        nn.init.uniform_(self.patch_embed.proj.bias, -math.sqrt(k), math.sqrt(k))
+
+
+def make_backbone(model_name: str) -> DinoVisionTransformer:
+    v = cfg.VARIANTS[model_name]
+    return DinoVisionTransformer(
+        embed_dim=v.embed_dim, depth=v.depth, num_heads=v.num_heads,
+        ffn_ratio=(4.0 if v.ffn_layer == "mlp" else 3.0), qkv_bias=v.qkv_bias, layerscale_init=1e-5,
+        ffn_layer=("mlp" if v.ffn_layer == "mlp" else "swiglu64"), n_storage_tokens=cfg.N_STORAGE_TOKENS,
+        mask_k_bias=True, untie_global_and_local_cls_norm=v.untie_global_and_local_cls_norm,
+        drop_path_rate=v.drop_path_rate)
+
+
+# ----------------------------------------------------------------------------------------------- adapter
+class MSDeformAttn(_NoForward):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, ratio=1.0):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
+        self.im2col_step = 64
+        self.d_model, self.n_levels, self.n_heads, self.n_points, self.ratio = d_model, n_levels, n_heads, n_points, ratio
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, int(d_model * ratio))
+        self.output_proj = nn.Linear(int(d_model * ratio), d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """ms_deform_attn.py:137-156."""
+        nn.init.constant_(self.sampling_offsets.weight.data, 0.0)
+        thetas = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        grid = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid = (grid / grid.abs().max(-1, keepdim=True)[0]).view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1)
+        for i in range(self.n_points):
+            grid[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(grid.view(-1))
+        nn.init.constant_(self.attention_weights.weight.data, 0.0)
+        nn.init.constant_(self.attention_weights.bias.data, 0.0)
+        nn.init.xavier_uniform_(self.value_proj.weight.data)
+        nn.init.constant_(self.value_proj.bias.data, 0.0)
+        nn.init.xavier_uniform_(self.output_proj.weight.data)
+        nn.init.constant_(self.output_proj.bias.data, 0.0)
+
+
+class DWConv(_NoForward):
+    def __init__(self, dim=768):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+
+class ConvFFN(_NoForward):
+    def __init__(self, in_features, hidden_features=None, out_features=None, drop=0.0):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features or in_features)
+        self.dwconv = DWConv(hidden_features or in_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
+        self.drop = nn.Dropout(drop)
+
+
+class Extractor(_NoForward):
+    def __init__(self, dim, num_heads=6, n_points=4, n_levels=1, deform_ratio=1.0, with_cffn=True, cffn_ratio=0.25,
+                 drop=0.0, drop_path=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), with_cp=False):
+        super().__init__()
+        self.query_norm = norm_layer(dim)
+        self.feat_norm = norm_layer(dim)
+        self.attn = MSDeformAttn(d_model=dim, n_levels=n_levels, n_heads=num_heads, n_points=n_points, ratio=deform_ratio)
+        self.with_cffn, self.with_cp = with_cffn, with_cp
+        if with_cffn:
+            self.ffn = ConvFFN(in_features=dim, hidden_features=int(dim * cffn_ratio), drop=drop)
+            self.ffn_norm = norm_layer(dim)
+            self.drop_path = nn.Identity()
+            self.drop_path_rate = drop_path
+
+
+class InteractionBlockWithCls(_NoForward):
+    def __init__(self, dim, num_heads=6, n_points=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), drop=0.0, drop_path=0.0,
+                 with_cffn=True, cffn_ratio=0.25, init_values=0.0, deform_ratio=1.0, extra_extractor=False, with_cp=False):
+        super().__init__()
+        mk = lambda: Extractor(dim=dim, n_levels=1, num_heads=num_heads, n_points=n_points, norm_layer=norm_layer,
+                               deform_ratio=deform_ratio, with_cffn=with_cffn, cffn_ratio=cffn_ratio, drop=drop,
+                               drop_path=drop_path, with_cp=with_cp)
+        self.extractor = mk()
+        self.extra_extractors = nn.Sequential(mk(), mk()) if extra_extractor else None
+
+
+class SpatialPriorModule(_NoForward):
+    def __init__(self, inplanes=64, embed_dim=384, with_cp=False):
+        super().__init__()
+        self.with_cp = with_cp
+        c = inplanes
+        self.stem = nn.Sequential(
+            nn.Conv2d(3, c, 3, 2, 1, bias=False), nn.SyncBatchNorm(c), nn.ReLU(inplace=True),
+            nn.Conv2d(c, c, 3, 1, 1, bias=False), nn.SyncBatchNorm(c), nn.ReLU(inplace=True),
+            nn.Conv2d(c, c, 3, 1, 1, bias=False), nn.SyncBatchNorm(c), nn.ReLU(inplace=True),
+            nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
+        self.conv2 = nn.Sequential(nn.Conv2d(c, 2 * c, 3, 2, 1, bias=False), nn.SyncBatchNorm(2 * c), nn.ReLU(inplace=True))
+        self.conv3 = nn.Sequential(nn.Conv2d(2 * c, 4 * c, 3, 2, 1, bias=False), nn.SyncBatchNorm(4 * c), nn.ReLU(inplace=True))
+        self.conv4 = nn.Sequential(nn.Conv2d(4 * c, 4 * c, 3, 2, 1, bias=False), nn.SyncBatchNorm(4 * c), nn.ReLU(inplace=True))
+        self.fc1 = nn.Conv2d(c, embed_dim, 1)
+        self.fc2 = nn.Conv2d(2 * c, embed_dim, 1)
+        self.fc3 = nn.Conv2d(4 * c, embed_dim, 1)
+        self.fc4 = nn.Conv2d(4 * c, embed_dim, 1)
+
+
+class DINOv3_Adapter(_NoForward):
+    def __init__(self, backbone, interaction_indexes=[9, 19, 29, 39], pretrain_size=512, conv_inplane=64, n_points=4,
+                 deform_num_heads=16, drop_path_rate=0.3, init_values=0.0, with_cffn=True, cffn_ratio=0.25,
+                 deform_ratio=0.5, add_vit_feature=True, use_extra_extractor=True, with_cp=True):
+        super().__init__()
+        self.backbone = backbone
+        self.backbone.requires_grad_(False)   # the reference freezes the backbone (dinov3_adapter.py:326)
+        self.pretrain_size = (pretrain_size, pretrain_size)
+        self.interaction_indexes = list(interaction_indexes)
+        self.add_vit_feature = add_vit_feature
+        embed_dim = self.backbone.embed_dim
+        self.patch_size = self.backbone.patch_size
+        self.level_embed = nn.Parameter(torch.zeros(3, embed_dim))
+        self.spm = SpatialPriorModule(inplanes=conv_inplane, embed_dim=embed_dim, with_cp=False)
+        n = len(self.interaction_indexes)
+        self.interactions = nn.Sequential(*[
+            InteractionBlockWithCls(dim=embed_dim, num_heads=deform_num_heads, n_points=n_points, init_values=init_values,
+                                    drop_path=drop_path_rate, with_cffn=with_cffn, cffn_ratio=cffn_ratio,
+                                    deform_ratio=deform_ratio,
+                                    extra_extractor=(i == n - 1) and use_extra_extractor, with_cp=with_cp)
+            for i in range(n)])
+        self.up = nn.ConvTranspose2d(embed_dim, embed_dim, 2, 2)
+        self.norm1, self.norm2 = nn.SyncBatchNorm(embed_dim), nn.SyncBatchNorm(embed_dim)
+        self.norm3, self.norm4 = nn.SyncBatchNorm(embed_dim), nn.SyncBatchNorm(embed_dim)
+        self.up.apply(self._init_weights)
+        self.spm.apply(self._init_weights)
+        self.interactions.apply(self._init_weights)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        nn.init.normal_(self.level_embed)
+
+    @staticmethod
+    def _init_weights(m):
+        """dinov3_adapter.py:375-388."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, (nn.LayerNorm, nn.BatchNorm2d)):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+        elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+            m.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+            if m.bias is not None:
+                m.bias.data.zero_()
+
+
+# ----------------------------------------------------------------------------------------------- FAPM / ups
+class SqueezeExcitation(_NoForward):
+    def __init__(self, channels: int, reduction: int = 16):
+        super().__init__()
+        reduced = max(1, channels // reduction)
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Conv2d(channels, reduced, 1, bias=True), nn.ReLU(inplace=True),
+                                nn.Conv2d(reduced, channels, 1, bias=True), nn.Sigmoid())
+
+
+class DepthwiseSeparableConv(_NoForward):
+    def __init__(self, in_ch, out_ch, kernel_size=3, stride=1, padding=1, bias=False, norm=nn.BatchNorm2d, act=nn.ReLU,
+                 norm_kwargs=None, act_kwargs=None):
+        super().__init__()
+        norm_kwargs = {} if norm_kwargs is None else norm_kwargs
+        act_kwargs = {"inplace": True} if act_kwargs is None else act_kwargs
+        self.depthwise = nn.Conv2d(in_ch, in_ch, kernel_size, stride, padding, groups=in_ch, bias=bias)
+        self.pointwise = nn.Conv2d(in_ch, out_ch, 1, bias=bias)
+        self.bn = norm(out_ch, **norm_kwargs) if norm is not None else nn.Identity()
+        self.act = act(**act_kwargs) if act is not None else nn.Identity()
+
+
+class LearnableUpsampleBlock(_NoForward):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.up2 = nn.ConvTranspose2d(channels, channels, kernel_size=2, stride=2, bias=True)
+
+
+class FAPM(_NoForward):
+    def __init__(self, in_ch: int, rank: int, out_ch_list: List[int], norm=nn.BatchNorm2d, act=nn.ReLU,
+                 norm_kwargs: dict = None, act_kwargs: dict = None, bias: bool = False):
+        super().__init__()
+        norm_kwargs = {} if norm_kwargs is None else norm_kwargs
+        act_kwargs = {"inplace": True} if act_kwargs is None else act_kwargs
+        self.shared_basis = nn.Conv2d(in_ch, rank, 1, bias=bias)
+        self.specific_bases = nn.ModuleList([nn.Conv2d(in_ch, rank, 1, bias=bias) for _ in out_ch_list])
+        self.film_generators = nn.ModuleList([nn.Conv2d(rank, rank * 2, 1, bias=bias) for _ in out_ch_list])
+        self.refinement_blocks = nn.ModuleList()
+        self.shortcut_projections = nn.ModuleList()
+        for oc in out_ch_list:
+            self.refinement_blocks.append(nn.Sequential(
+                nn.Conv2d(rank, oc, 1, bias=bias),
+                norm(oc, **norm_kwargs) if norm is not None else nn.Identity(),
+                act(**act_kwargs) if act is not None else nn.Identity(),
+                DepthwiseSeparableConv(oc, oc, 3, 1, 1, bias=bias, norm=norm, act=act, norm_kwargs=norm_kwargs,
+                                       act_kwargs=act_kwargs),
+                nn.Conv2d(oc, oc, 1, bias=bias),
+                SqueezeExcitation(oc)))
+            self.shortcut_projections.append(nn.Conv2d(rank, oc, 1, bias=bias) if rank != oc else nn.Identity())
+
+
+class DINOv3EncoderAdapter(_NoForward):
+    def __init__(self, dinov3_adapter: DINOv3_Adapter, target_channels: List[int], adapter_type: str = "default",
+                 rank: int = 256, conv_op=nn.Conv2d, norm_op=nn.BatchNorm2d, norm_op_kwargs: dict = None,
+                 dropout_op=None, dropout_op_kwargs: dict = None, nonlin=nn.ReLU, nonlin_kwargs: dict = None,
+                 conv_bias: bool = False):
+        super().__init__()
+        self.dinov3_adapter = dinov3_adapter
+        self.target_channels = target_channels
+        self.conv_op = conv_op
+        self.norm_op = norm_op if norm_op is not None else nn.BatchNorm2d
+        self.norm_op_kwargs = norm_op_kwargs if norm_op_kwargs is not None else {}
+        self.nonlin = nonlin if nonlin is not None else nn.ReLU
+        self.nonlin_kwargs = nonlin_kwargs if nonlin_kwargs is not None else {"inplace": True}
+        self.conv_bias = conv_bias
+        self.dropout_op, self.dropout_op_kwargs = dropout_op, dropout_op_kwargs
+        in_ch = self.dinov3_adapter.backbone.embed_dim
+        self.fapm = FAPM(in_ch, rank, target_channels, norm=self.norm_op, act=self.nonlin, norm_kwargs=self.norm_op_kwargs,
+                         act_kwargs=self.nonlin_kwargs, bias=conv_bias)
+        self.ups = nn.ModuleList([LearnableUpsampleBlock(oc) for oc in target_channels])
+        self.output_channels = target_channels
+        self.strides = [[2, 2]] * len(target_channels)
+        self.kernel_sizes = [[3, 3]] * len(target_channels)
+
+    def compute_conv_feature_map_size(self, input_size):
+        return 0
+
+
+# ----------------------------------------------------------------------------------------------- decoder
+class ConvDropoutNormReLU(_NoForward):
+    """dynamic_network_architectures 0.4.x (third party): conv -> [dropout] -> norm -> nonlin, registered twice."""
+
+    def __init__(self, conv_op, input_channels, output_channels, kernel_size, stride, conv_bias=False, norm_op=None,
+                 norm_op_kwargs=None, dropout_op=None, dropout_op_kwargs=None, nonlin=None, nonlin_kwargs=None,
+                 nonlin_first=False):
+        super().__init__()
+        ks = list(kernel_size) if isinstance(kernel_size, (tuple, list)) else [kernel_size] * 2
+        st = list(stride) if isinstance(stride, (tuple, list)) else [stride] * 2
+        ops = []
+        self.conv = conv_op(input_channels, output_channels, ks, st, padding=[(i - 1) // 2 for i in ks], dilation=1,
+                            bias=conv_bias)
+        ops.append(self.conv)
+        if dropout_op is not None:
+            self.dropout = dropout_op(**(dropout_op_kwargs or {}))
+            ops.append(self.dropout)
+        if norm_op is not None:
+            self.norm = norm_op(output_channels, **(norm_op_kwargs or {}))
+            ops.append(self.norm)
+        if nonlin is not None:
+            self.nonlin = nonlin(**(nonlin_kwargs or {}))
+            ops.append(self.nonlin)
+        if nonlin_first and (norm_op is not None and nonlin is not None):
+            ops[-1], ops[-2] = ops[-2], ops[-1]
+        self.all_modules = nn.Sequential(*ops)
+
+
+class StackedConvBlocks(_NoForward):
+    def __init__(self, num_convs, conv_op, input_channels, output_channels, kernel_size, initial_stride, conv_bias=False,
+                 norm_op=None, norm_op_kwargs=None, dropout_op=None, dropout_op_kwargs=None, nonlin=None,
+                 nonlin_kwargs=None, nonlin_first=False):
+        super().__init__()
+        if not isinstance(output_channels, (tuple, list)):
+            output_channels = [output_channels] * num_convs
+        rest = (conv_bias, norm_op, norm_op_kwargs, dropout_op, dropout_op_kwargs, nonlin, nonlin_kwargs, nonlin_first)
+        self.convs = nn.Sequential(
+            ConvDropoutNormReLU(conv_op, input_channels, output_channels[0], kernel_size, initial_stride, *rest),
+            *[ConvDropoutNormReLU(conv_op, output_channels[i - 1], output_channels[i], kernel_size, 1, *rest)
+              for i in range(1, num_convs)])
+        self.output_channels = output_channels[-1]
+
+
+class UNetDecoder(_NoForward):
+    def __init__(self, encoder, num_classes: int, n_conv_per_stage, deep_supervision, nonlin_first: bool = False,
+                 norm_op=None, norm_op_kwargs: dict = None, dropout_op=None, dropout_op_kwargs: dict = None, nonlin=None,
+                 nonlin_kwargs: dict = None, conv_bias: bool = None):
+        super().__init__()
+        self.deep_supervision = deep_supervision
+        self.encoder = encoder
+        self.num_classes = num_classes
+        n_enc = len(encoder.output_channels)
+        if isinstance(n_conv_per_stage, int):
+            n_conv_per_stage = [n_conv_per_stage] * (n_enc - 1)
+        assert len(n_conv_per_stage) == n_enc - 1, "n_conv_per_stage must have as many entries as we have " \
+                                                   "resolution stages - 1 (n_stages in encoder - 1), here: %d" % n_enc
+        if encoder.conv_op is not nn.Conv2d:
+            raise NotImplementedError("the B200 forward path is 2D (conv_op=Conv2d), as forced by main_dinov3")
+        conv_bias = encoder.conv_bias if conv_bias is None else conv_bias
+        norm_op = encoder.norm_op if norm_op is None else norm_op
+        norm_op_kwargs = encoder.norm_op_kwargs if norm_op_kwargs is None else norm_op_kwargs
+        dropout_op = encoder.dropout_op if dropout_op is None else dropout_op
+        dropout_op_kwargs = encoder.dropout_op_kwargs if dropout_op_kwargs is None else dropout_op_kwargs
+        nonlin = encoder.nonlin if nonlin is None else nonlin
+        nonlin_kwargs = encoder.nonlin_kwargs if nonlin_kwargs is None else nonlin_kwargs
+        stages, transpconvs, seg_layers = [], [], []
+        for s in range(1, n_enc):
+            below, skip = encoder.output_channels[-s], encoder.output_channels[-(s + 1)]
+            st = encoder.strides[-s]
+            transpconvs.append(nn.ConvTranspose2d(below, skip, st, st, bias=conv_bias))
+            stages.append(StackedConvBlocks(n_conv_per_stage[s - 1], encoder.conv_op, 2 * skip, skip,
+                                            encoder.kernel_sizes[-(s + 1)], 1, conv_bias, norm_op, norm_op_kwargs,
+                                            dropout_op, dropout_op_kwargs, nonlin, nonlin_kwargs, nonlin_first))
+            seg_layers.append(encoder.conv_op(skip, num_classes, 1, 1, 0, bias=True))
+        self.stages = nn.ModuleList(stages)
+        self.transpconvs = nn.ModuleList(transpconvs)
+        self.seg_layers = nn.ModuleList(seg_layers)
+
+    def compute_conv_feature_map_size(self, input_size):
+        return 0
+
+
+# ----------------------------------------------------------------------------------------------- DinoUNet
+def load_dinov3_model(model_name: str, pretrained_path: str = None) -> DinoVisionTransformer:
+    """dinounet_training.py:51-75.  The reference downloads weights when the path is missing; this box has no network,
+    so that branch raises unless DINOUNET_B200_ALLOW_RANDOM_BACKBONE=1 (random-init backbone: benchmarks / tests)."""
+    if model_name not in cfg.VARIANTS:
+        raise ValueError(f"Unsupported model: {model_name}. Supported models: {list(cfg.VARIANTS)}")
+    model = make_backbone(model_name)
+    if pretrained_path and os.path.exists(pretrained_path):
+        state_dict = torch.load(pretrained_path, map_location="cpu")
+        model.load_state_dict(state_dict, strict=True)
+    elif os.environ.get("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "0") != "1":
+        raise FileNotFoundError(
+            f"DINOv3 weights not found at {pretrained_path!r} and there is no network to download them; "
+            "set DINOUNET_B200_ALLOW_RANDOM_BACKBONE=1 to build a random-init backbone")
+    return model
+
+
+class DinoUNet(nn.Module):
+    """U-Net with DINOv3_Adapter as encoder (dinounet_training.py:632-829), forward on hand-written sm_100a kernels."""
+
+    #: 16-bit types of the kernel path: ViT GEMMs / everything else (the reference's inner bf16 / outer fp16 autocast)
+    vit_dtype = "bf16"
+    rest_dtype = "fp16"
+
+    def __init__(self, network_config: dict = None, input_channels: int = None, num_classes: int = None,
+                 dinov3_pretrained_path: str = "dinounet/checkpoints/dinov3_vits16_pretrain_lvd1689m-08c60483.pth",
+                 dinov3_model_name: str = "dinov3_vits16", adapter_type: str = "default", n_stages: int = None,
+                 features_per_stage=None, conv_op=None, kernel_sizes=None, strides=None, n_conv_per_stage=None,
+                 n_conv_per_stage_decoder=None, conv_bias: bool = False, norm_op=None, norm_op_kwargs: dict = None,
+                 dropout_op=None, dropout_op_kwargs: dict = None, nonlin=None, nonlin_kwargs: dict = None,
+                 deep_supervision: bool = False, nonlin_first: bool = False):
+        super().__init__()
+        if network_config is not None:
+            arch = network_config["architecture"]
+            _res = lambda o: pydoc.locate(o) if isinstance(o, str) else o
+            input_channels = input_channels or 3
+            self.adapter_type = adapter_type
+            num_classes = num_classes or 2
+            n_stages = arch["n_stages"]
+            features_per_stage = arch["features_per_stage"]
+            conv_op = _res(arch["conv_op"])
+            kernel_sizes, strides = arch["kernel_sizes"], arch["strides"]
+            n_conv_per_stage = arch["n_conv_per_stage"]
+            n_conv_per_stage_decoder = arch["n_conv_per_stage_decoder"]
+            conv_bias = arch.get("conv_bias", False)
+            norm_op = _res(arch["norm_op"])
+            norm_op_kwargs = arch.get("norm_op_kwargs", {})
+            dropout_op = _res(arch["dropout_op"])
+            dropout_op_kwargs = arch.get("dropout_op_kwargs", {})
+            nonlin = _res(arch["nonlin"])
+            nonlin_kwargs = arch.get("nonlin_kwargs", {})
+            deep_supervision = arch.get("deep_supervision", False)
+            nonlin_first = arch.get("nonlin_first", False)
+        if isinstance(n_conv_per_stage_decoder, int):
+            n_conv_per_stage_decoder = [n_conv_per_stage_decoder] * (n_stages - 1)
+        if n_stages != 4:   # dinounet_training.py:703-711 (silent coercion, kept)
+            print(f"Warning: DINOv3_Adapter outputs 4 scales, but n_stages={n_stages}. Adjusting to 4.")
+            n_stages = 4
+            if isinstance(features_per_stage, int):
+                features_per_stage = [features_per_stage * (2 ** i) for i in range(4)]
+            elif len(features_per_stage) != 4:
+                base = features_per_stage[0] if features_per_stage else 32
+                features_per_stage = [base * (2 ** i) for i in range(4)]
+            n_conv_per_stage_decoder = list(n_conv_per_stage_decoder)[:3] if len(n_conv_per_stage_decoder) >= 3 else [2, 2, 2]
+        self.num_classes = num_classes
+        self.dinov3_model_name = dinov3_model_name
+        self.encoder = self._create_dinov3_encoder(dinov3_pretrained_path, dinov3_model_name, list(features_per_stage),
+                                                   conv_op, norm_op, norm_op_kwargs, dropout_op, dropout_op_kwargs,
+                                                   nonlin, nonlin_kwargs, conv_bias, adapter_type)
+        self.decoder = UNetDecoder(self.encoder, num_classes, n_conv_per_stage_decoder, deep_supervision,
+                                   nonlin_first=nonlin_first)
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _create_dinov3_encoder(self, pretrained_path, model_name, features_per_stage, conv_op, norm_op, norm_op_kwargs,
+                               dropout_op, dropout_op_kwargs, nonlin, nonlin_kwargs, conv_bias, adapter_type="default"):
+        if model_name not in cfg.VARIANTS:   # same failure as dinounet_training.py:737-738
+            raise ValueError(f"Unknown model: {model_name}")
+        v = cfg.VARIANTS[model_name]
+        backbone = load_dinov3_model(model_name, pretrained_path)
+        adapter = DINOv3_Adapter(backbone=backbone, interaction_indexes=list(v.interaction_indexes), pretrain_size=512,
+                                 conv_inplane=cfg.CONV_INPLANE, n_points=cfg.DEFORM_POINTS,
+                                 deform_num_heads=cfg.DEFORM_HEADS, drop_path_rate=0.3, init_values=0.0, with_cffn=True,
+                                 cffn_ratio=cfg.CFFN_RATIO, deform_ratio=cfg.DEFORM_RATIO, add_vit_feature=True,
+                                 use_extra_extractor=True, with_cp=True)
+        return DINOv3EncoderAdapter(dinov3_adapter=adapter, target_channels=features_per_stage, conv_op=conv_op,
+                                    norm_op=norm_op, norm_op_kwargs=norm_op_kwargs, dropout_op=dropout_op,
+                                    dropout_op_kwargs=dropout_op_kwargs, nonlin=nonlin, nonlin_kwargs=nonlin_kwargs,
+                                    conv_bias=conv_bias)
+
+    # ---- engine management -------------------------------------------------------------------------------------
+    def _invalidate(self):
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def repack(self):
+        """Call after mutating parameters in place (e.g. an optimizer step) to refresh the packed kernel weights."""
+        self._engine = None
+
+    def _get_engine(self, device):
+        from ..engine import ForwardEngine
+        if self._engine is None or self._engine.device != device:
+            sd = {k: t for k, t in self.state_dict().items() if not k.startswith("decoder.encoder.")}
+            self._engine = ForwardEngine(self.dinov3_model_name, sd, self.num_classes, device, self.vit_dtype,
+                                         self.rest_dtype, tuple(self.encoder.target_channels))
+        return self._engine
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.decoder.deep_supervision:
+            raise NotImplementedError("deep supervision outputs are not produced by the B200 forward path "
+                                      "(DinoUNetTrainer derives from nnUNetTrainerNoDeepSupervision)")
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError("dinounet_b200 implements the forward (inference / validation) path; call "
+                                      "under torch.no_grad() / .eval(). Backward kernels are a later-round item.")
+        B, Cc, H, W = x.shape
+        if Cc == 1:                       # dinounet_training.py:491-497
+            x = x.repeat(1, 3, 1, 1)
+        elif Cc != 3:
+            x = x.repeat(1, 3 // Cc + (1 if 3 % Cc != 0 else 0), 1, 1)[:, :3] if Cc < 3 else x[:, :3]
+        x = x.float().contiguous()
+        logits, _ = self._get_engine(x.device).forward(x)
+        return logits.clone()
+
+    @torch.no_grad()
+    def predict_labels(self, x: torch.Tensor) -> torch.Tensor:
+        """argmax mask (uint8) straight from the fused seg-head kernel (nnUNetTrainer.py:977)."""
+        x = x.float().contiguous()
+        _, labels = self._get_engine(x.device).forward(x)
+        return labels.clone()
+
+    def compute_conv_feature_map_size(self, input_size):
+        assert len(input_size) == 2, "just give the image size without color/feature channels or batch channel. " \
+                                     "Do not give input_size=(b, c, x, y(, z)). Give input_size=(x, y(, z))!"
+        return self.encoder.compute_conv_feature_map_size(input_size) + self.decoder.compute_conv_feature_map_size(input_size)
+
+    @staticmethod
+    def initialize(module):
+        pass  # InitWeights_He is never applied on this path in the reference
+
+    @classmethod
+    def from_config(cls, network_config: dict, input_channels: int, num_classes: int,
+                    dinov3_pretrained_path: str = "dinov3_vits16_pretrain_lvd1689m-08c60483.pth",
+                    dinov3_model_name: str = "dinov3_vits16"):
+        return cls(network_config=network_config, input_channels=input_channels, num_classes=num_classes,
+                   dinov3_pretrained_path=dinov3_pretrained_path, dinov3_model_name=dinov3_model_name)

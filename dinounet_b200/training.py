@@ -1,0 +1,83 @@
+"""Trainer plugin hook (the primary drop-in boundary).
+
+Mirrors `DinoUNetTrainer` and its four subclasses (dinounet_training.py:833-930): `set_network_config` stores the
+planner's architecture dict on the class, and the static `build_network_architecture` hook
+(nnUNetTrainer.py:265-298) returns the B200-native `DinoUNet`.  When the reference's nnU-Net package is importable the
+trainers derive from its `nnUNetTrainerNoDeepSupervision`, so `api.training(trainer_class=DinoUNetTrainer_l, ...)`
+works unchanged; otherwise they derive from `object` (the hook itself is a staticmethod and needs no base class).
+"""
+from typing import List, Tuple, Union
+
+from torch import nn
+
+from . import config as cfg
+from .network_architecture import DinoUNet
+
+try:  # the reference package (needs batchgenerators etc.); optional
+    from dinounet.training.nnUNetTrainer.nnUNetTrainerNoDeepSupervision import nnUNetTrainerNoDeepSupervision as _Base
+except Exception:  # pragma: no cover - reference stack absent
+    _Base = object
+
+
+class DinoUNetTrainer(_Base):
+    _network_config = None
+    _dinov3_pretrained_path = None
+    _dinov3_model_name = None
+
+    @classmethod
+    def set_network_config(cls, network_config, dinov3_pretrained_path=None, dinov3_model_name=None,
+                           adapter_type="default"):
+        cls._network_config = network_config
+        if dinov3_pretrained_path is not None:
+            cls._dinov3_pretrained_path = dinov3_pretrained_path
+        if dinov3_model_name is not None:
+            cls._dinov3_model_name = dinov3_model_name
+        # the static hook reads the base class (dinounet_training.py:851-855)
+        DinoUNetTrainer._network_config = cls._network_config
+        DinoUNetTrainer._dinov3_model_name = cls._dinov3_model_name
+        DinoUNetTrainer._dinov3_pretrained_path = cls._dinov3_pretrained_path
+
+    @staticmethod
+    def build_network_architecture(architecture_class_name: str, arch_init_kwargs: dict,
+                                   arch_init_kwargs_req_import: Union[List[str], Tuple[str, ...]],
+                                   num_input_channels: int, num_output_channels: int,
+                                   enable_deep_supervision: bool = True) -> nn.Module:
+        if DinoUNetTrainer._network_config is None:
+            raise RuntimeError("call set_network_config(network_config) before build_network_architecture")
+        config = DinoUNetTrainer._network_config.copy()
+        config["architecture"] = config["architecture"].copy()
+        config["architecture"]["deep_supervision"] = enable_deep_supervision
+        return DinoUNet.from_config(network_config=config, input_channels=num_input_channels,
+                                    num_classes=num_output_channels,
+                                    dinov3_pretrained_path=DinoUNetTrainer._dinov3_pretrained_path,
+                                    dinov3_model_name=DinoUNetTrainer._dinov3_model_name)
+
+
+class DinoUNetTrainer_s(DinoUNetTrainer):
+    _dinov3_model_name = "dinounet_s"
+    _dinov3_pretrained_path = cfg.CHECKPOINTS["dinounet_s"]
+
+
+class DinoUNetTrainer_b(DinoUNetTrainer):
+    _dinov3_model_name = "dinounet_b"
+    _dinov3_pretrained_path = cfg.CHECKPOINTS["dinounet_b"]
+
+
+class DinoUNetTrainer_l(DinoUNetTrainer):
+    _dinov3_model_name = "dinounet_l"
+    _dinov3_pretrained_path = cfg.CHECKPOINTS["dinounet_l"]
+
+
+class DinoUNetTrainer_7b(DinoUNetTrainer):
+    _dinov3_model_name = "dinounet_7b"
+    _dinov3_pretrained_path = cfg.CHECKPOINTS["dinounet_7b"]
+
+
+DINOV3_TRAINERS = {"dinounet_s": DinoUNetTrainer_s, "dinounet_b": DinoUNetTrainer_b, "dinounet_l": DinoUNetTrainer_l,
+                   "dinounet_7b": DinoUNetTrainer_7b}
+
+
+def get_dinov3_trainer(model_name: str):
+    if model_name not in DINOV3_TRAINERS:
+        raise ValueError(f"Unsupported model: {model_name}. Supported models: {list(DINOV3_TRAINERS)}")
+    return DINOV3_TRAINERS[model_name]

@@ -1,0 +1,198 @@
+/* dinounet_b200 — C-ABI of the B200-native Dino U-Net forward path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every function launches hand-written sm_100a kernels on the
+ * given CUDA stream, never allocates, never synchronises, and returns 0 on success or a negative error code
+ * (message via b2u_last_error()).  All device tensors are channels-last ("token-major"): [rows, C] with C contiguous.
+ *
+ * Reference interface each entry replaces (paths relative to the reference repo root):
+ *   - the reference's ONLY native FFI is the pybind11 module `MultiScaleDeformableAttention`
+ *     (dinounet/dinov3/eval/segmentation/models/utils/ops/src/vision.cpp:18-21, ms_deform_attn.h:26-67);
+ *     b2u_msda_forward is its drop-in (same tensor meaning, fused softmax/location prologue available).
+ *   - every other entry replaces an ATen/cuDNN/cuBLAS library call that the reference's Python forward makes
+ *     (SURVEY.md section 2.3); the call site is cited per function.
+ */
+#ifndef DINOUNET_B200_H_
+#define DINOUNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b2u_stream_t; /* cudaStream_t */
+
+enum { B2U_F16 = 0, B2U_BF16 = 1 };
+enum { B2U_ACT_NONE = 0, B2U_ACT_GELU = 1, B2U_ACT_RELU = 2, B2U_ACT_LRELU = 3 };
+enum { B2U_CONV_NONE = 0, B2U_CONV3X3_S1 = 1, B2U_CONV3X3_S2 = 2 };
+
+/* Epilogue applied to each fp32 accumulator element acc[m, n], in this order:
+ *   v = acc + bias[n]; if (round16) v = round_to_dtype(v); v = act1(v); v = v * scale[n] + shift[n]; v = act2(v);
+ *   v += residual[orow, ocol] (fp32) ; v += add16[orow, ocol] (16-bit) ; out[orow, ocol] = v
+ * (orow, ocol) = output addressing: identity, batch row-remap, or 2x2 pixel-shuffle (ConvTranspose2d k2 s2). */
+typedef struct b2u_epilogue {
+  void* out;            /* 16-bit (dtype) or fp32 */
+  int32_t out_fp32;     /* 1: out is float */
+  int64_t ldc;          /* output row stride, elements */
+  int32_t col_off;      /* output column offset (concat buffers) */
+  int32_t rows_in;      /* row remap: orow = (m / rows_in) * rows_out + row_off + m % rows_in ; 0 = identity */
+  int32_t rows_out;
+  int32_t row_off;
+  int32_t ps_cout;      /* >0: pixel-shuffle store, n = q*ps_cout + co, q = 2*a + b, input pixel grid ps_h x ps_w */
+  int32_t ps_h;
+  int32_t ps_w;
+  const float* bias;    /* [N] or NULL */
+  const float* scale;   /* [N] or NULL */
+  const float* shift;   /* [N] or NULL */
+  int32_t act1;
+  int32_t act2;
+  int32_t round16;
+  const float* residual; /* fp32 [*, ldres], may alias out */
+  int64_t ldres;
+  const void* add16;     /* 16-bit [*, ldadd] */
+  int64_t ldadd;
+} b2u_epilogue;
+
+/* tcgen05 tensor-core GEMM / implicit-GEMM 3x3 convolution:  acc[M, N] = A[M, K] * Wp[N, K]^T.
+ * conv == NONE : A is [M, K] row-major (row stride lda).  Replaces F.linear / 1x1 Conv2d / ConvTranspose2d(k2,s2)
+ *                (attention.py:88-90, ffn_layers.py:43-49, ms_deform_attn.py:183-215, dinov3_adapter.py:274-277,467,
+ *                dinounet_training.py:419-441,255-264,613).
+ * conv != NONE : A is an NHWC image [B, Hin, Win, C]; the kernel walks the 9 taps with TMA halo tiles (zero fill),
+ *                no im2col buffer.  Wp is [N, 9*Cpad] with k = tap*Cpad + c, Cpad = ceil(C/64)*64.  Output pixel
+ *                grid is Hin/stride x Win/stride.  Replaces Conv2d(3x3,pad 1) (dinov3_adapter.py:239-273,
+ *                dynamic_network_architectures ConvDropoutNormReLU). */
+typedef struct b2u_gemm_params {
+  int32_t M, N, K;
+  const void* A;
+  int64_t lda;
+  const void* Wp;       /* packed weights [N, ldw], 16-bit, zero padded */
+  int64_t ldw;
+  int32_t dtype;        /* B2U_F16 / B2U_BF16 for A, Wp and 16-bit outputs */
+  int32_t conv;
+  int32_t B, Hin, Win, C;
+  b2u_epilogue epi;
+} b2u_gemm_params;
+
+int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream);
+
+/* QKV projection with masked bias + RoPE + head split fused in the epilogue (attention.py:30-40,66-92):
+ *   qkv = A[M=B*ntok, D] * Wp[3D, D]^T + bias (already multiplied by bias_mask); rounded to dtype; q,k rows with
+ *   token index >= prefix rotated with sin/cos[(tok - prefix), 64] (fp32); written as q,k,v [B, heads, ntok, 64]. */
+typedef struct b2u_qkv_params {
+  int32_t B, ntok, D, heads, prefix;
+  const void* A;
+  int64_t lda;
+  const void* Wp;
+  int64_t ldw;
+  const float* bias;    /* [3D] or NULL */
+  const float* rope_sin;
+  const float* rope_cos;
+  void* q;
+  void* k;
+  void* v;
+  int32_t dtype;
+} b2u_qkv_params;
+
+int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream);
+
+/* Non-causal softmax attention, head_dim 64 (attention.py:106-118 -> F.scaled_dot_product_attention):
+ *   q,k,v [B, heads, ntok, 64] -> out [B, ntok, heads*64]. */
+int b2u_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t heads, int32_t ntok,
+                  float scale, int32_t dtype, b2u_stream_t stream);
+
+/* LayerNorm over the last dim (block.py:193-194, vision_transformer.py:300, dinov3_adapter.py:142-148):
+ *   in fp32 [rows_sel, D] -> out (16-bit or fp32).  Row selection: for output row r,
+ *   input row = (r / rows_out) * rows_in + row_off + r % rows_out  (rows_out == 0: identity). */
+int b2u_layernorm(const float* in, void* out, const float* gamma, const float* beta, int32_t rows, int32_t D,
+                  float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32, int32_t dtype,
+                  b2u_stream_t stream);
+
+/* fp32 -> 16-bit cast of a [rows, D] matrix with the same row selection as b2u_layernorm. */
+int b2u_cast_rows(const float* in, void* out, int32_t rows, int32_t D, int32_t rows_in, int32_t rows_out,
+                  int32_t row_off, int32_t dtype, b2u_stream_t stream);
+
+/* Patch-embed operand: x fp32 NCHW [B,3,S,S] -> [B*(S/16)^2, 768] 16-bit with k = c*256 + ky*16 + kx
+ * (non-overlapping patches: a permutation + cast, no duplication)  (patch_embed.py:64-76). */
+int b2u_patchify(const float* x, void* out, int32_t B, int32_t S, int32_t dtype, b2u_stream_t stream);
+
+/* cls/storage prefix rows of the token stream: X[b, t, :] = prefix[t, :] for t < n_prefix (vision_transformer.py:207-214). */
+int b2u_write_prefix(float* X, const float* prefix, int32_t B, int32_t ntok, int32_t n_prefix, int32_t D,
+                     b2u_stream_t stream);
+
+/* SPM stem conv0: Conv2d(3,64,3,s2,p1,no bias)+BN(eval)+ReLU reading fp32 NCHW, writing NHWC 16-bit
+ * (dinov3_adapter.py:241-243).  w is [64,3,3,3] fp32; scale/shift = folded BN. */
+int b2u_stem_conv0(const float* x, const float* w, const float* scale, const float* shift, void* out, int32_t B,
+                   int32_t S, int32_t dtype, b2u_stream_t stream);
+
+/* MaxPool2d(3, s2, p1) on NHWC 16-bit (dinov3_adapter.py:250). */
+int b2u_maxpool3x3s2(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t dtype,
+                     b2u_stream_t stream);
+
+/* Depthwise 3x3 (pad 1) + bias (+GELU) on NHWC 16-bit.  `planes` > 1 processes the ConvFFN token stream
+ * [B, 21n, C] as three planes (2h x 2w, h x w, h/2 x w/2) with shared weights (dinov3_adapter.py:99-109);
+ * planes == 1 is a plain [B,H,W,C] image (dinounet_training.py:241-243).  w is tap-major [9, C] fp32. */
+int b2u_dwconv3x3(const void* in, void* out, const float* w, const float* bias, int32_t B, int32_t H, int32_t W,
+                  int32_t C, int32_t planes, int32_t act, int32_t dtype, b2u_stream_t stream);
+
+/* MultiScaleDeformableAttention forward, single level, n_heads x n_points, fused prologue
+ * (ms_deform_attn.py:185-213 + ms_deform_im2col_cuda.cuh:242-304):
+ *   value  [B, Hv*Wv, heads, dh] 16-bit;  offaw fp32 [B*Lq, heads*points*3] = (offsets(x,y) | attention logits);
+ *   reference point of query q = cell centre of q in the pyramid of (2Hv x 2Wv, Hv x Wv, Hv/2 x Wv/2) grids;
+ *   loc = ref + off / (Wv, Hv); weights = softmax over points; bilinear, zero padding, align_corners=False.
+ *   out [B*Lq, heads*dh] 16-bit. */
+int b2u_msda_forward(const void* value, const float* offaw, void* out, int32_t B, int32_t Hv, int32_t Wv,
+                     int32_t heads, int32_t dh, int32_t points, int32_t dtype, b2u_stream_t stream);
+
+/* Drop-in for the reference pybind op `ms_deform_attn_forward` (ops/src/vision.cpp:18, ms_deform_attn.h:26-45):
+ * value fp32 [B, S, heads, dh]; spatial_shapes int64 [levels, 2] (H, W) and level_start_index int64 [levels] on the
+ * DEVICE (as in the reference); sampling locations fp32 [B, Lq, heads, levels, points, 2]; attention weights fp32
+ * [B, Lq, heads, levels, points]; out fp32 [B, Lq, heads*dh].  (im2col_step is a launch-chunking detail of the
+ * reference kernel and has no equivalent here.) */
+int b2u_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                         const float* loc, const float* attw, float* out, int32_t B, int32_t S, int32_t Lq,
+                         int32_t heads, int32_t dh, int32_t levels, int32_t points, b2u_stream_t stream);
+
+/* Adapter tail (dinov3_adapter.py:467-482): out[b,y,x,:] = BN_eval( base[b,y,x,:] + bilinear(tap[b,:,:,:] -> HxW) ).
+ * base: fp32 token stream slice or 16-bit image (base_fp32), tap fp32 [B, Ht*Wt, D] (token-major), align_corners=False. */
+int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_batch_stride, const float* tap, void* out,
+                  const float* scale, const float* shift, int32_t B, int32_t H, int32_t W, int32_t Ht, int32_t Wt,
+                  int32_t D, int32_t dtype, b2u_stream_t stream);
+
+/* InstanceNorm statistics: sums[b, c, 0..1] += (sum x, sum x^2) over the rows of image b.  x 16-bit [B*rows, C]
+ * (dinounet_training.py:400-401; ConvDropoutNormReLU norm). sums must be zeroed by the caller. */
+int b2u_in_stats(const void* x, int64_t ldx, float* sums, int32_t B, int32_t rows, int32_t C, int32_t dtype,
+                 b2u_stream_t stream);
+
+/* InstanceNorm apply + LeakyReLU(0.01): y = lrelu((x - mean) * rstd * gamma + beta), biased variance, eps. */
+int b2u_in_apply(const void* x, int64_t ldx, void* y, int64_t ldy, const float* sums, const float* gamma,
+                 const float* beta, int32_t B, int32_t rows, int32_t C, float eps, int32_t dtype, b2u_stream_t stream);
+
+/* FiLM: z[r, j] = gb[r, j] * zz[r, zoff + j] + gb[r, R + j]  (dinounet_training.py:427-429). */
+int b2u_film(const void* gb, const void* zz, int64_t ldzz, int32_t zoff, void* z, int32_t rows, int32_t R,
+             int32_t dtype, b2u_stream_t stream);
+
+/* Squeeze-excitation gate + shortcut (dinounet_training.py:222-225,437-439):
+ *   pooled[b,c] = mean_rows t ; g = sigmoid(W2 relu(W1 pooled + b1) + b2) ; out = t * g + sc. */
+int b2u_se_gate(const float* sums, const float* w1, const float* b1, const float* w2, const float* b2, float* gate,
+                int32_t B, int32_t C, int32_t Cr, int32_t rows, b2u_stream_t stream);
+int b2u_se_apply(const void* t, const void* sc, int64_t ldsc, const float* gate, void* out, int32_t B, int32_t rows,
+                 int32_t C, int32_t dtype, b2u_stream_t stream);
+
+/* Final InstanceNorm + LeakyReLU + 1x1 segmentation head + argmax (dinounet_training.py:597,619; nnUNetTrainer.py:977):
+ *   x 16-bit [B*rows, C]; logits NCHW fp32 [B, ncls, rows]; labels uint8 [B, rows] (may be NULL). */
+int b2u_seg_head(const void* x, const float* sums, const float* gamma, const float* beta, float eps, const float* w,
+                 const float* b, float* logits, uint8_t* labels, int32_t B, int32_t rows, int32_t C, int32_t ncls,
+                 int32_t dtype, b2u_stream_t stream);
+
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream (statistics accumulators must be zeroed every forward). */
+int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream);
+
+const char* b2u_last_error(void);
+int b2u_version(void);
+/* Number of kernel launches issued through this library since load (bench.py's gpu_launches evidence). */
+int64_t b2u_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINOUNET_B200_H_ */

@@ -1,0 +1,110 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dinounet_b200.h declares; the host-side mirror has
+the reference's state-dict keys and plugin hook; and the product fails loudly (no CPU fallback) without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+import dinounet_b200
+from dinounet_b200 import config, lib
+from oracle import dinounet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__
+    __graft_entry__.build()
+    return lib.load()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "dinounet_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b2u_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(built, name), f"{name} declared in the header but not exported"
+    assert declared == set(lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert built.b2u_version() >= 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors vs the real C layout: compile a probe against the header with gcc and compare every offset."""
+    import ctypes as C
+    import subprocess
+    structs = {"b2u_epilogue": lib.Epilogue, "b2u_gemm_params": lib.GemmParams, "b2u_qkv_params": lib.QkvParams}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dinounet_b200.h"\nint main(){' + "".join(lines) + "return 0;}")
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def _build(model):
+    os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
+    return dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, model)
+
+
+@pytest.mark.parametrize("model", ["dinounet_s", "dinounet_b"])
+def test_state_dict_keys_match_reference_spec(model):
+    net = _build(model)
+    sd = net.state_dict()
+    ref = O.make_state_dict(model, 2, 0)
+    assert set(sd) == set(ref)
+    assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in sd)
+    net.load_state_dict(ref, strict=True)
+    assert net.decoder.deep_supervision is False
+    assert net.encoder.output_channels == [32, 64, 128, 256] and net.encoder.strides == [[2, 2]] * 4
+    assert not any(p.requires_grad for p in net.encoder.dinov3_adapter.backbone.parameters())
+
+
+def test_unknown_model_raises_like_reference():
+    os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
+    with pytest.raises(ValueError):   # dinounet_training.py:737-738 (the default name is not a registry key)
+        dinounet_b200.DinoUNet(network_config={"architecture": dict(config.DEFAULT_ARCHITECTURE)})
+
+
+def test_missing_checkpoint_raises_without_network():
+    os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "0"
+    try:
+        with pytest.raises(FileNotFoundError):
+            dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2,
+                                               "/nonexistent.pth", "dinounet_s")
+    finally:
+        os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
+
+
+def test_trainer_hook_builds_the_native_model():
+    T = dinounet_b200.get_dinov3_trainer("dinounet_s")
+    os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
+    T.set_network_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, dinov3_pretrained_path=None)
+    net = T.build_network_architecture("DinoUNet", {}, [], 3, 2, enable_deep_supervision=False)
+    assert isinstance(net, dinounet_b200.DinoUNet) and net.dinov3_model_name == "dinounet_s"
+    with pytest.raises(ValueError):
+        dinounet_b200.get_dinov3_trainer("dinov3_vits16")
+
+
+def test_no_cpu_fallback(built):
+    net = _build("dinounet_s").eval()
+    with torch.no_grad(), pytest.raises(lib.NativeLibraryError):
+        net(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(NotImplementedError):   # training-mode forward is not silently emulated either
+        net.train()(torch.zeros(1, 3, 64, 64))
+
+
+def test_engine_rejects_unbuilt_variants(built):
+    from dinounet_b200.engine import ForwardEngine
+    with pytest.raises(NotImplementedError):
+        ForwardEngine("dinounet_7b", {}, 2, torch.device("cpu"))

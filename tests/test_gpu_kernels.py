@@ -1,0 +1,321 @@
+"""-m gpu: every hand-written kernel against a plain PyTorch fp32 reference of the same op, through the C-ABI.
+Tolerances are those of the 16-bit storage type (bf16 eps 2^-8, fp16 eps 2^-11) on O(1) data, stated per test."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dinounet_b200 import lib as L
+from oracle import dinounet_oracle as O
+from tests.gpu_helpers import TD, P, gemm, rel_err, stream
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, dt=torch.float32, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dt)
+
+
+@pytest.mark.parametrize("dtype", [L.BF16, L.F16])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1029, 384, 384), (300, 192, 96), (4096, 32, 32), (777, 64, 256),
+                                   (2058, 1536, 384)])
+def test_gemm_plain(dtype, M, N, K):
+    td = TD[dtype]
+    A, W = _rand(M, K, dt=td), _rand(N, K, dt=td, scale=K ** -0.5, seed=1)
+    bias = _rand(N, seed=2)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=td)
+    gemm(A, W, out, dtype, bias=bias)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    tol = 2 ** -7 if dtype == L.BF16 else 2 ** -10
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < tol, rel_err(out, ref)
+
+
+def test_gemm_epilogue_residual_scale_gelu_fp32out():
+    M, N, K = 1029 * 2, 384, 1536
+    dtype, td = L.BF16, torch.bfloat16
+    A, W = _rand(M, K, dt=td), _rand(N, K, dt=td, scale=K ** -0.5, seed=1)
+    bias, gamma = _rand(N, seed=2), _rand(N, seed=3)
+    X = _rand(M, N, seed=4)
+    X0 = X.clone()
+    gemm(A, W, X, dtype, out_fp32=True, bias=bias, scale=gamma, residual=X, ldres=N)
+    torch.cuda.synchronize()
+    lin = (A.float() @ W.float().t() + bias).to(td).float()
+    ref = X0 + lin * gamma
+    assert (X - ref).abs().max().item() < 2e-2 * ref.abs().max().item() / 4
+    # GELU(erf) after rounding, 16-bit store
+    out = torch.empty(M, N, device=DEV, dtype=td)
+    gemm(A, W, out, dtype, bias=bias, act1=L.ACT_GELU)
+    torch.cuda.synchronize()
+    ref = F.gelu(lin).to(td)
+    assert rel_err(out, ref) < 2 ** -6
+
+
+def test_gemm_row_remap_and_coloffset():
+    B, Pn, Nn, D, K = 3, 64, 69, 128, 64
+    dtype, td = L.F16, torch.float16
+    A, W = _rand(B * Pn, K, dt=td), _rand(D, K, dt=td, scale=K ** -0.5, seed=1)
+    X = torch.zeros(B * Nn, 2 * D, device=DEV)
+    gemm(A, W, X, dtype, out_fp32=True, rows=(Pn, Nn, 5), col_off=D, ldc=2 * D)
+    torch.cuda.synchronize()
+    ref = (A.float() @ W.float().t()).to(td).float().view(B, Pn, D)
+    got = X.view(B, Nn, 2 * D)
+    assert rel_err(got[:, 5:, D:], ref) < 1e-3
+    assert got[:, :5].abs().max() == 0 and got[:, :, :D].abs().max() == 0
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 32, 16), (256, 128, 8), (384, 384, 16)])
+def test_gemm_convtranspose_pixelshuffle(cin, cout, hw):
+    B = 2
+    dtype, td = L.F16, torch.float16
+    x = _rand(B, hw, hw, cin, dt=td)
+    w = _rand(cin, cout, 2, 2, scale=cin ** -0.5, seed=1)
+    bias = _rand(cout, seed=2)
+    add = _rand(B, 2 * hw, 2 * hw, cout, dt=td, seed=3)
+    Wp = w.permute(2, 3, 1, 0).reshape(4 * cout, cin).to(td).contiguous()
+    out = torch.empty(B * 4 * hw * hw, cout, device=DEV, dtype=td)
+    gemm(x.view(-1, cin), Wp, out, dtype, ps=(cout, hw, hw), bias=bias.repeat(4).contiguous(), add16=add, ldadd=cout)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.to(td).float(), bias, stride=2)
+    ref = ref.to(td).float() + add.float().permute(0, 3, 1, 2)
+    got = out.view(B, 2 * hw, 2 * hw, cout).permute(0, 3, 1, 2).float()
+    assert rel_err(got, ref) < 2e-3
+
+
+def _pack_conv(w, td):
+    N, Cc = w.shape[:2]
+    cpad = (Cc + 63) // 64 * 64
+    p = torch.zeros(N, 9, cpad, device=w.device)
+    p[:, :, :Cc] = w.permute(0, 2, 3, 1).reshape(N, 9, Cc)
+    return p.reshape(N, 9 * cpad).to(td).contiguous()
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+@pytest.mark.parametrize("cin,cout,hw,B", [(64, 64, 32, 2), (32, 32, 64, 1), (256, 128, 16, 2), (128, 256, 8, 3),
+                                           (64, 32, 256, 1)])
+def test_conv3x3_implicit_gemm(stride, cin, cout, hw, B):
+    dtype, td = L.F16, torch.float16
+    x = _rand(B, hw, hw, cin, dt=td)
+    w = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=1)
+    bias = _rand(cout, seed=2)
+    ho = hw // stride
+    out = torch.full((B * ho * ho, cout), float("nan"), device=DEV, dtype=td)
+    gemm(x.view(-1, cin), _pack_conv(w, td), out, dtype, M=0, K=9 * cin, lda=cin, bias=bias,
+         conv=L.CONV3X3_S2 if stride == 2 else L.CONV3X3_S1, img=(B, hw, hw, cin))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(td).float(), bias, stride=stride, padding=1)
+    got = out.view(B, ho, ho, cout).permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 2e-3, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("dtype", [L.BF16, L.F16])
+def test_qkv_rope_and_attention(dtype):
+    td = TD[dtype]
+    B, h, D, Hh = 2, 16, 384, 6
+    Pn = h * h
+    N = Pn + 5
+    lib = L.load()
+    Y = _rand(B * N, D, dt=td)
+    Wq = _rand(3 * D, D, dt=td, scale=D ** -0.5, seed=1)
+    bias = _rand(3 * D, seed=2, scale=0.1)
+    periods = 100.0 ** (2 * torch.arange(16, dtype=torch.float32) / 32)
+    sin, cos = O.rope_sincos(periods, h, h)
+    sin, cos = sin.to(DEV).contiguous(), cos.to(DEV).contiguous()
+    q, k, v = (torch.full((B, Hh, N, 64), float("nan"), device=DEV, dtype=td) for _ in range(3))
+    p = L.QkvParams()
+    p.B, p.ntok, p.D, p.heads, p.prefix = B, N, D, Hh, 5
+    p.A, p.lda, p.Wp, p.ldw, p.bias = P(Y), D, P(Wq), D, P(bias)
+    p.rope_sin, p.rope_cos, p.q, p.k, p.v, p.dtype = P(sin), P(cos), P(q), P(k), P(v), dtype
+    L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv")
+    torch.cuda.synchronize()
+    qkv = (Y.float() @ Wq.float().t() + bias).to(td)
+    qr, kr, vr = [t.transpose(1, 2) for t in torch.unbind(qkv.reshape(B, N, 3, Hh, 64), 2)]
+    qr, kr = O._rope(qr, sin, cos), O._rope(kr, sin, cos)
+    tol = 2 ** -6 if dtype == L.BF16 else 2 ** -9
+    assert rel_err(q, qr) < tol and rel_err(k, kr) < tol and rel_err(v, vr) < tol
+    out = torch.full((B, N, D), float("nan"), device=DEV, dtype=td)
+    L.check(lib.b2u_attention(P(q), P(k), P(v), P(out), B, Hh, N, 64 ** -0.5, dtype, stream()), "attention")
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, D)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -8), rel_err(out, ref)
+
+
+def test_attention_1029_tokens():
+    dtype, td = L.BF16, torch.bfloat16
+    B, Hh, N = 1, 3, 1029
+    q, k, v = (_rand(B, Hh, N, 64, dt=td, seed=s) for s in range(3))
+    out = torch.empty(B, N, Hh * 64, device=DEV, dtype=td)
+    L.check(L.load().b2u_attention(P(q), P(k), P(v), P(out), B, Hh, N, 0.125, dtype, stream()), "attention")
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, Hh * 64)
+    assert rel_err(out, ref) < 2 ** -6
+
+
+def test_layernorm_and_cast():
+    lib = L.load()
+    B, Nn, Pn, D = 2, 69, 64, 384
+    X = _rand(B * Nn, D) * 3 + 1
+    g, b = _rand(D, seed=1), _rand(D, seed=2)
+    out = torch.empty(B * Pn, D, device=DEV)
+    L.check(lib.b2u_layernorm(P(X), P(out), P(g), P(b), B * Pn, D, 1e-5, Nn, Pn, 5, 1, L.BF16, stream()), "ln")
+    torch.cuda.synchronize()
+    ref = F.layer_norm(X.view(B, Nn, D)[:, 5:], (D,), g, b, 1e-5).reshape(B * Pn, D)
+    assert (out - ref).abs().max() < 2e-5
+    o16 = torch.empty(B * Nn, D, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_layernorm(P(X), P(o16), P(g), P(b), B * Nn, D, 1e-6, 0, 0, 0, 0, L.F16, stream()), "ln16")
+    c16 = torch.empty(B * Pn, D, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_cast_rows(P(X), P(c16), B * Pn, D, Nn, Pn, 5, L.F16, stream()), "cast")
+    torch.cuda.synchronize()
+    assert rel_err(o16, F.layer_norm(X, (D,), g, b, 1e-6)) < 2e-3
+    assert torch.equal(c16, X.view(B, Nn, D)[:, 5:].reshape(B * Pn, D).half())
+
+
+def test_patchify_prefix_stem_maxpool():
+    lib = L.load()
+    B, S = 2, 64
+    x = _rand(B, 3, S, S)
+    out = torch.empty(B * 16, 768, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.b2u_patchify(P(x), P(out), B, S, L.BF16, stream()), "patchify")
+    ref = F.unfold(x, 16, stride=16).transpose(1, 2).reshape(B * 16, 768).bfloat16()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    w = _rand(64, 3, 3, 3, scale=27 ** -0.5, seed=1)
+    sc, sh = _rand(64, seed=2).abs() + 0.5, _rand(64, seed=3)
+    so = torch.empty(B, S // 2, S // 2, 64, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_stem_conv0(P(x), P(w), P(sc), P(sh), P(so), B, S, L.F16, stream()), "stem")
+    ref = F.relu(F.conv2d(x, w, stride=2, padding=1).half().float() * sc[None, :, None, None] + sh[None, :, None, None])
+    torch.cuda.synchronize()
+    assert rel_err(so.permute(0, 3, 1, 2), ref) < 2e-3
+    mp = torch.empty(B, S // 4, S // 4, 64, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_maxpool3x3s2(P(so), P(mp), B, S // 2, S // 2, 64, L.F16, stream()), "maxpool")
+    torch.cuda.synchronize()
+    assert torch.equal(mp.permute(0, 3, 1, 2), F.max_pool2d(so.permute(0, 3, 1, 2).float(), 3, 2, 1).half())
+
+
+def test_dwconv_three_planes_gelu():
+    lib = L.load()
+    B, Hc, Cc = 2, 8, 96
+    n = (Hc // 2) ** 2
+    x = _rand(B, 21 * n, Cc, dt=torch.float16)
+    w, bias = _rand(Cc, 1, 3, 3, scale=1 / 3, seed=1), _rand(Cc, seed=2)
+    out = torch.empty_like(x)
+    w9 = w.reshape(Cc, 9).t().contiguous()
+    L.check(lib.b2u_dwconv3x3(P(x), P(out), P(w9), P(bias), B, Hc, Hc, Cc, 3, L.ACT_GELU, L.F16, stream()), "dw")
+    torch.cuda.synchronize()
+    parts = []
+    for sl, hh in ((slice(0, 16 * n), 2 * Hc), (slice(16 * n, 20 * n), Hc), (slice(20 * n, 21 * n), Hc // 2)):
+        t = x[:, sl].float().transpose(1, 2).reshape(B, Cc, hh, hh)
+        parts.append(F.conv2d(t, w, bias, padding=1, groups=Cc).flatten(2).transpose(1, 2))
+    ref = F.gelu(torch.cat(parts, 1).half().float())
+    assert rel_err(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("dh", [12, 24, 32])
+def test_msda_forward_matches_reference_sampling(dh):
+    """the op the reference itself pins in ops/test.py: CUDA sampling == grid_sample formulation."""
+    lib = L.load()
+    B, Hv, heads, pts = 2, 16, 16, 4
+    HW = Hv * Hv
+    Lq = 21 * HW // 4
+    value = _rand(B, HW, heads, dh, dt=torch.float16)
+    offaw = torch.cat([_rand(B * Lq, 128, scale=3.0, seed=1), _rand(B * Lq, 64, seed=2)], 1).contiguous()
+    out = torch.empty(B * Lq, heads * dh, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_msda_forward(P(value), P(offaw), P(out), B, Hv, Hv, heads, dh, pts, L.F16, stream()), "msda")
+    torch.cuda.synchronize()
+    ref_pts = O.reference_points([(2 * Hv, 2 * Hv), (Hv, Hv), (Hv // 2, Hv // 2)], DEV)
+    off = offaw[:, :128].view(B, Lq, heads, 1, pts, 2)
+    aw = F.softmax(offaw[:, 128:].view(B, Lq, heads, pts), -1).view(B, Lq, heads, 1, pts)
+    loc = ref_pts[:, :, None, :, None, :] + off / torch.tensor([Hv, Hv], device=DEV)
+    ref = O.msda_core(value.float(), [(Hv, Hv)], loc, aw)
+    assert rel_err(out.view(B, Lq, -1), ref) < 2e-3, rel_err(out.view(B, Lq, -1), ref)
+
+
+def test_msda_f32_dropin_reference_fixture():
+    """ops/test.py:24-64 fixture: N,M,D=1,2,2; Lq,L,P=2,2,2; shapes [(6,4),(3,2)]; seed 3."""
+    lib = L.load()
+    N_, M_, D_, Lq_, L_, P_ = 1, 2, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S_ = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    value = (torch.rand(N_, S_, M_, D_) * 0.01).to(DEV)
+    loc = torch.rand(N_, Lq_, M_, L_, P_, 2).to(DEV)
+    aw = torch.rand(N_, Lq_, M_, L_, P_).to(DEV) + 1e-5
+    aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).contiguous()
+    out = torch.empty(N_, Lq_, M_ * D_, device=DEV)
+    L.check(lib.b2u_msda_forward_f32(P(value), P(shapes), P(lsi), P(loc), P(aw), P(out), N_, S_, Lq_, M_, D_, L_, P_,
+                                     stream()), "msda_f32")
+    torch.cuda.synchronize()
+    ref = O.msda_core(value, [(6, 4), (3, 2)], loc, aw)
+    assert torch.allclose(out, ref, rtol=1e-2, atol=1e-3)   # the reference's own fp32 tolerance (ops/test.py:81)
+    assert (out - ref).abs().max() < 1e-6
+
+
+def test_instancenorm_film_se_seg():
+    lib = L.load()
+    B, rows, Cc = 2, 4096, 32
+    x = (_rand(B * rows, 2 * Cc, dt=torch.float16) * 2 + 0.5)
+    sums = torch.zeros(B, Cc, 2, device=DEV)
+    L.check(lib.b2u_in_stats(P(x), 2 * Cc, P(sums), B, rows, Cc, L.F16, stream()), "stats")
+    g, b = _rand(Cc, seed=1), _rand(Cc, seed=2)
+    y = torch.empty(B * rows, Cc, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_in_apply(P(x), 2 * Cc, P(y), Cc, P(sums), P(g), P(b), B, rows, Cc, 1e-5, L.F16, stream()), "apply")
+    torch.cuda.synchronize()
+    xin = x[:, :Cc].float().view(B, rows, Cc).transpose(1, 2).reshape(B, Cc, 64, 64)
+    ref = F.leaky_relu(F.instance_norm(xin, None, None, g, b, True, 0.1, 1e-5), 0.01)
+    assert rel_err(y.view(B, rows, Cc).transpose(1, 2).reshape(B, Cc, 64, 64), ref) < 3e-3
+    # seg head on the same statistics
+    w, wb = _rand(2, Cc, seed=3), _rand(2, seed=4)
+    xc = x[:, :Cc].contiguous()
+    logits = torch.empty(B, 2, rows, device=DEV)
+    labels = torch.empty(B, rows, device=DEV, dtype=torch.uint8)
+    L.check(lib.b2u_seg_head(P(xc), P(sums), P(g), P(b), 1e-5, P(w), P(wb), P(logits), P(labels), B, rows, Cc, 2, L.F16,
+                             stream()), "seg")
+    torch.cuda.synchronize()
+    refl = F.conv2d(ref.half().float(), w.view(2, Cc, 1, 1), wb).flatten(2)
+    assert rel_err(logits, refl) < 3e-3
+    assert (labels.long() == logits.argmax(1)).all()
+    # FiLM
+    R = 256
+    gb, zz = _rand(1000, 2 * R, dt=torch.float16, seed=5), _rand(1000, 2 * R, dt=torch.float16, seed=6)
+    z = torch.empty(1000, R, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_film(P(gb), P(zz), 2 * R, R, P(z), 1000, R, L.F16, stream()), "film")
+    torch.cuda.synchronize()
+    assert rel_err(z, gb[:, :R].float() * zz[:, R:].float() + gb[:, R:].float()) < 2e-3
+    # SE gate + apply
+    w1, b1, w2, b2 = _rand(2, Cc, seed=7), _rand(2, seed=8), _rand(Cc, 2, seed=9), _rand(Cc, seed=10)
+    gate = torch.empty(B, Cc, device=DEV)
+    L.check(lib.b2u_se_gate(P(sums), P(w1), P(b1), P(w2), P(b2), P(gate), B, Cc, 2, rows, stream()), "gate")
+    outse = torch.empty(B * rows, Cc, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_se_apply(P(xc), x.data_ptr() + Cc * 2, 2 * Cc, P(gate), P(outse), B, rows, Cc, L.F16, stream()), "se")
+    torch.cuda.synchronize()
+    pooled = x[:, :Cc].float().view(B, rows, Cc).mean(1)
+    gref = torch.sigmoid(F.relu(pooled @ w1.t() + b1) @ w2.t() + b2)
+    assert (gate - gref).abs().max() < 1e-4
+    ref = x[:, :Cc].float().view(B, rows, Cc) * gref[:, None] + x[:, Cc:].float().view(B, rows, Cc)
+    assert rel_err(outse.view(B, rows, Cc), ref) < 2e-3
+
+
+def test_tail_fuse_bilinear_bn():
+    lib = L.load()
+    B, D, Ht = 2, 384, 8
+    for H in (32, 16, 8, 4):
+        tap = _rand(B, Ht * Ht, D, seed=H)
+        base = _rand(B, H * H, D, seed=H + 1)
+        sc, sh = _rand(D, seed=2).abs() + 0.5, _rand(D, seed=3)
+        out = torch.empty(B, H * H, D, device=DEV, dtype=torch.float16)
+        L.check(lib.b2u_tail_fuse(P(base), 1, H * H * D, P(tap), P(out), P(sc), P(sh), B, H, H, Ht, Ht, D, L.F16,
+                                  stream()), "tail")
+        torch.cuda.synchronize()
+        t = tap.transpose(1, 2).reshape(B, D, Ht, Ht)
+        up = F.interpolate(t, size=(H, H), mode="bilinear", align_corners=False)
+        ref = (base.transpose(1, 2).reshape(B, D, H, H) + up) * sc[None, :, None, None] + sh[None, :, None, None]
+        got = out.float().transpose(1, 2).reshape(B, D, H, H)
+        assert rel_err(got, ref) < 2e-3, (H, rel_err(got, ref))
