@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the Dino U-Net forward path (BASELINE.json metric: 2D 512x512 patches/sec, dinounet_l forward).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (hand-written sm_100a kernels, C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU forward (oracle port) on host cores
+
+One "step" = one forward over one batch of synthetic 3x512x512 patches (per-GPU batch fixed -> weak scaling).  For N>1
+the driver launches one rank per GPU with torch.distributed.run; each rank runs its own batch shard (no data-path
+collective inside the forward) and the step ends with ONE NCCL all-gather of the logits.
+Rank 0 prints exactly one JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="dinounet_l", choices=["dinounet_s", "dinounet_b", "dinounet_l"])
+    ap.add_argument("--batch", type=int, default=32, help="patches per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--vit-dtype", default="bf16")
+    ap.add_argument("--rest-dtype", default="fp16")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="patches in the bounded CPU-baseline sample (0 = skip)")
+    ap.add_argument("--ops-out", default="", help="write the per-kernel timing breakdown (JSON) here")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_forward_patches_per_s(model, size, n_patches, threads=None):
+    """The reference's algorithm on host cores: the oracle restatement (bit-identical to the reference forward,
+    tests/test_oracle_vs_reference.py), fp32, eval, all host threads; bounded sample of the same workload."""
+    import torch
+    from oracle import dinounet_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = O.make_state_dict(model, 2, seed=0)
+    x = O.make_input(1, size, 0)
+    O.forward(sd, model, x)  # warm-up (allocator, thread pools)
+    t0 = time.perf_counter()
+    for i in range(n_patches):
+        O.forward(sd, model, O.make_input(1, size, i + 1))
+    dt = time.perf_counter() - t0
+    return n_patches / dt, threads, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(1, a.steps)
+    import torch
+    from oracle import dinounet_oracle as O
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = O.make_state_dict(a.model, 2, seed=0)
+    for _ in range(max(1, min(a.warmup, 1))):
+        O.forward(sd, a.model, O.make_input(1, a.size, 0))
+    t0 = time.perf_counter()
+    for i in range(n):
+        O.forward(sd, a.model, O.make_input(1, a.size, i + 1))   # one step = a bounded sample: 1 patch of the workload
+    dt = time.perf_counter() - t0
+    v = n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "2D patches/sec (512x512) forward", "value": v, "unit": "patches/s",
+        "n_gpus": a.gpus, "steps": n, "warmup": a.warmup, "ms_per_step": 1e3 * dt / n, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{a.model} forward, {a.size}x{a.size}x3, per-GPU batch {a.batch} (reference arm: 1 patch/step sample)"},
+        "cpu_baseline": {"value": v, "unit": "patches/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} x 1 patch {a.model}@{a.size} fp32 eval forward, oracle port of the reference"},
+        "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "1")
+    import dinounet_b200
+    from dinounet_b200 import config, lib
+    from oracle import dinounet_oracle as O   # synthetic weights/inputs + FLOP model + cpu_baseline only
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+
+    B, S, K, W = a.batch, a.size, a.steps, max(3, a.warmup)
+    sd = O.make_state_dict(a.model, 2, seed=0)
+    net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, a.model)
+    net.load_state_dict(sd, strict=True)
+    net.vit_dtype, net.rest_dtype = a.vit_dtype, a.rest_dtype
+    net = net.to(dev).eval()
+    del sd
+    eng = net._get_engine(dev)
+    plan, bufs = eng.get_plan(B, S)
+    n_kernels = len(plan.calls)
+    # three resident input batches (3 x 100 MB at B=32 > 126 MB L2) rotated between steps; the per-step activation
+    # working set (GBs) is itself >> L2, so no step starts with a warm cache.
+    xs = [O.make_input(B, S, 100 + rank * 7 + i).to(dev) for i in range(3)]
+    gathered = torch.empty((world,) + tuple(bufs["logits"].shape), device=dev) if world > 1 else None
+    use_graph = not a.no_graph
+
+    def step(i):
+        logits, _ = eng.forward(xs[i % 3], use_graph=use_graph)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logits)
+        return logits
+
+    with torch.no_grad():
+        for i in range(W):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record()
+            for i in range(K):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        value = world * B * K / (ms / 1e3)
+
+        # ---- e2e: the public API call (net(x)) with HOST buffers: H2D of the inputs and D2H of the logits in the timed region
+        hx = [O.make_input(B, S, 200 + i).pin_memory() for i in range(2)]
+        hy = torch.empty(tuple(bufs["logits"].shape), dtype=torch.float32).pin_memory()
+        for i in range(2):
+            hy.copy_(net(hx[i % 2].to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            y = net(hx[i % 2].to(dev, non_blocking=True))
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, y)
+            hy.copy_(y, non_blocking=True)
+            torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = world * B * K / te.item()
+
+        # ---- per-kernel timing (one extra eager step with CUDA events around every launch, same stream)
+        breakdown, roof = {}, None
+        if rank == 0:
+            stream = torch.cuda.current_stream(dev)
+            evs = []
+            for name, fn, args in plan.calls:
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record(stream)
+                rc = fn(*args, __import__("ctypes").c_void_p(stream.cuda_stream))
+                e_.record(stream)
+                assert rc == 0, (name, lib.last_error())
+                evs.append((name, s_, e_))
+            torch.cuda.synchronize()
+            fam = {}
+            for name, s_, e_ in evs:
+                base = name.split(".")[-1] if name[0] in "be" and name[1].isdigit() else name
+                key = ("vit." + base) if name.startswith("b") and name[1].isdigit() else (
+                    "extractor." + base if name.startswith("e") and name[1].isdigit() else name.split(".")[0])
+                fam[key] = fam.get(key, 0.0) + s_.elapsed_time(e_)
+            breakdown = dict(sorted(fam.items(), key=lambda kv: -kv[1]))
+            # dominant kernel: the tcgen05 GEMM family of the ViT (qkv, proj, fc1, fc2) -> tensor-core roofline
+            v = config.VARIANTS[a.model]
+            T = B * ((S // 16) ** 2 + config.N_PREFIX)
+            flops = v.depth * 2 * T * v.embed_dim * (3 * v.embed_dim + v.embed_dim + 2 * v.ffn_hidden)
+            t_gemm = sum(fam.get(k, 0) for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2"))
+            pk = peaks()
+            ach = flops / (t_gemm * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*,bf16> (ViT qkv/proj/fc1/fc2, %d launches/step)" % (4 * v.depth),
+                    "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                    "peak_source": pk["src"] + " (bf16 sustained)", "share_of_step": t_gemm / sum(fam.values())}
+            if a.ops_out:
+                os.makedirs(os.path.dirname(a.ops_out) or ".", exist_ok=True)
+                json.dump({"per_family_ms": breakdown, "per_op_ms": [(n, s_.elapsed_time(e_)) for n, s_, e_ in evs]},
+                          open(a.ops_out, "w"), indent=1)
+
+    if rank == 0:
+        cpu = None
+        if a.cpu_sample > 0:
+            v_cpu, cores, dt = cpu_forward_patches_per_s(a.model, S, a.cpu_sample)
+            cpu = {"value": v_cpu, "unit": "patches/s", "cores": cores, "kind": "port",
+                   "sample": f"{a.cpu_sample} x 1 patch {a.model}@{S} fp32 eval forward ({dt:.1f} s), oracle port of the reference"}
+        total_flops = O.algorithmic_flops_per_patch(a.model, S)
+        out = {
+            "metric": "2D patches/sec (512x512) forward", "value": value, "unit": "patches/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": f"{a.vit_dtype} (ViT GEMMs/attention) + {a.rest_dtype} (adapter/FAPM/decoder), fp32 accumulate/residuals",
+            "data": "synthetic", "impl": "b200",
+            "config": {"workload": f"{a.model} forward, {S}x{S}x3, per-GPU batch {B}, random-init weights (seed 0)",
+                       "global_batch": B * world, "parallelism": f"batch-sharded dp{world} + 1 NCCL all-gather of logits" if world > 1 else "single GPU",
+                       "l2": "3 resident input batches rotated (3x%.0f MB) and a per-step activation working set >> 126 MB L2" % (B * 3 * S * S * 4 / 1e6),
+                       "cuda_graph": use_graph},
+            "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
+                    "d2h_bytes_per_step": B * 2 * S * S * 4},
+            "gpu_launches": K * n_kernels, "kernels_per_step": n_kernels,
+            "clocks": clk.summary(),
+            "roofline": roof, "cpu_baseline": cpu,
+            "model_tflops": value / world * total_flops / 1e12,
+            "breakdown_ms": {k: round(v, 3) for k, v in list(breakdown.items())[:14]},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -389,50 +389,73 @@ extern "C" int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_b
 }
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm
-// stats: block = (image b, row chunk); thread = (row lane, 8-channel group); smem tree over row lanes; atomics to [B,C,2].
+// stats: block = (row chunk, image b); thread = (row lane, 8-channel group); smem tree over row lanes; the block's
+// partial (sum, sumsq) per channel goes to a workspace slot, and the LAST block of each image (ticket counter) adds the
+// slots in fixed chunk order -> bitwise deterministic, no float atomics, no zero-fill of `sums` needed.
+static inline int in_stats_chunk(int rows) { return rows >= 8192 ? 2048 : (rows >= 1024 ? 256 : 64); }
+
 template <typename T>
 __global__ void __launch_bounds__(256) in_stats_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ sums,
-                                                       int rows, int C8, int chunk) {
+                                                       float* __restrict__ work, int rows, int C8, int chunk) {
   extern __shared__ float red[];  // [rows_par][C8*16]
-  const int b = blockIdx.y;
+  __shared__ int s_last;
+  const int b = blockIdx.y, nchunks = gridDim.x, B = gridDim.y;
   const int cg = threadIdx.x % C8, rl = threadIdx.x / C8;
   const int rows_par = 256 / C8;
   const int r0 = blockIdx.x * chunk;
   const int r1 = min(rows, r0 + chunk);
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (rl < rows_par) {
-    for (int r = r0 + rl; r < r1; r += rows_par) {
-      Vec8<T> v;
-      v.load(x + (static_cast<long long>(b) * rows + r) * ldx + cg * 8);
-      float f[8];
-      v.to_float(f);
+  for (int r = r0 + rl; r < r1; r += rows_par) {
+    Vec8<T> v;
+    v.load(x + (static_cast<long long>(b) * rows + r) * ldx + cg * 8);
+    float f[8];
+    v.to_float(f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
-    }
-    float* my = red + (rl * C8 + cg) * 16;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { my[j] = s[j]; my[8 + j] = q[j]; }
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
   }
+  float* my = red + (rl * C8 + cg) * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { my[j] = s[j]; my[8 + j] = q[j]; }
   __syncthreads();
-  // C8*16 outputs, each summed over rows_par partials
-  for (int o = threadIdx.x; o < C8 * 16; o += 256) {
+  const int nout = C8 * 16;  // per image: C channels x (sum, sumsq), laid out [cg][k][j]
+  int* counters = reinterpret_cast<int*>(work);
+  float* part = work + B + (static_cast<long long>(b) * nchunks + blockIdx.x) * nout;
+  for (int o = threadIdx.x; o < nout; o += 256) {
     float t = 0.f;
-    for (int p = 0; p < rows_par; ++p) t += red[p * C8 * 16 + o];
-    const int g = o / 16, j = o % 16;
-    const int c = g * 8 + (j & 7);
-    atomicAdd(sums + (static_cast<long long>(b) * C8 * 8 + c) * 2 + (j >> 3), t);
+    for (int p = 0; p < rows_par; ++p) t += red[p * nout + o];
+    part[o] = t;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counters + b, 1) == nchunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = work + B + static_cast<long long>(b) * nchunks * nout;
+  for (int o = threadIdx.x; o < nout; o += 256) {
+    float t = 0.f;
+    for (int c = 0; c < nchunks; ++c) t += __ldcg(pb + static_cast<long long>(c) * nout + o);
+    const int g = o / 16, j = o % 16;
+    sums[(static_cast<long long>(b) * C8 * 8 + g * 8 + (j & 7)) * 2 + (j >> 3)] = t;
+  }
+  if (threadIdx.x == 0) counters[b] = 0;  // self-resetting ticket
 }
 
-extern "C" int b2u_in_stats(const void* x, int64_t ldx, float* sums, int32_t B, int32_t rows, int32_t C, int32_t dtype,
-                            b2u_stream_t stream_) {
+extern "C" int64_t b2u_in_stats_work_floats(int32_t B, int32_t rows, int32_t C) {
+  const int chunk = in_stats_chunk(rows);
+  return static_cast<int64_t>(B) + static_cast<int64_t>(B) * ((rows + chunk - 1) / chunk) * C * 2;
+}
+
+extern "C" int b2u_in_stats(const void* x, int64_t ldx, float* sums, float* work, int32_t B, int32_t rows, int32_t C,
+                            int32_t dtype, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (C % 8 || C > 2048 || (256 % (C / 8))) return set_error(-1, "b2u_in_stats: C must be 8*2^k <= 2048");
+  if (!work) return set_error(-1, "b2u_in_stats: workspace required");
   const int C8 = C / 8;
-  const int chunk = rows >= 8192 ? 2048 : (rows >= 1024 ? 256 : 64);
+  const int chunk = in_stats_chunk(rows);
   dim3 grid((rows + chunk - 1) / chunk, B);
   const size_t smem = static_cast<size_t>(256 / C8) * C8 * 16 * sizeof(float);
-  B2U_DISPATCH_T(dtype, (in_stats_kernel<T><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), ldx, sums, rows, C8, chunk)));
+  B2U_DISPATCH_T(dtype, (in_stats_kernel<T><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), ldx, sums, work, rows, C8, chunk)));
   return check_launch("in_stats");
 }
 

@@ -386,7 +386,9 @@ class ForwardEngine:
         n_stats = 3 * 4 + 6
         stats = buf("stats", (n_stats, B, 256, 2), torch.float32)
         gate = buf("gate", (B, 256), torch.float32)
-        plan.add("zero_stats", lib.b2u_zero, _ptr(stats), stats.numel() * 4)
+        wfl = max(int(lib.b2u_in_stats_work_floats(B, (S4 >> i) ** 2, oc)) for i, oc in enumerate(self.features))
+        wfl = max([wfl] + [int(lib.b2u_in_stats_work_floats(B, (S4 << s) ** 2, self.features[2 - s])) for s in range(3)])
+        bufs["in_work"] = in_work = torch.zeros(wfl, dtype=torch.float32, device=dev)   # ticket counters start at zero
         feats = self.features
         cat = [buf("cat0", (B * S4 * S4, 2 * feats[2]), tr), buf("cat1", (B * S2 * S2, 2 * feats[1]), tr),
                buf("cat2", (B * S * S, 2 * feats[0]), tr)]
@@ -410,17 +412,17 @@ class ForwardEngine:
             plan.add(pre + "film", lib.b2u_film, _ptr(GB), _ptr(ZZ), 2 * R, R, _ptr(Z), px, R, rt)
             self._gemm(plan, pre + "reduce_sc", Z, px, R, R, w[pre + "w3"], n3_, RS, n3_, rt, bias=w[pre + "b3"])
             s_a, s_b, s_c = sums_slot(), sums_slot(), sums_slot()
-            plan.add(pre + "in1.stats", lib.b2u_in_stats, _ptr(RS), n3_, _ptr(s_a), B, r * r, oc, rt)
+            plan.add(pre + "in1.stats", lib.b2u_in_stats, _ptr(RS), n3_, _ptr(s_a), _ptr(in_work), B, r * r, oc, rt)
             plan.add(pre + "in1.apply", lib.b2u_in_apply, _ptr(RS), n3_, _ptr(T1), oc, _ptr(s_a), _ptr(w[pre + "in1w"]),
                      _ptr(w[pre + "in1b"]), B, r * r, oc, cfg.IN_EPS, rt)
             plan.add(pre + "dw", lib.b2u_dwconv3x3, _ptr(T1), _ptr(T2), _ptr(w[pre + "dw"]), _ptr(w[pre + "dwb"]), B, r, r, oc,
                      1, L.ACT_NONE, rt)
             self._gemm(plan, pre + "pw", T2, px, oc, oc, w[pre + "pw"], oc, T1, oc, rt, bias=w[pre + "pwb"])
-            plan.add(pre + "in2.stats", lib.b2u_in_stats, _ptr(T1), oc, _ptr(s_b), B, r * r, oc, rt)
+            plan.add(pre + "in2.stats", lib.b2u_in_stats, _ptr(T1), oc, _ptr(s_b), _ptr(in_work), B, r * r, oc, rt)
             plan.add(pre + "in2.apply", lib.b2u_in_apply, _ptr(T1), oc, _ptr(T2), oc, _ptr(s_b), _ptr(w[pre + "in2w"]),
                      _ptr(w[pre + "in2b"]), B, r * r, oc, cfg.IN_EPS, rt)
             self._gemm(plan, pre + "refine", T2, px, oc, oc, w[pre + "ref"], oc, T1, oc, rt, bias=w[pre + "refb"])
-            plan.add(pre + "se.pool", lib.b2u_in_stats, _ptr(T1), oc, _ptr(s_c), B, r * r, oc, rt)
+            plan.add(pre + "se.pool", lib.b2u_in_stats, _ptr(T1), oc, _ptr(s_c), _ptr(in_work), B, r * r, oc, rt)
             plan.add(pre + "se.gate", lib.b2u_se_gate, _ptr(s_c), _ptr(w[pre + "se1"]), _ptr(w[pre + "se1b"]), _ptr(w[pre + "se2"]),
                      _ptr(w[pre + "se2b"]), _ptr(gate), B, oc, max(1, oc // 16), r * r)
             if has_sc:
@@ -454,7 +456,7 @@ class ForwardEngine:
                 self._gemm(plan, f"d{s}.conv{j}", src, 0, 9 * cin, cin, w[f"d{s}.c{j}"], skip, CO, skip, rt,
                            bias=w[f"d{s}.c{j}b"], conv=L.CONV3X3_S1, img=(B, r_hi, r_hi, cin))
                 ss = sums_slot()
-                plan.add(f"d{s}.in{j}.stats", lib.b2u_in_stats, _ptr(CO), skip, _ptr(ss), B, r_hi * r_hi, skip, rt)
+                plan.add(f"d{s}.in{j}.stats", lib.b2u_in_stats, _ptr(CO), skip, _ptr(ss), _ptr(in_work), B, r_hi * r_hi, skip, rt)
                 if s == 2 and j == 1:
                     plan.add("seg_head", lib.b2u_seg_head, _ptr(CO), _ptr(ss), _ptr(w[f"d{s}.n{j}w"]), _ptr(w[f"d{s}.n{j}b"]),
                              cfg.IN_EPS, _ptr(w["seg.w"]), _ptr(w["seg.b"]), _ptr(logits), _ptr(labels), B, r_hi * r_hi, skip,

@@ -68,7 +68,8 @@ SIGNATURES = {
     "b2u_msda_forward": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_msda_forward_f32": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_tail_fuse": [vp, i32, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
-    "b2u_in_stats": [vp, i64, vp, i32, i32, i32, i32, vp],
+    "b2u_in_stats_work_floats": [i32, i32, i32],
+    "b2u_in_stats": [vp, i64, vp, vp, i32, i32, i32, i32, vp],
     "b2u_in_apply": [vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, f32, i32, vp],
     "b2u_film": [vp, vp, i64, i32, vp, i32, i32, i32, vp],
     "b2u_se_gate": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
@@ -79,7 +80,7 @@ SIGNATURES = {
     "b2u_version": [],
     "b2u_launch_count": [],
 }
-_RESTYPES = {"b2u_last_error": C.c_char_p, "b2u_launch_count": C.c_int64}
+_RESTYPES = {"b2u_last_error": C.c_char_p, "b2u_launch_count": C.c_int64, "b2u_in_stats_work_floats": C.c_int64}
 
 _lib: Optional[C.CDLL] = None
 

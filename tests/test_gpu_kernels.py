@@ -262,8 +262,14 @@ def test_instancenorm_film_se_seg():
     lib = L.load()
     B, rows, Cc = 2, 4096, 32
     x = (_rand(B * rows, 2 * Cc, dt=torch.float16) * 2 + 0.5)
-    sums = torch.zeros(B, Cc, 2, device=DEV)
-    L.check(lib.b2u_in_stats(P(x), 2 * Cc, P(sums), B, rows, Cc, L.F16, stream()), "stats")
+    sums = torch.full((B, Cc, 2), float("nan"), device=DEV)
+    work = torch.zeros(int(lib.b2u_in_stats_work_floats(B, rows, Cc)), device=DEV)
+    L.check(lib.b2u_in_stats(P(x), 2 * Cc, P(sums), P(work), B, rows, Cc, L.F16, stream()), "stats")
+    s1 = sums.clone()
+    L.check(lib.b2u_in_stats(P(x), 2 * Cc, P(sums), P(work), B, rows, Cc, L.F16, stream()), "stats")   # tickets self-reset
+    torch.cuda.synchronize()
+    assert torch.equal(s1, sums)
+    assert rel_err(sums[..., 0], x[:, :Cc].float().view(B, rows, Cc).sum(1)) < 1e-5
     g, b = _rand(Cc, seed=1), _rand(Cc, seed=2)
     y = torch.empty(B * rows, Cc, device=DEV, dtype=torch.float16)
     L.check(lib.b2u_in_apply(P(x), 2 * Cc, P(y), Cc, P(sums), P(g), P(b), B, rows, Cc, 1e-5, L.F16, stream()), "apply")

@@ -39,6 +39,11 @@ def _compare(y, ref, ref_regime=None, name=""):
     margin = (ref[:, 0] - ref[:, 1]).abs()
     flips = (y.argmax(1) != ref.argmax(1))
     msg = f"{name}: rel err {err:.3e}, flips {int(flips.sum())}/{flips.numel()}"
+    if ref_regime is not None and not torch.isfinite(ref_regime).all():
+        # observed for dinounet_l with the synthetic O(1) weights: the reference's OWN fp16/bf16 autocast regime overflows
+        # (non-finite logits from torch eager), while the kernel path (fp32 residual/query streams) stays finite.
+        print(f"{name}: reference-regime eager forward is NON-FINITE on this case; comparing against fp32 truth only")
+        ref_regime = None
     if ref_regime is not None:
         rr = ref_regime.float().cpu()
         err_r = (rr - ref).abs().max().item() / scale
@@ -131,7 +136,7 @@ def test_batch_items_are_independent_and_deterministic():
         y1 = net(x[1:2].contiguous())
         y3b = net(x)
     assert torch.equal(y3, y3b)
-    assert (y3[1:2] - y1).abs().max().item() < 1e-5   # only IN/SE statistics use atomics (order-dependent fp32 sums)
+    assert torch.equal(y3[1:2], y1)   # per-image reductions have a fixed order (no float atomics anywhere)
 
 
 def test_cuda_graph_replay_matches_eager_launches():
@@ -145,4 +150,4 @@ def test_cuda_graph_replay_matches_eager_launches():
         yg, _ = eng.forward(x, use_graph=True)
         yg2, _ = eng.forward(x, use_graph=True)
     torch.cuda.synchronize()
-    assert (yg - y).abs().max().item() < 1e-5 and (yg2 - y).abs().max().item() < 1e-5
+    assert torch.equal(yg, y) and torch.equal(yg2, y)

@@ -39,10 +39,9 @@ with open("gpurun_out/gpu_tests.log", "w") as log:
         dt = time.time() - t0
         print(f"{status:8s} {dt:6.1f}s {tid}", flush=True)
         log.write(f"===== {status} {dt:.1f}s {tid}\n")
+        log.write("\n".join(l for l in out.splitlines() if "rel err" in l or "stage " in l or "NON-FINITE" in l) + "\n")
         if status != "PASS":
             log.write(out + "\n")
-        else:
-            log.write("\n".join(l for l in out.splitlines() if "rel err" in l or "stage" in l) + "\n")
         log.flush()
         res.append(status)
 print({s: res.count(s) for s in set(res)})
