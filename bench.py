@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--vit-dtype", default="bf16")
     ap.add_argument("--rest-dtype", default="fp16")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--gemm-impl", default="v2", choices=["v1", "v2"])
     ap.add_argument("--cpu-sample", type=int, default=2, help="patches in the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--ops-out", default="", help="write the per-kernel timing breakdown (JSON) here")
     return ap.parse_args()
@@ -148,7 +149,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    lib.load()
+    lib.load().b2u_set_option(0, 1 if a.gemm_impl == "v1" else 0)
 
     B, S, K, W = a.batch, a.size, a.steps, max(3, a.warmup)
     sd = O.make_state_dict(a.model, 2, seed=0)

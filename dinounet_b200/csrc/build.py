@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["gemm_tc.cu", "attention.cu", "elementwise.cu", "msda.cu", "host_util.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "attention.cu", "elementwise.cu", "msda.cu", "host_util.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libdinounet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

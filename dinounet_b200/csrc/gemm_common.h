@@ -1,0 +1,42 @@
+// Shared between the GEMM kernel generations (gemm_tc.cu: v1 one-tile-per-CTA, gemm_tc2.cu: v2 persistent).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/dinounet_b200.h"
+
+namespace b2u {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
+
+struct alignas(64) GemmMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct GemmArgs {
+  int M, N;
+  int num_kb;
+  int n_tiles;
+  int m_tiles;
+  int conv;  // 0 plain, 1 3x3 s1, 2 3x3 s2
+  int cb;    // channel blocks per tap
+  int Ho, Wo;
+  int TW, TH, tiles_x, tiles_y;
+  b2u_epilogue epi;
+  // QKV epilogue
+  int ntok, D, heads, prefix;
+  const float* rope_sin;
+  const float* rope_cos;
+  void* q;
+  void* k;
+  void* v;
+};
+
+int num_sms();
+int gemm_v1_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
+int gemm_v2_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
+int get_option(int key);
+
+}  // namespace b2u

@@ -10,34 +10,9 @@
 #include "common.cuh"
 #include "../../include/dinounet_b200.h"
 #include "host_util.h"
+#include "gemm_common.h"
 
 namespace b2u {
-
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
-
-struct alignas(64) GemmMaps {
-  CUtensorMap a[4];
-  CUtensorMap b;
-};
-
-struct GemmArgs {
-  int M, N;
-  int num_kb;
-  int n_tiles;
-  int conv;  // 0 plain, 1 3x3 s1, 2 3x3 s2
-  int cb;    // channel blocks per tap
-  int Ho, Wo;
-  int TW, TH, tiles_x, tiles_y;
-  b2u_epilogue epi;
-  // QKV epilogue
-  int ntok, D, heads, prefix;
-  const float* rope_sin;
-  const float* rope_cos;
-  void* q;
-  void* k;
-  void* v;
-};
 
 template <int BN> struct Cfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
@@ -325,25 +300,35 @@ static int launch_variant(const GemmMaps& maps, const GemmArgs& args, int grid, 
   return check_launch("gemm_tc");
 }
 
-template <bool QKV>
-static int dispatch(int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, int grid, cudaStream_t stream) {
-#define B2U_CASE(BN_)                                                                       \
-  case BN_:                                                                                 \
-    return dtype == B2U_BF16 ? launch_variant<BN_, QKV, __nv_bfloat16>(maps, args, grid, stream) \
-                             : launch_variant<BN_, QKV, __half>(maps, args, grid, stream);
-  if constexpr (QKV) {
-    switch (bn) { B2U_CASE(128) default: break; }
+int gemm_v1_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  const long long grid_ll = static_cast<long long>(args.m_tiles) * args.n_tiles;
+  if (grid_ll <= 0 || grid_ll > 0x7FFFFFFFLL) return set_error(-1, "gemm_tc: bad grid");
+  const int grid = static_cast<int>(grid_ll);
+#define B2U_CASE(Q_, BN_)                                                                          \
+  case BN_:                                                                                        \
+    return dtype == B2U_BF16 ? launch_variant<BN_, Q_, __nv_bfloat16>(maps, args, grid, stream)   \
+                             : launch_variant<BN_, Q_, __half>(maps, args, grid, stream);
+  if (qkv) {
+    switch (bn) { B2U_CASE(true, 128) default: break; }
   } else {
-    switch (bn) { B2U_CASE(32) B2U_CASE(64) B2U_CASE(128) B2U_CASE(256) default: break; }
+    switch (bn) { B2U_CASE(false, 32) B2U_CASE(false, 64) B2U_CASE(false, 128) default: break; }
   }
 #undef B2U_CASE
   return set_error(-3, "gemm_tc: unsupported BLOCK_N %d", bn);
 }
 
-static int pick_bn(int N) {
+// v2 (persistent, 128x256 tiles) is the default; option 0 (B2U_OPT_GEMM_IMPL) = 1 selects the v1 kernel for A/B runs
+static int pick_bn(int N, bool v2) {
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  return 128;
+  if (!v2 || N <= 128) return 128;
+  const int waste = (N + 255) / 256 * 256 - N;
+  return (waste == 0 || waste * 8 <= N) ? 256 : 128;
+}
+
+static int run_gemm(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  return get_option(0) == 1 ? gemm_v1_dispatch(qkv, bn, dtype, maps, args, stream)
+                            : gemm_v2_dispatch(qkv, bn, dtype, maps, args, stream);
 }
 
 // 2-D K-major operand map: dims {K, rows}, box {64, box_rows}, 128B swizzle, OOB zero fill.
@@ -368,7 +353,8 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
   a.N = p->N;
   a.epi = p->epi;
   a.conv = p->conv;
-  const int bn = pick_bn(p->N);
+  const bool v2 = get_option(0) != 1;
+  const int bn = pick_bn(p->N, v2);
   a.n_tiles = (p->N + bn - 1) / bn;
   long long m_tiles;
   int rc;
@@ -414,9 +400,9 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
     }
     if ((rc = make_map_2d(&maps.b, p->Wp, p->N, static_cast<int64_t>(a.num_kb) * BK, p->ldw, bn, p->dtype))) return rc;
   }
-  const long long grid = m_tiles * a.n_tiles;
-  if (grid <= 0 || grid > 0x7FFFFFFFLL) return set_error(-1, "b2u_gemm: bad grid");
-  return dispatch<false>(bn, p->dtype, maps, a, static_cast<int>(grid), stream);
+  if (m_tiles <= 0 || m_tiles > 0x7FFFFFFFLL) return set_error(-1, "b2u_gemm: bad grid");
+  a.m_tiles = static_cast<int>(m_tiles);
+  return run_gemm(false, bn, p->dtype, maps, a, stream);
 }
 
 extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
@@ -428,7 +414,8 @@ extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   a.M = p->B * p->ntok;
   a.N = 3 * p->D;
   a.num_kb = (p->D + BK - 1) / BK;
-  const int bn = 128;
+  const bool v2 = get_option(0) != 1;
+  const int bn = v2 ? pick_bn(a.N, true) : 128;
   a.n_tiles = (a.N + bn - 1) / bn;
   a.conv = 0;
   a.epi.bias = p->bias;
@@ -438,8 +425,8 @@ extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   int rc;
   if ((rc = make_map_2d(&maps.a[0], p->A, a.M, p->D, p->lda, BM, p->dtype))) return rc;
   if ((rc = make_map_2d(&maps.b, p->Wp, a.N, p->D, p->ldw, bn, p->dtype))) return rc;
-  const long long grid = ((static_cast<long long>(a.M) + BM - 1) / BM) * a.n_tiles;
-  return dispatch<true>(bn, p->dtype, maps, a, static_cast<int>(grid), stream);
+  a.m_tiles = static_cast<int>((static_cast<long long>(a.M) + BM - 1) / BM);
+  return run_gemm(true, bn, p->dtype, maps, a, stream);
 }
 
 }  // namespace b2u

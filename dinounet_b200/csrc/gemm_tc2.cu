@@ -1,0 +1,425 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution, v2: persistent, warp-specialised, double-buffered TMEM.
+//
+//   grid = min(#tiles, #SMs) CTAs of 192 threads, one per SM, each looping over output tiles (n fastest, so the CTAs
+//   running concurrently share A rows through L2):
+//     warp 0   : TMA producer  — 4-stage (BN<=128: 6-stage) ring of {A 128x64, W BNx64} 128B-swizzled tiles
+//     warp 1   : MMA issuer    — one thread issues tcgen05.mma (M=128, N=BN, K=16) into accumulator buffer (tile & 1)
+//     warps 2-5: epilogue      — tcgen05.ld their 32-lane TMEM quarter in 32-column chunks, transpose through a
+//                                swizzled 4 KB smem patch per warp, then apply the fused epilogue in a row-contiguous
+//                                layout (per-column params are per-lane constants) and issue fully coalesced 16 B
+//                                loads/stores (residual / skip tensors / output).
+//   The accumulator of tile i+1 is produced while the epilogue drains tile i (TMEM: 2 x BN columns).
+//   Convolution mode: A tiles are 4-D TMA halo boxes of the NHWC image (9 taps x channel blocks, OOB = zero padding).
+#include "common.cuh"
+#include "../../include/dinounet_b200.h"
+#include "host_util.h"
+#include "gemm_common.h"
+
+namespace b2u {
+
+template <int BN> struct Cfg2 {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = 4 * 4096;        // 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int kBiasBytes = BN * 4;
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+__device__ __forceinline__ float apply_act2(float v, int act) {
+  if (act == B2U_ACT_GELU) return gelu_erf(v);
+  if (act == B2U_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == B2U_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BN, bool QKV, typename T>
+__global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
+  using C = Cfg2<BN>;
+  using TT = T16<T>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  float* s_bias = reinterpret_cast<float*>(staging + C::kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes + C::kBiasBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total_tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = static_cast<int>(tile % args.n_tiles);
+        const int mt = static_cast<int>(tile / args.n_tiles);
+        int img = 0, y0 = 0, x0 = 0;
+        if (args.conv) {
+          const int per_img = args.tiles_x * args.tiles_y;
+          img = mt / per_img;
+          const int r = mt - img * per_img;
+          y0 = (r / args.tiles_x) * args.TH;
+          x0 = (r % args.tiles_x) * args.TW;
+        }
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * C::kStageBytes;
+          uint8_t* sB = sA + C::kABytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (args.conv == 0) {
+            tma_load_2d(sA, &maps.a[0], &full_bar[stage], kb * BK, mt * BM);
+          } else {
+            const int tap = kb / args.cb;
+            const int c0 = (kb - tap * args.cb) * BK;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            if (args.conv == 1) {
+              tma_load_4d(sA, &maps.a[0], &full_bar[stage], c0, x0 + dx - 1, y0 + dy - 1, img);
+            } else {
+              const int py = (dy + 1) & 1, px = (dx + 1) & 1;
+              tma_load_4d(sA, &maps.a[py * 2 + px], &full_bar[stage], c0, x0 + (dx == 0 ? -1 : 0),
+                          y0 + (dy == 0 ? -1 : 0), img);
+            }
+          }
+          tma_load_2d(sB, &maps.b, &full_bar[stage], kb * BK, nt * BN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(TT::kFmt, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = make_desc_k128(sA);
+          const uint64_t db = make_desc_k128(sA + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_f16(tacc, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q4 = warp & 3;
+    const int ew = warp - 2;                         // staging patch index
+    uint8_t* patch = staging + ew * 4096;
+    const uint32_t patch_u32 = smem_u32(patch);
+    const b2u_epilogue& e = args.epi;
+    const int etid = threadIdx.x - 64;               // 0..127 among epilogue threads
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int nt = static_cast<int>(tile % args.n_tiles);
+      const int mt = static_cast<int>(tile / args.n_tiles);
+      const int n0 = nt * BN;
+      int img = 0, y0 = 0, x0 = 0;
+      if (args.conv) {
+        const int per_img = args.tiles_x * args.tiles_y;
+        img = mt / per_img;
+        const int r = mt - img * per_img;
+        y0 = (r / args.tiles_x) * args.TH;
+        x0 = (r % args.tiles_x) * args.TW;
+      }
+      // logical row (token / pixel) of tile row `tr`, validity
+      auto row_of = [&](int tr, long long& m) -> bool {
+        if (args.conv == 0) {
+          m = static_cast<long long>(mt) * BM + tr;
+          return m < args.M;
+        }
+        const int ty = tr / args.TW, tx = tr - ty * args.TW;
+        const int y = y0 + ty, x = x0 + tx;
+        m = (static_cast<long long>(img) * args.Ho + y) * args.Wo + x;
+        return (y < args.Ho) && (x < args.Wo);
+      };
+
+      if constexpr (QKV) {
+        // stage the (masked) bias of this tile's columns once
+        epi_bar_sync();
+        for (int i = etid; i < BN; i += 128) s_bias[i] = (e.bias && n0 + i < args.N) ? __ldg(e.bias + n0 + i) : 0.f;
+        epi_bar_sync();
+        // phase-1 owner row
+        long long m1;
+        const bool v1 = row_of(q4 * 32 + lane, m1);
+        const int b1 = static_cast<int>(m1 / args.ntok);
+        const int t1 = static_cast<int>(m1 - static_cast<long long>(b1) * args.ntok);
+        const bool rot = v1 && t1 >= args.prefix;
+        const float* sinr = args.rope_sin + static_cast<long long>(rot ? t1 - args.prefix : 0) * 64;
+        const float* cosr = args.rope_cos + static_cast<long long>(rot ? t1 - args.prefix : 0) * 64;
+        // phase-2 rows of this lane: rr = i*4 + lane/8  (8 lanes x 16 B = one 128 B head row)
+        long long dst_off[8];
+        bool dst_ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          long long m2;
+          dst_ok[i] = row_of(q4 * 32 + i * 4 + (lane >> 3), m2);
+          const int b2 = static_cast<int>(m2 / args.ntok);
+          const int t2 = static_cast<int>(m2 - static_cast<long long>(b2) * args.ntok);
+          dst_off[i] = (static_cast<long long>(b2) * args.heads * args.ntok + t2) * 64;
+        }
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll 1
+        for (int g = 0; g < BN / 64; ++g) {
+          uint32_t v0[32], v1r[32];
+          tmem_ld32(taddr + g * 64, v0);
+          tmem_ld32(taddr + g * 64 + 32, v1r);
+          tmem_ld_wait();
+          const int n = n0 + g * 64;
+          if (n >= args.N) continue;   // warp-uniform
+          const int which = n / args.D;
+          const int head = (n - which * args.D) >> 6;
+          float x[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x[j] = TT::to_f(TT::from_f(__uint_as_float(v0[j]) + s_bias[g * 64 + j]));
+            x[32 + j] = TT::to_f(TT::from_f(__uint_as_float(v1r[j]) + s_bias[g * 64 + 32 + j]));
+          }
+          uint32_t packed[32];
+          if (which < 2 && rot) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 c_lo = *reinterpret_cast<const float4*>(cosr + j), s_lo = *reinterpret_cast<const float4*>(sinr + j);
+              const float4 c_hi = *reinterpret_cast<const float4*>(cosr + 32 + j), s_hi = *reinterpret_cast<const float4*>(sinr + 32 + j);
+              packed[j / 2] = TT::pack2(x[j] * c_lo.x - x[j + 32] * s_lo.x, x[j + 1] * c_lo.y - x[j + 33] * s_lo.y);
+              packed[j / 2 + 1] = TT::pack2(x[j + 2] * c_lo.z - x[j + 34] * s_lo.z, x[j + 3] * c_lo.w - x[j + 35] * s_lo.w);
+              packed[16 + j / 2] = TT::pack2(x[j + 32] * c_hi.x + x[j] * s_hi.x, x[j + 33] * c_hi.y + x[j + 1] * s_hi.y);
+              packed[16 + j / 2 + 1] = TT::pack2(x[j + 34] * c_hi.z + x[j + 2] * s_hi.z, x[j + 35] * c_hi.w + x[j + 3] * s_hi.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) packed[j / 2] = TT::pack2(x[j], x[j + 1]);
+          }
+          // stage: row = lane, 8 x 16 B chunks, chunk position c ^ (row & 7)
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(patch + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          __syncwarp();
+          T* base = reinterpret_cast<T*>(which == 0 ? args.q : (which == 1 ? args.k : args.v)) +
+                    static_cast<long long>(head) * args.ntok * 64 + (lane & 7) * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);
+            const uint4 val = *reinterpret_cast<const uint4*>(patch + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            if (dst_ok[i]) *reinterpret_cast<uint4*>(base + dst_off[i]) = val;
+          }
+        }
+      } else {
+        // ---- phase-2 row assignment: fp32 output -> 8 lanes per row (4 cols each), 4 rows per pass, 8 passes;
+        //                              16-bit output -> 4 lanes per row (8 cols each), 8 rows per pass, 4 passes.
+        const bool o32 = e.out_fp32 != 0;
+        const int lpr = o32 ? 8 : 4;                 // lanes per row
+        const int rpp = 32 / lpr;                    // rows per pass
+        const int npass = 32 / rpp;
+        const int lcol = (lane % lpr) * (32 / lpr);  // first column (within the 32-col chunk) of this lane
+        long long rbase[8];                          // output row index (or pixel-shuffle base) per pass
+        bool rok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rok[i] = false;
+          rbase[i] = 0;
+          if (i < npass) {
+            long long m;
+            rok[i] = row_of(q4 * 32 + i * rpp + lane / lpr, m);
+            if (e.ps_cout > 0) {
+              const long long hw = static_cast<long long>(e.ps_h) * e.ps_w;
+              const int pb = static_cast<int>(m / hw);
+              const int rem = static_cast<int>(m - pb * hw);
+              const int pi = rem / e.ps_w, pj = rem - pi * e.ps_w;
+              rbase[i] = (static_cast<long long>(pb) * (2 * e.ps_h) + 2 * pi) * (2 * e.ps_w) + 2 * pj;
+            } else if (e.rows_in > 0) {
+              rbase[i] = (m / e.rows_in) * e.rows_out + e.row_off + (m % e.rows_in);
+            } else {
+              rbase[i] = m;
+            }
+          }
+        }
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          const int n = n0 + ch * 32;
+          if (n >= args.N) continue;   // warp-uniform
+          // stage raw fp32 accumulators: row = lane, 8 x 16 B groups at position j ^ (row & 7)
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(patch + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          int ocol = n + lcol;
+          long long radd = 0;
+          if (e.ps_cout > 0) {
+            const int qd = n / e.ps_cout;
+            ocol -= qd * e.ps_cout;
+            radd = static_cast<long long>(qd >> 1) * (2 * e.ps_w) + (qd & 1);
+          }
+          ocol += e.col_off;
+          if (o32) {
+            float bi[4] = {0, 0, 0, 0}, sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0};
+            if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol)); bi[0] = t.x; bi[1] = t.y; bi[2] = t.z; bi[3] = t.w; }
+            if (e.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.scale + n + lcol)); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
+            if (e.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.shift + n + lcol)); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3);
+              const float4 a4 = *reinterpret_cast<const float4*>(patch + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+              if (!rok[i]) continue;
+              float f[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float a = f[j] + bi[j];
+                if (e.round16) a = TT::to_f(TT::from_f(a));
+                a = apply_act2(a, e.act1);
+                a = a * sc[j] + sh[j];
+                f[j] = apply_act2(a, e.act2);
+              }
+              const long long orow = rbase[i] + radd;
+              if (e.residual) {
+                const float4 rv = *reinterpret_cast<const float4*>(e.residual + orow * e.ldres + ocol);
+                f[0] += rv.x; f[1] += rv.y; f[2] += rv.z; f[3] += rv.w;
+              }
+              if (e.add16) {
+                const uint2 av = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(e.add16) + orow * e.ldadd + ocol);
+                const float2 t0 = TT::unpack2(av.x), t1 = TT::unpack2(av.y);
+                f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + orow * e.ldc + ocol) = make_float4(f[0], f[1], f[2], f[3]);
+            }
+          } else {
+            float bi[8], sc[8], sh[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { bi[j] = 0.f; sc[j] = 1.f; sh[j] = 0.f; }
+            if (e.bias) {
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol)), t1 = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol + 4));
+              bi[0] = t0.x; bi[1] = t0.y; bi[2] = t0.z; bi[3] = t0.w; bi[4] = t1.x; bi[5] = t1.y; bi[6] = t1.z; bi[7] = t1.w;
+            }
+            if (e.scale) {
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(e.scale + n + lcol)), t1 = __ldg(reinterpret_cast<const float4*>(e.scale + n + lcol + 4));
+              sc[0] = t0.x; sc[1] = t0.y; sc[2] = t0.z; sc[3] = t0.w; sc[4] = t1.x; sc[5] = t1.y; sc[6] = t1.z; sc[7] = t1.w;
+            }
+            if (e.shift) {
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(e.shift + n + lcol)), t1 = __ldg(reinterpret_cast<const float4*>(e.shift + n + lcol + 4));
+              sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + (lane >> 2);
+              const int g0 = (lane & 3) * 2;
+              const float4 a4 = *reinterpret_cast<const float4*>(patch + rr * 128 + ((g0 ^ (rr & 7)) << 4));
+              const float4 b4 = *reinterpret_cast<const float4*>(patch + rr * 128 + (((g0 + 1) ^ (rr & 7)) << 4));
+              if (!rok[i]) continue;
+              float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a = f[j] + bi[j];
+                if (e.round16) a = TT::to_f(TT::from_f(a));
+                a = apply_act2(a, e.act1);
+                a = a * sc[j] + sh[j];
+                f[j] = apply_act2(a, e.act2);
+              }
+              const long long orow = rbase[i] + radd;
+              if (e.residual) {
+                const float4 r0 = *reinterpret_cast<const float4*>(e.residual + orow * e.ldres + ocol);
+                const float4 r1 = *reinterpret_cast<const float4*>(e.residual + orow * e.ldres + ocol + 4);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+              }
+              if (e.add16) {
+                const uint4 av = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(e.add16) + orow * e.ldadd + ocol);
+                const float2 t0 = TT::unpack2(av.x), t1 = TT::unpack2(av.y), t2 = TT::unpack2(av.z), t3 = TT::unpack2(av.w);
+                f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y; f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(e.out) + orow * e.ldc + ocol) =
+                  make_uint4(TT::pack2(f[0], f[1]), TT::pack2(f[2], f[3]), TT::pack2(f[4], f[5]), TT::pack2(f[6], f[7]));
+            }
+          }
+        }
+      }
+      // this warp is done reading accumulator buffer `buf`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <int BN, bool QKV, typename T>
+static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  auto kern = gemm_tc2_kernel<BN, QKV, T>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmem);
+    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
+  const int sms = num_sms();
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  kern<<<grid, 192, Cfg2<BN>::kSmem, stream>>>(maps, args);
+  return check_launch("gemm_tc2");
+}
+
+int gemm_v2_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+#define B2U_CASE2(Q_, BN_)                                                                        \
+  case BN_:                                                                                       \
+    return dtype == B2U_BF16 ? launch_variant2<BN_, Q_, __nv_bfloat16>(maps, args, stream)        \
+                             : launch_variant2<BN_, Q_, __half>(maps, args, stream);
+  if (qkv) {
+    switch (bn) { B2U_CASE2(true, 128) B2U_CASE2(true, 256) default: break; }
+  } else {
+    switch (bn) { B2U_CASE2(false, 32) B2U_CASE2(false, 64) B2U_CASE2(false, 128) B2U_CASE2(false, 256) default: break; }
+  }
+#undef B2U_CASE2
+  return set_error(-3, "gemm_tc2: unsupported BLOCK_N %d", bn);
+}
+
+}  // namespace b2u

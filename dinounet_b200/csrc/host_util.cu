@@ -5,6 +5,7 @@
 #include <cstdio>
 
 #include "../../include/dinounet_b200.h"
+#include "gemm_common.h"
 
 namespace b2u {
 
@@ -57,6 +58,29 @@ int encode_tensor_map(CUtensorMap* map, int dtype, int rank, const void* base, c
 }
 
 }  // namespace b2u
+
+namespace b2u {
+static int g_options[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int get_option(int key) { return (key >= 0 && key < 8) ? g_options[key] : 0; }
+int num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+}  // namespace b2u
+
+extern "C" int b2u_set_option(int32_t key, int32_t value) {
+  if (key < 0 || key >= 8) return b2u::set_error(-1, "b2u_set_option: bad key %d", key);
+  b2u::g_options[key] = value;
+  return 0;
+}
 
 extern "C" int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream) {
   cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream));

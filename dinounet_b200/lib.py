@@ -76,6 +76,7 @@ SIGNATURES = {
     "b2u_se_apply": [vp, vp, i64, vp, vp, i32, i32, i32, i32, vp],
     "b2u_seg_head": [vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "b2u_zero": [vp, i64, vp],
+    "b2u_set_option": [i32, i32],
     "b2u_last_error": [],
     "b2u_version": [],
     "b2u_launch_count": [],

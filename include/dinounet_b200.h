@@ -190,6 +190,11 @@ int b2u_seg_head(const void* x, const float* sums, const float* gamma, const flo
 /* cudaMemsetAsync(ptr, 0, bytes) on the stream (statistics accumulators must be zeroed every forward). */
 int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream);
 
+/* Tuning / A-B switches.  key 0 (B2U_OPT_GEMM_IMPL): 0 = persistent 128x256-tile tcgen05 kernel (default),
+ * 1 = the first-generation one-tile-per-CTA kernel. */
+enum { B2U_OPT_GEMM_IMPL = 0 };
+int b2u_set_option(int32_t key, int32_t value);
+
 const char* b2u_last_error(void);
 int b2u_version(void);
 /* Number of kernel launches issued through this library since load (bench.py's gpu_launches evidence). */

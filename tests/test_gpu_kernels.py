@@ -15,6 +15,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(params=["v2", "v1"])
+def gemm_impl(request):
+    """Runs the GEMM-family tests on both kernel generations (B2U_OPT_GEMM_IMPL)."""
+    L.load().b2u_set_option(0, 1 if request.param == "v1" else 0)
+    yield request.param
+    L.load().b2u_set_option(0, 0)
+
+
 def _rand(*shape, dt=torch.float32, scale=1.0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
     return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dt)
@@ -22,8 +30,8 @@ def _rand(*shape, dt=torch.float32, scale=1.0, seed=0):
 
 @pytest.mark.parametrize("dtype", [L.BF16, L.F16])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1029, 384, 384), (300, 192, 96), (4096, 32, 32), (777, 64, 256),
-                                   (2058, 1536, 384)])
-def test_gemm_plain(dtype, M, N, K):
+                                   (2058, 1536, 384), (1500, 1024, 512), (20000, 4096, 256)])
+def test_gemm_plain(gemm_impl, dtype, M, N, K):
     td = TD[dtype]
     A, W = _rand(M, K, dt=td), _rand(N, K, dt=td, scale=K ** -0.5, seed=1)
     bias = _rand(N, seed=2)
@@ -36,7 +44,7 @@ def test_gemm_plain(dtype, M, N, K):
     assert rel_err(out, ref) < tol, rel_err(out, ref)
 
 
-def test_gemm_epilogue_residual_scale_gelu_fp32out():
+def test_gemm_epilogue_residual_scale_gelu_fp32out(gemm_impl):
     M, N, K = 1029 * 2, 384, 1536
     dtype, td = L.BF16, torch.bfloat16
     A, W = _rand(M, K, dt=td), _rand(N, K, dt=td, scale=K ** -0.5, seed=1)
@@ -56,7 +64,7 @@ def test_gemm_epilogue_residual_scale_gelu_fp32out():
     assert rel_err(out, ref) < 2 ** -6
 
 
-def test_gemm_row_remap_and_coloffset():
+def test_gemm_row_remap_and_coloffset(gemm_impl):
     B, Pn, Nn, D, K = 3, 64, 69, 128, 64
     dtype, td = L.F16, torch.float16
     A, W = _rand(B * Pn, K, dt=td), _rand(D, K, dt=td, scale=K ** -0.5, seed=1)
@@ -70,7 +78,7 @@ def test_gemm_row_remap_and_coloffset():
 
 
 @pytest.mark.parametrize("cin,cout,hw", [(64, 32, 16), (256, 128, 8), (384, 384, 16)])
-def test_gemm_convtranspose_pixelshuffle(cin, cout, hw):
+def test_gemm_convtranspose_pixelshuffle(gemm_impl, cin, cout, hw):
     B = 2
     dtype, td = L.F16, torch.float16
     x = _rand(B, hw, hw, cin, dt=td)
@@ -98,7 +106,7 @@ def _pack_conv(w, td):
 @pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("cin,cout,hw,B", [(64, 64, 32, 2), (32, 32, 64, 1), (256, 128, 16, 2), (128, 256, 8, 3),
                                            (64, 32, 256, 1)])
-def test_conv3x3_implicit_gemm(stride, cin, cout, hw, B):
+def test_conv3x3_implicit_gemm(gemm_impl, stride, cin, cout, hw, B):
     dtype, td = L.F16, torch.float16
     x = _rand(B, hw, hw, cin, dt=td)
     w = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=1)
@@ -115,7 +123,7 @@ def test_conv3x3_implicit_gemm(stride, cin, cout, hw, B):
 
 
 @pytest.mark.parametrize("dtype", [L.BF16, L.F16])
-def test_qkv_rope_and_attention(dtype):
+def test_qkv_rope_and_attention(gemm_impl, dtype):
     td = TD[dtype]
     B, h, D, Hh = 2, 16, 384, 6
     Pn = h * h
