@@ -1,10 +1,11 @@
 // tcgen05 GEMM / implicit-GEMM 3x3 convolution, v2: persistent, warp-specialised, double-buffered TMEM.
 //
-//   grid = min(#tiles, #SMs) CTAs of 192 threads, one per SM, each looping over output tiles (n fastest, so the CTAs
+//   grid = min(#tiles, #SMs) CTAs of 320 threads, one per SM, each looping over output tiles (n fastest, so the CTAs
 //   running concurrently share A rows through L2):
 //     warp 0   : TMA producer  — 4-stage (BN<=128: 6-stage) ring of {A 128x64, W BNx64} 128B-swizzled tiles
 //     warp 1   : MMA issuer    — one thread issues tcgen05.mma (M=128, N=BN, K=16) into accumulator buffer (tile & 1)
-//     warps 2-5: epilogue      — tcgen05.ld their 32-lane TMEM quarter in 32-column chunks, transpose through a
+//     warps 2-9: epilogue      — two warps per 32-lane TMEM quarter (each takes half of the tile's columns):
+//                                tcgen05.ld in 32-column chunks, transpose through a
 //                                swizzled 4 KB smem patch per warp, then apply the fused epilogue in a row-contiguous
 //                                layout (per-column params are per-lane constants) and issue fully coalesced 16 B
 //                                loads/stores (residual / skip tensors / output).
@@ -22,7 +23,7 @@ template <int BN> struct Cfg2 {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 4 * 4096;        // 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int kStagingBytes = 8 * 4096;        // 8 epilogue warps x (32 rows x 128 B)
   static constexpr int kBiasBytes = BN * 4;
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
@@ -35,10 +36,36 @@ __device__ __forceinline__ float apply_act2(float v, int act) {
   return v;
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): branch-free, 2 MUFU + ~10 FMA (erff() is ~2x that)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float er = 1.0f - p * t * __expf(-ax * ax);   // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(er, x));
+}
+
+template <int NV>
+__device__ __forceinline__ void act_vec(float (&f)[NV], int act) {
+  if (act == B2U_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = gelu_fast(f[j]);
+  } else if (act == B2U_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if (act == B2U_ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) f[j] = f[j] > 0.f ? f[j] : 0.01f * f[j];
+  }
+}
 
 template <int BN, bool QKV, typename T>
-__global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
+__global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
   using C = Cfg2<BN>;
   using TT = T16<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -59,7 +86,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
@@ -136,9 +163,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
     const int q4 = warp & 3;
     const int ew = warp - 2;                         // staging patch index
+    const int half = ew >> 2;                        // which half of the tile's columns this warp drains
     uint8_t* patch = staging + ew * 4096;
     const uint32_t patch_u32 = smem_u32(patch);
     const b2u_epilogue& e = args.epi;
@@ -172,7 +200,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
       if constexpr (QKV) {
         // stage the (masked) bias of this tile's columns once
         epi_bar_sync();
-        for (int i = etid; i < BN; i += 128) s_bias[i] = (e.bias && n0 + i < args.N) ? __ldg(e.bias + n0 + i) : 0.f;
+        for (int i = etid; i < BN; i += 256) s_bias[i] = (e.bias && n0 + i < args.N) ? __ldg(e.bias + n0 + i) : 0.f;
         epi_bar_sync();
         // phase-1 owner row
         long long m1;
@@ -197,7 +225,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
 #pragma unroll 1
-        for (int g = 0; g < BN / 64; ++g) {
+        for (int g = half * (BN / 128); g < (half + 1) * (BN / 128); ++g) {
           uint32_t v0[32], v1r[32];
           tmem_ld32(taddr + g * 64, v0);
           tmem_ld32(taddr + g * 64 + 32, v1r);
@@ -260,6 +288,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
           if (i < npass) {
             long long m;
             rok[i] = row_of(q4 * 32 + i * rpp + lane / lpr, m);
+            if (!rok[i]) m = 0;   // keep addresses in bounds for the unconditional operand prefetch (stores stay predicated)
             if (e.ps_cout > 0) {
               const long long hw = static_cast<long long>(e.ps_h) * e.ps_w;
               const int pb = static_cast<int>(m / hw);
@@ -276,19 +305,16 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
         mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
+        constexpr int kChunks = BN / 32;
+        constexpr int kPerHalf = kChunks >= 2 ? kChunks / 2 : 1;
+        const int ch_begin = kChunks >= 2 ? half * kPerHalf : 0;
+        const int ch_end = kChunks >= 2 ? ch_begin + kPerHalf : (half == 0 ? 1 : 0);
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
           uint32_t v[32];
           tmem_ld32(taddr + ch * 32, v);
-          tmem_ld_wait();
           const int n = n0 + ch * 32;
-          if (n >= args.N) continue;   // warp-uniform
-          // stage raw fp32 accumulators: row = lane, 8 x 16 B groups at position j ^ (row & 7)
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(patch + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
+          const bool live = n < args.N;   // warp-uniform
           int ocol = n + lcol;
           long long radd = 0;
           if (e.ps_cout > 0) {
@@ -297,6 +323,42 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
             radd = static_cast<long long>(qd >> 1) * (2 * e.ps_w) + (qd & 1);
           }
           ocol += e.col_off;
+          // ---- prefetch residual / skip operands for every pass of this chunk (latency overlaps the TMEM load)
+          float4 res[8];
+          uint4 add[4];
+          if (live && e.residual) {
+            if (o32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const float4*>(e.residual + (rbase[i] + radd) * e.ldres + ocol);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                res[2 * i] = *reinterpret_cast<const float4*>(e.residual + (rbase[i] + radd) * e.ldres + ocol);
+                res[2 * i + 1] = *reinterpret_cast<const float4*>(e.residual + (rbase[i] + radd) * e.ldres + ocol + 4);
+              }
+            }
+          }
+          if (live && e.add16) {
+            if (o32) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {   // two passes per register (uint2 each)
+                const uint2 a0 = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(e.add16) + (rbase[2 * i] + radd) * e.ldadd + ocol);
+                const uint2 a1 = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(e.add16) + (rbase[2 * i + 1] + radd) * e.ldadd + ocol);
+                add[i] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) add[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(e.add16) + (rbase[i] + radd) * e.ldadd + ocol);
+            }
+          }
+          tmem_ld_wait();
+          if (!live) continue;
+          // stage raw fp32 accumulators: row = lane, 8 x 16 B groups at position j ^ (row & 7)
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(patch + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
           if (o32) {
             float bi[4] = {0, 0, 0, 0}, sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0};
             if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol)); bi[0] = t.x; bi[1] = t.y; bi[2] = t.z; bi[3] = t.w; }
@@ -306,27 +368,23 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3);
               const float4 a4 = *reinterpret_cast<const float4*>(patch + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-              if (!rok[i]) continue;
-              float f[4] = {a4.x, a4.y, a4.z, a4.w};
+              float f[4] = {a4.x + bi[0], a4.y + bi[1], a4.z + bi[2], a4.w + bi[3]};
+              if (e.round16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float a = f[j] + bi[j];
-                if (e.round16) a = TT::to_f(TT::from_f(a));
-                a = apply_act2(a, e.act1);
-                a = a * sc[j] + sh[j];
-                f[j] = apply_act2(a, e.act2);
+                for (int j = 0; j < 4; ++j) f[j] = TT::to_f(TT::from_f(f[j]));
               }
-              const long long orow = rbase[i] + radd;
-              if (e.residual) {
-                const float4 rv = *reinterpret_cast<const float4*>(e.residual + orow * e.ldres + ocol);
-                f[0] += rv.x; f[1] += rv.y; f[2] += rv.z; f[3] += rv.w;
-              }
+              act_vec<4>(f, e.act1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+              act_vec<4>(f, e.act2);
+              if (e.residual) { f[0] += res[i].x; f[1] += res[i].y; f[2] += res[i].z; f[3] += res[i].w; }
               if (e.add16) {
-                const uint2 av = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(e.add16) + orow * e.ldadd + ocol);
-                const float2 t0 = TT::unpack2(av.x), t1 = TT::unpack2(av.y);
+                const uint4 pr = add[i >> 1];
+                const float2 t0 = TT::unpack2((i & 1) ? pr.z : pr.x), t1 = TT::unpack2((i & 1) ? pr.w : pr.y);
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
               }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + orow * e.ldc + ocol) = make_float4(f[0], f[1], f[2], f[3]);
+              if (rok[i])
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (rbase[i] + radd) * e.ldc + ocol) = make_float4(f[0], f[1], f[2], f[3]);
             }
           } else {
             float bi[8], sc[8], sh[8];
@@ -350,29 +408,26 @@ __global__ void __launch_bounds__(192, 1) gemm_tc2_kernel(const __grid_constant_
               const int g0 = (lane & 3) * 2;
               const float4 a4 = *reinterpret_cast<const float4*>(patch + rr * 128 + ((g0 ^ (rr & 7)) << 4));
               const float4 b4 = *reinterpret_cast<const float4*>(patch + rr * 128 + (((g0 + 1) ^ (rr & 7)) << 4));
-              if (!rok[i]) continue;
-              float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+              float f[8] = {a4.x + bi[0], a4.y + bi[1], a4.z + bi[2], a4.w + bi[3], b4.x + bi[4], b4.y + bi[5], b4.z + bi[6], b4.w + bi[7]};
+              if (e.round16) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a = f[j] + bi[j];
-                if (e.round16) a = TT::to_f(TT::from_f(a));
-                a = apply_act2(a, e.act1);
-                a = a * sc[j] + sh[j];
-                f[j] = apply_act2(a, e.act2);
+                for (int j = 0; j < 8; ++j) f[j] = TT::to_f(TT::from_f(f[j]));
               }
-              const long long orow = rbase[i] + radd;
+              act_vec<8>(f, e.act1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+              act_vec<8>(f, e.act2);
               if (e.residual) {
-                const float4 r0 = *reinterpret_cast<const float4*>(e.residual + orow * e.ldres + ocol);
-                const float4 r1 = *reinterpret_cast<const float4*>(e.residual + orow * e.ldres + ocol + 4);
-                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                f[0] += res[2 * i].x; f[1] += res[2 * i].y; f[2] += res[2 * i].z; f[3] += res[2 * i].w;
+                f[4] += res[2 * i + 1].x; f[5] += res[2 * i + 1].y; f[6] += res[2 * i + 1].z; f[7] += res[2 * i + 1].w;
               }
               if (e.add16) {
-                const uint4 av = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(e.add16) + orow * e.ldadd + ocol);
-                const float2 t0 = TT::unpack2(av.x), t1 = TT::unpack2(av.y), t2 = TT::unpack2(av.z), t3 = TT::unpack2(av.w);
+                const float2 t0 = TT::unpack2(add[i].x), t1 = TT::unpack2(add[i].y), t2 = TT::unpack2(add[i].z), t3 = TT::unpack2(add[i].w);
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y; f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
-              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(e.out) + orow * e.ldc + ocol) =
-                  make_uint4(TT::pack2(f[0], f[1]), TT::pack2(f[2], f[3]), TT::pack2(f[4], f[5]), TT::pack2(f[6], f[7]));
+              if (rok[i])
+                *reinterpret_cast<uint4*>(reinterpret_cast<T*>(e.out) + (rbase[i] + radd) * e.ldc + ocol) =
+                    make_uint4(TT::pack2(f[0], f[1]), TT::pack2(f[2], f[3]), TT::pack2(f[4], f[5]), TT::pack2(f[6], f[7]));
             }
           }
         }
@@ -404,7 +459,7 @@ static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStrea
   const long long tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
   const int sms = num_sms();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kern<<<grid, 192, Cfg2<BN>::kSmem, stream>>>(maps, args);
+  kern<<<grid, 320, Cfg2<BN>::kSmem, stream>>>(maps, args);
   return check_launch("gemm_tc2");
 }
 
