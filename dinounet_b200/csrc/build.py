@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "attention.cu", "elementwise.cu", "msda.cu", "host_util.cu"]
+SOURCES = ["gemm_tc.cu", ("gemm_tc2.cu", "gemm_tc2_bf16.o", ["-DB2U_GEMM2_TYPE=1"]), ("gemm_tc2.cu", "gemm_tc2_f16.o", ["-DB2U_GEMM2_TYPE=0"]), "attention.cu", "elementwise.cu", "msda.cu", "host_util.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libdinounet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -26,14 +26,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
     for s in SOURCES:
+        extra = []
+        if isinstance(s, tuple):
+            s, oname, extra = s
+        else:
+            oname = s.replace(".cu", ".o")
         src = os.path.join(HERE, s)
-        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        obj = os.path.join(objdir, oname)
         objs.append(obj)
         if force or _stale(obj, src):
-            cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+            cmd = [NVCC, *FLAGS, *extra, "-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
-            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            procs.append((oname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     relink = force or bool(procs) or not os.path.exists(OUT)
     for s, p in procs:
         out, _ = p.communicate()

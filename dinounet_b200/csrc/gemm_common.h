@@ -36,7 +36,12 @@ struct GemmArgs {
 
 int num_sms();
 int gemm_v1_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
-int gemm_v2_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
+int gemm_v2_dispatch_bf16(bool qkv, int bn, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
+int gemm_v2_dispatch_f16(bool qkv, int bn, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
+inline int gemm_v2_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  return dtype == B2U_BF16 ? gemm_v2_dispatch_bf16(qkv, bn, maps, args, stream)
+                           : gemm_v2_dispatch_f16(qkv, bn, maps, args, stream);
+}
 int get_option(int key);
 
 }  // namespace b2u

@@ -38,10 +38,28 @@ __device__ __forceinline__ float apply_act2(float v, int act) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  const uint4 r = lds128(addr);
+  return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): branch-free, 2 MUFU + ~10 FMA (erff() is ~2x that)
 __device__ __forceinline__ float gelu_fast(float x) {
   const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -50,8 +68,9 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(er, x));
 }
 
-template <int NV>
-__device__ __forceinline__ void act_vec(float (&f)[NV], int act) {
+template <int ACT, int NV>
+__device__ __forceinline__ void act_vec(float (&f)[NV]) {
+  constexpr int act = ACT;
   if (act == B2U_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) f[j] = gelu_fast(f[j]);
@@ -64,7 +83,9 @@ __device__ __forceinline__ void act_vec(float (&f)[NV], int act) {
   }
 }
 
-template <int BN, bool QKV, typename T>
+// EPI: 0 = generic 16-bit out, 1 = generic fp32 out, 2 = QKV(+RoPE, head split).  ACT1 / ACT2: compile-time activations
+// after the bias / after the affine (B2U_ACT_*), so the fully unrolled epilogue stays small enough for the I-cache.
+template <int BN, int EPI, int ACT1, int ACT2, typename T>
 __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
   using C = Cfg2<BN>;
   using TT = T16<T>;
@@ -197,7 +218,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         return (y < args.Ho) && (x < args.Wo);
       };
 
-      if constexpr (QKV) {
+      if constexpr (EPI == 2) {
         // stage the (masked) bias of this tile's columns once
         epi_bar_sync();
         for (int i = etid; i < BN; i += 256) s_bias[i] = (e.bias && n0 + i < args.N) ? __ldg(e.bias + n0 + i) : 0.f;
@@ -259,22 +280,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(patch + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            sts128(patch_u32 + lane * 128 + ((c ^ (lane & 7)) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
           __syncwarp();
           T* base = reinterpret_cast<T*>(which == 0 ? args.q : (which == 1 ? args.k : args.v)) +
                     static_cast<long long>(head) * args.ntok * 64 + (lane & 7) * 8;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + (lane >> 3);
-            const uint4 val = *reinterpret_cast<const uint4*>(patch + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            const uint4 val = lds128(patch_u32 + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
             if (dst_ok[i]) *reinterpret_cast<uint4*>(base + dst_off[i]) = val;
           }
         }
       } else {
         // ---- phase-2 row assignment: fp32 output -> 8 lanes per row (4 cols each), 4 rows per pass, 8 passes;
         //                              16-bit output -> 4 lanes per row (8 cols each), 8 rows per pass, 4 passes.
-        const bool o32 = e.out_fp32 != 0;
+        constexpr bool o32 = (EPI == 1);
         const int lpr = o32 ? 8 : 4;                 // lanes per row
         const int rpp = 32 / lpr;                    // rows per pass
         const int npass = 32 / rpp;
@@ -289,14 +309,16 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             long long m;
             rok[i] = row_of(q4 * 32 + i * rpp + lane / lpr, m);
             if (!rok[i]) m = 0;   // keep addresses in bounds for the unconditional operand prefetch (stores stay predicated)
+            const unsigned mu = static_cast<unsigned>(m);   // logical row counts fit 32 bits (checked on the host)
             if (e.ps_cout > 0) {
-              const long long hw = static_cast<long long>(e.ps_h) * e.ps_w;
-              const int pb = static_cast<int>(m / hw);
-              const int rem = static_cast<int>(m - pb * hw);
-              const int pi = rem / e.ps_w, pj = rem - pi * e.ps_w;
+              const unsigned hw = static_cast<unsigned>(e.ps_h) * e.ps_w;
+              const unsigned pb = mu / hw;
+              const unsigned rem = mu - pb * hw;
+              const unsigned pi = rem / e.ps_w, pj = rem - pi * e.ps_w;
               rbase[i] = (static_cast<long long>(pb) * (2 * e.ps_h) + 2 * pi) * (2 * e.ps_w) + 2 * pj;
             } else if (e.rows_in > 0) {
-              rbase[i] = (m / e.rows_in) * e.rows_out + e.row_off + (m % e.rows_in);
+              const unsigned qb = mu / static_cast<unsigned>(e.rows_in);
+              rbase[i] = static_cast<long long>(qb) * e.rows_out + e.row_off + (mu - qb * e.rows_in);
             } else {
               rbase[i] = m;
             }
@@ -351,32 +373,41 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
               for (int i = 0; i < 4; ++i) add[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(e.add16) + (rbase[i] + radd) * e.ldadd + ocol);
             }
           }
+          // per-column parameters of this lane (constant over the rows): loaded before the TMEM wait
+          constexpr int NV = o32 ? 4 : 8;
+          float bi[NV], sc[NV], sh[NV];
+#pragma unroll
+          for (int j = 0; j < NV; ++j) { bi[j] = 0.f; sc[j] = 1.f; sh[j] = 0.f; }
+          if (live) {
+#pragma unroll
+            for (int h = 0; h < NV / 4; ++h) {
+              if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol + 4 * h)); bi[4 * h] = t.x; bi[4 * h + 1] = t.y; bi[4 * h + 2] = t.z; bi[4 * h + 3] = t.w; }
+              if (e.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.scale + n + lcol + 4 * h)); sc[4 * h] = t.x; sc[4 * h + 1] = t.y; sc[4 * h + 2] = t.z; sc[4 * h + 3] = t.w; }
+              if (e.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.shift + n + lcol + 4 * h)); sh[4 * h] = t.x; sh[4 * h + 1] = t.y; sh[4 * h + 2] = t.z; sh[4 * h + 3] = t.w; }
+            }
+          }
           tmem_ld_wait();
           if (!live) continue;
           // stage raw fp32 accumulators: row = lane, 8 x 16 B groups at position j ^ (row & 7)
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(patch + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            sts128(patch_u32 + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
-          if (o32) {
-            float bi[4] = {0, 0, 0, 0}, sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0};
-            if (e.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol)); bi[0] = t.x; bi[1] = t.y; bi[2] = t.z; bi[3] = t.w; }
-            if (e.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.scale + n + lcol)); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
-            if (e.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(e.shift + n + lcol)); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
+          if constexpr (o32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3);
-              const float4 a4 = *reinterpret_cast<const float4*>(patch + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+              const float4 a4 = lds128f(patch_u32 + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
               float f[4] = {a4.x + bi[0], a4.y + bi[1], a4.z + bi[2], a4.w + bi[3]};
               if (e.round16) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) f[j] = TT::to_f(TT::from_f(f[j]));
               }
-              act_vec<4>(f, e.act1);
+              act_vec<ACT1, 4>(f);
 #pragma unroll
               for (int j = 0; j < 4; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-              act_vec<4>(f, e.act2);
+              act_vec<ACT2, 4>(f);
               if (e.residual) { f[0] += res[i].x; f[1] += res[i].y; f[2] += res[i].z; f[3] += res[i].w; }
               if (e.add16) {
                 const uint4 pr = add[i >> 1];
@@ -387,36 +418,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (rbase[i] + radd) * e.ldc + ocol) = make_float4(f[0], f[1], f[2], f[3]);
             }
           } else {
-            float bi[8], sc[8], sh[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { bi[j] = 0.f; sc[j] = 1.f; sh[j] = 0.f; }
-            if (e.bias) {
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol)), t1 = __ldg(reinterpret_cast<const float4*>(e.bias + n + lcol + 4));
-              bi[0] = t0.x; bi[1] = t0.y; bi[2] = t0.z; bi[3] = t0.w; bi[4] = t1.x; bi[5] = t1.y; bi[6] = t1.z; bi[7] = t1.w;
-            }
-            if (e.scale) {
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(e.scale + n + lcol)), t1 = __ldg(reinterpret_cast<const float4*>(e.scale + n + lcol + 4));
-              sc[0] = t0.x; sc[1] = t0.y; sc[2] = t0.z; sc[3] = t0.w; sc[4] = t1.x; sc[5] = t1.y; sc[6] = t1.z; sc[7] = t1.w;
-            }
-            if (e.shift) {
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(e.shift + n + lcol)), t1 = __ldg(reinterpret_cast<const float4*>(e.shift + n + lcol + 4));
-              sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
-            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = i * 8 + (lane >> 2);
               const int g0 = (lane & 3) * 2;
-              const float4 a4 = *reinterpret_cast<const float4*>(patch + rr * 128 + ((g0 ^ (rr & 7)) << 4));
-              const float4 b4 = *reinterpret_cast<const float4*>(patch + rr * 128 + (((g0 + 1) ^ (rr & 7)) << 4));
+              const float4 a4 = lds128f(patch_u32 + rr * 128 + ((g0 ^ (rr & 7)) << 4));
+              const float4 b4 = lds128f(patch_u32 + rr * 128 + (((g0 + 1) ^ (rr & 7)) << 4));
               float f[8] = {a4.x + bi[0], a4.y + bi[1], a4.z + bi[2], a4.w + bi[3], b4.x + bi[4], b4.y + bi[5], b4.z + bi[6], b4.w + bi[7]};
               if (e.round16) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = TT::to_f(TT::from_f(f[j]));
               }
-              act_vec<8>(f, e.act1);
+              act_vec<ACT1, 8>(f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-              act_vec<8>(f, e.act2);
+              act_vec<ACT2, 8>(f);
               if (e.residual) {
                 f[0] += res[2 * i].x; f[1] += res[2 * i].y; f[2] += res[2 * i].z; f[3] += res[2 * i].w;
                 f[4] += res[2 * i + 1].x; f[5] += res[2 * i + 1].y; f[6] += res[2 * i + 1].z; f[7] += res[2 * i + 1].w;
@@ -447,9 +463,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <int BN, bool QKV, typename T>
+template <int BN, int EPI, int ACT1, int ACT2, typename T>
 static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
-  auto kern = gemm_tc2_kernel<BN, QKV, T>;
+  auto kern = gemm_tc2_kernel<BN, EPI, ACT1, ACT2, T>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmem);
@@ -463,18 +479,49 @@ static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStrea
   return check_launch("gemm_tc2");
 }
 
-int gemm_v2_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
-#define B2U_CASE2(Q_, BN_)                                                                        \
-  case BN_:                                                                                       \
-    return dtype == B2U_BF16 ? launch_variant2<BN_, Q_, __nv_bfloat16>(maps, args, stream)        \
-                             : launch_variant2<BN_, Q_, __half>(maps, args, stream);
+template <int BN, typename T>
+static int dispatch_epi(bool qkv, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
   if (qkv) {
-    switch (bn) { B2U_CASE2(true, 128) B2U_CASE2(true, 256) default: break; }
-  } else {
-    switch (bn) { B2U_CASE2(false, 32) B2U_CASE2(false, 64) B2U_CASE2(false, 128) B2U_CASE2(false, 256) default: break; }
+    if constexpr (BN >= 128) return launch_variant2<BN, 2, 0, 0, T>(maps, args, stream);
+    else return set_error(-3, "gemm_tc2: QKV epilogue needs BLOCK_N >= 128");
   }
-#undef B2U_CASE2
+  const int a1 = args.epi.act1, a2 = args.epi.act2;
+  if (args.epi.out_fp32) {
+    if (a1 == 0 && a2 == 0) return launch_variant2<BN, 1, 0, 0, T>(maps, args, stream);
+  } else {
+    if (a1 == 0 && a2 == 0) return launch_variant2<BN, 0, 0, 0, T>(maps, args, stream);
+    if (a1 == B2U_ACT_GELU && a2 == 0) return launch_variant2<BN, 0, B2U_ACT_GELU, 0, T>(maps, args, stream);
+    if (a1 == 0 && a2 == B2U_ACT_RELU) return launch_variant2<BN, 0, 0, B2U_ACT_RELU, T>(maps, args, stream);
+    if (a1 == 0 && a2 == B2U_ACT_LRELU) return launch_variant2<BN, 0, 0, B2U_ACT_LRELU, T>(maps, args, stream);
+  }
+  return set_error(-3, "gemm_tc2: epilogue combination (out_fp32=%d, act1=%d, act2=%d) is not instantiated",
+                   args.epi.out_fp32, a1, a2);
+}
+
+template <typename T>
+int gemm_v2_dispatch_t(bool qkv, int bn, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  if (args.M < 0) return set_error(-1, "gemm_tc2: M too large");
+  switch (bn) {
+    case 32: return dispatch_epi<32, T>(qkv, maps, args, stream);
+    case 64: return dispatch_epi<64, T>(qkv, maps, args, stream);
+    case 128: return dispatch_epi<128, T>(qkv, maps, args, stream);
+    case 256: return dispatch_epi<256, T>(qkv, maps, args, stream);
+    default: break;
+  }
   return set_error(-3, "gemm_tc2: unsupported BLOCK_N %d", bn);
 }
+
+#ifndef B2U_GEMM2_TYPE
+#error "compile gemm_tc2.cu once per 16-bit type with -DB2U_GEMM2_TYPE=0 (fp16) / 1 (bf16)"
+#endif
+#if B2U_GEMM2_TYPE == 1
+int gemm_v2_dispatch_bf16(bool qkv, int bn, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  return gemm_v2_dispatch_t<__nv_bfloat16>(qkv, bn, maps, args, stream);
+}
+#else
+int gemm_v2_dispatch_f16(bool qkv, int bn, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  return gemm_v2_dispatch_t<__half>(qkv, bn, maps, args, stream);
+}
+#endif
 
 }  // namespace b2u

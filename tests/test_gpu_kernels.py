@@ -120,6 +120,14 @@ def test_conv3x3_implicit_gemm(gemm_impl, stride, cin, cout, hw, B):
     got = out.view(B, ho, ho, cout).permute(0, 3, 1, 2).float()
     assert torch.isfinite(got).all()
     assert rel_err(got, ref) < 2e-3, rel_err(got, ref)
+    # folded-BN + ReLU epilogue (SPM: dinov3_adapter.py:241-273)
+    sc, sh = _rand(cout, seed=5).abs() + 0.5, _rand(cout, seed=6)
+    gemm(x.view(-1, cin), _pack_conv(w, td), out, dtype, M=0, K=9 * cin, lda=cin, scale=sc, shift=sh, act2=L.ACT_RELU,
+         conv=L.CONV3X3_S2 if stride == 2 else L.CONV3X3_S1, img=(B, hw, hw, cin))
+    torch.cuda.synchronize()
+    ref2 = F.relu((ref - bias[None, :, None, None]).half().float() * sc[None, :, None, None] + sh[None, :, None, None])
+    got = out.view(B, ho, ho, cout).permute(0, 3, 1, 2).float()
+    assert rel_err(got, ref2) < 3e-3, rel_err(got, ref2)
 
 
 @pytest.mark.parametrize("dtype", [L.BF16, L.F16])

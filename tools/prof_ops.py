@@ -1,0 +1,56 @@
+"""Standalone launches of the hot kernels at dinounet_l / B=32 / 512^2 shapes, for ncu captures:
+   ncu --set full --import-source on -k regex:<kernel> ... python tools/prof_ops.py <op> [reps]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dinounet_b200 import lib as L  # noqa: E402
+from tests.gpu_helpers import P, gemm, stream  # noqa: E402
+
+op = sys.argv[1] if len(sys.argv) > 1 else "fc1"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+lib = L.load()
+dev = "cuda"
+T, D, Hd = 32 * 1029, 1024, 4096
+bf = torch.bfloat16
+g = torch.Generator().manual_seed(0)
+rnd = lambda *s, dt=bf, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev).to(dt)
+
+if op in ("fc1", "fc2", "proj"):
+    if op == "fc1":
+        A, W, bias = rnd(T, D), rnd(Hd, D, sc=D ** -0.5), rnd(Hd, dt=torch.float32)
+        out = torch.empty(T, Hd, device=dev, dtype=bf)
+        run = lambda: gemm(A, W, out, L.BF16, bias=bias, act1=L.ACT_GELU)
+    elif op == "fc2":
+        A, W, bias = rnd(T, Hd), rnd(D, Hd, sc=Hd ** -0.5), rnd(D, dt=torch.float32)
+        X, ls = rnd(T, D, dt=torch.float32), rnd(D, dt=torch.float32)
+        run = lambda: gemm(A, W, X, L.BF16, out_fp32=True, bias=bias, scale=ls, residual=X, ldres=D)
+    else:
+        A, W, bias = rnd(T, D), rnd(D, D, sc=D ** -0.5), rnd(D, dt=torch.float32)
+        X, ls = rnd(T, D, dt=torch.float32), rnd(D, dt=torch.float32)
+        run = lambda: gemm(A, W, X, L.BF16, out_fp32=True, bias=bias, scale=ls, residual=X, ldres=D)
+elif op == "attn":
+    q, k, v = (rnd(32, 16, 1029, 64) for _ in range(3))
+    o = torch.empty(32, 1029, 1024, device=dev, dtype=bf)
+    run = lambda: L.check(lib.b2u_attention(P(q), P(k), P(v), P(o), 32, 16, 1029, 0.125, L.BF16, stream()), "attn")
+elif op == "conv":   # decoder 512^2 conv 64 -> 32
+    x = rnd(32 * 512 * 512, 64, dt=torch.float16)
+    w = rnd(32, 9 * 64, dt=torch.float16, sc=0.05)
+    bias = rnd(32, dt=torch.float32)
+    out = torch.empty(32 * 512 * 512, 32, device=dev, dtype=torch.float16)
+    run = lambda: gemm(x, w, out, L.F16, M=0, K=9 * 64, lda=64, bias=bias, conv=L.CONV3X3_S1, img=(32, 512, 512, 64))
+else:
+    raise SystemExit("unknown op")
+
+for _ in range(reps):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    run()
+e1.record()
+torch.cuda.synchronize()
+print(f"{op}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us / launch")
