@@ -137,6 +137,7 @@ def main():
     os.environ.setdefault("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "1")
     import dinounet_b200
     from dinounet_b200 import config, lib
+    from dinounet_b200.parallel import gather_logits
     from oracle import dinounet_oracle as O   # synthetic weights/inputs + FLOP model + cpu_baseline only
 
     rank = int(os.environ.get("RANK", "0"))
@@ -164,13 +165,12 @@ def main():
     # three resident input batches (3 x 100 MB at B=32 > 126 MB L2) rotated between steps; the per-step activation
     # working set (GBs) is itself >> L2, so no step starts with a warm cache.
     xs = [O.make_input(B, S, 100 + rank * 7 + i).to(dev) for i in range(3)]
-    gathered = torch.empty((world,) + tuple(bufs["logits"].shape), device=dev) if world > 1 else None
     use_graph = not a.no_graph
 
     def step(i):
         logits, _ = eng.forward(xs[i % 3], use_graph=use_graph)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, logits)
+            return gather_logits(logits, B * world)      # the ONE collective of the step (NCCL all-gather)
         return logits
 
     with torch.no_grad():
@@ -209,7 +209,7 @@ def main():
         for i in range(K):
             y = net(hx[i % 2].to(dev, non_blocking=True))
             if world > 1:
-                dist.all_gather_into_tensor(gathered, y)
+                gather_logits(y, B * world)
             hy.copy_(y, non_blocking=True)
             torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], device=dev)

@@ -1,0 +1,47 @@
+"""Batch-sharded inference across the GPUs of one box (BASELINE config 4).
+
+The forward path shards trivially: every patch is independent in eval mode (BatchNorm uses running statistics,
+InstanceNorm is per sample), so each rank runs its contiguous slice of the batch on replicated weights and the step
+ends with ONE all-gather of the logits (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests).  No collective
+exists inside the forward.  This does not exist in the reference (its predictor is batch-1 per tile,
+predict_from_raw_data.py:601-608); it is the new surface the north star asks for.
+"""
+from typing import Callable, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(batch: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, as-even-as-possible slice [lo, hi) of a global batch for `rank` (first `batch % world` ranks get +1)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_logits(local: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
+    """All-gather per-rank logits [b_r, C, H, W] (b_r from shard_bounds) into [global_batch, C, H, W] on every rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(global_batch, world, r) for r in range(world)]
+    per = max(hi - lo for lo, hi in sizes)
+    if all(hi - lo == per for lo, hi in sizes):           # even split: a single all_gather_into_tensor
+        out = local.new_empty((global_batch,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = local.new_zeros((per,) + tuple(local.shape[1:]))  # ragged split: pad to the largest shard, then trim
+    pad[: local.shape[0]] = local
+    buf = local.new_empty((world * per,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    return torch.cat([buf[r * per: r * per + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
+
+
+def sharded_forward(forward: Callable[[torch.Tensor], torch.Tensor], x_global: torch.Tensor, group=None) -> torch.Tensor:
+    """Run `forward` on this rank's slice of `x_global` and return the gathered logits of the whole batch."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(x_global.shape[0], world, rank)
+    return gather_logits(forward(x_global[lo:hi]), x_global.shape[0], group)

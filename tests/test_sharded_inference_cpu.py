@@ -1,0 +1,59 @@
+"""CPU, world_size 2, gloo: the N>1 path (batch sharding + one logits all-gather, dinounet_b200/parallel.py).
+The per-rank forward is a stand-in (the kernels need a GPU); what is tested is the host logic the 8-GPU run uses."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dinounet_b200.parallel import gather_logits, shard_bounds, sharded_forward
+
+
+def test_shard_bounds_cover_batch_exactly():
+    for B in (1, 2, 7, 32, 256):
+        for W in (1, 2, 3, 8):
+            spans = [shard_bounds(B, W, r) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(8, 2, 2)
+
+
+def _fake_forward(x):  # stand-in "network": per-sample deterministic function, [b,3,H,W] -> [b,2,H,W]
+    return torch.stack([x.sum(1), x.mean(1) * 2.0], 1)
+
+
+def _worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(B, 3, 8, 8, generator=g)
+        full = sharded_forward(_fake_forward, x)
+        ok = torch.equal(full, _fake_forward(x))
+        lo, hi = shard_bounds(B, world, rank)
+        ok = ok and torch.equal(gather_logits(_fake_forward(x[lo:hi]), B), _fake_forward(x))
+        q.put((rank, bool(ok), tuple(full.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [4, 5])
+def test_two_rank_gloo_gather_matches_single_process(B):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(shape == (B, 2, 8, 8) for _, _, shape in res)
