@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--rest-dtype", default="fp16")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--gemm-impl", default="v2", choices=["v1", "v2"])
+    ap.add_argument("--attn-impl", default="tc", choices=["tc", "mma"])
     ap.add_argument("--cpu-sample", type=int, default=2, help="patches in the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--ops-out", default="", help="write the per-kernel timing breakdown (JSON) here")
     return ap.parse_args()
@@ -156,7 +157,7 @@ def main():
     sd = O.make_state_dict(a.model, 2, seed=0)
     net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, a.model)
     net.load_state_dict(sd, strict=True)
-    net.vit_dtype, net.rest_dtype = a.vit_dtype, a.rest_dtype
+    net.vit_dtype, net.rest_dtype, net.attn_impl = a.vit_dtype, a.rest_dtype, a.attn_impl
     net = net.to(dev).eval()
     del sd
     eng = net._get_engine(dev)

@@ -1,0 +1,371 @@
+// tcgen05 / TMEM flash attention for the DINOv3 ViT (head_dim 64, non-causal, ntok = 1029 at 512^2).
+//
+// Persistent CTAs (1 per SM, 320 threads); one work item = (batch*head, pair of 128-row query tiles):
+//   warp 0    : TMA producer — Q tiles (once per item), K chunk [128 keys x 64] + V^T chunk [64 x 128 keys], 3-stage ring
+//   warp 1    : MMA issuer   — S_g = Q_g K^T  (M128 N128 K64, 4 x tcgen05.mma) into TMEM,
+//                              O_g[j&1] = P_g V (M128 N64 K128, 8 x tcgen05.mma) into a double-buffered TMEM chunk
+//   warps 2-5 : softmax group A (query tile 0), warps 6-9: softmax group B (query tile 1), one thread per query row:
+//               pass 1 tcgen05.ld S -> row max; pass 2 tcgen05.ld S -> exp2 -> 16-bit P into 128B-swizzled smem
+//               (the A operand of the PV MMA); then absorb the previous chunk's P V product from TMEM into fp32
+//               registers with the online-softmax correction.  While group A does softmax the tensor core works for B.
+// Every MMA operand is K-major SW128 (the layout the GEMM kernel already uses): V is consumed as V^T [B,H,64,npad]
+// (written transposed by the QKV epilogue), so no MN-major descriptors are needed.  TMEM: S 2x128 + O 2x2x64 = 512 cols.
+// Replaces F.scaled_dot_product_attention at dinounet/dinov3/layers/attention.py:116.
+#include "common.cuh"
+#include "../../include/dinounet_b200.h"
+#include "host_util.h"
+#include "gemm_common.h"
+
+namespace b2u {
+
+struct alignas(64) AttnMaps {
+  CUtensorMap q, k, vt;
+};
+struct AttnArgs {
+  int BH, heads, ntok, npairs, nchunks;
+  long long items;
+  float scale_log2e;
+  void* out;
+};
+
+constexpr int AT_STAGES = 3;
+constexpr int AT_QBYTES = 128 * 128;        // 128 rows x 64 x 2B
+constexpr int AT_PBYTES = 2 * 128 * 128;    // two K-blocks of [128 x 64]
+constexpr int AT_KBYTES = 128 * 128;
+constexpr int AT_VBYTES = 2 * 64 * 128;     // two K-blocks of [64 x 64]
+constexpr int AT_SMEM = 2 * AT_QBYTES + 2 * AT_PBYTES + AT_STAGES * (AT_KBYTES + AT_VBYTES) + 1024 + 256;
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void sts128a(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128a(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ float ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
+  using TT = T16<T>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // [2][16 KB]
+  uint8_t* sP = sQ + 2 * AT_QBYTES;                 // [2][32 KB]
+  uint8_t* sK = sP + 2 * AT_PBYTES;                 // [stages][16 KB]
+  uint8_t* sV = sK + AT_STAGES * AT_KBYTES;         // [stages][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_STAGES * AT_VBYTES);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_free = q_full + 2;           // [2]
+  uint64_t* kv_full = q_free + 2;          // [stages]
+  uint64_t* kv_empty = kv_full + AT_STAGES;
+  uint64_t* s_full = kv_empty + AT_STAGES; // [2]
+  uint64_t* s_free = s_full + 2;           // [2]
+  uint64_t* p_full = s_free + 2;           // [2]
+  uint64_t* o_full = p_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.vt);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&q_full[g], 1); mbar_init(&q_free[g], 1);
+      mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 128);
+      mbar_init(&p_full[g], 128); mbar_init(&o_full[g], 1);
+    }
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S_g at g*128 ; O_g[buf] at 256 + g*128 + buf*64
+  const int J = args.nchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t kv_phase = 0;
+      uint32_t qfree_cnt[2] = {0, 0};
+      for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
+        const int bh = static_cast<int>(item / args.npairs);
+        const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
+        for (int g = 0; g < 2; ++g) {
+          const int q0 = (pair * 2 + g) * 128;
+          if (q0 >= args.ntok) continue;
+          mbar_wait(&q_free[g], (qfree_cnt[g] & 1) ^ 1);
+          ++qfree_cnt[g];
+          mbar_expect_tx(&q_full[g], AT_QBYTES);
+          tma_load_3d(sQ + g * AT_QBYTES, &maps.q, &q_full[g], 0, q0, bh);
+        }
+        for (int j = 0; j < J; ++j) {
+          mbar_wait(&kv_empty[stage], kv_phase ^ 1);
+          mbar_expect_tx(&kv_full[stage], AT_KBYTES + AT_VBYTES);
+          tma_load_3d(sK + stage * AT_KBYTES, &maps.k, &kv_full[stage], 0, j * 128, bh);
+          tma_load_3d(sV + stage * AT_VBYTES, &maps.vt, &kv_full[stage], j * 128, 0, bh);
+          tma_load_3d(sV + stage * AT_VBYTES + 64 * 128, &maps.vt, &kv_full[stage], j * 128 + 64, 0, bh);
+          if (++stage == AT_STAGES) { stage = 0; kv_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(TT::kFmt, 128, 128);
+      constexpr uint32_t idesc_o = make_idesc_f16(TT::kFmt, 128, 64);
+      int stage = 0;
+      uint32_t kv_phase = 0;
+      uint32_t qfull_cnt[2] = {0, 0}, sfree_cnt[2] = {0, 0}, pfull_cnt[2] = {0, 0};
+      auto issue_s = [&](int g, int st) {
+        mbar_wait(&s_free[g], (sfree_cnt[g] & 1) ^ 1);   // softmax g has finished reading the previous S_g
+        ++sfree_cnt[g];
+        tc_fence_after();
+        const uint64_t da = make_desc_k128(smem_u32(sQ + g * AT_QBYTES));
+        const uint64_t db = make_desc_k128(smem_u32(sK + st * AT_KBYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tmem_base + g * 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(&s_full[g]);
+      };
+      for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
+        const int bh = static_cast<int>(item / args.npairs);
+        const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
+        const int nq = ((pair * 2 + 1) * 128 < args.ntok) ? 2 : 1;
+        for (int g = 0; g < nq; ++g) { mbar_wait(&q_full[g], qfull_cnt[g] & 1); ++qfull_cnt[g]; }
+        // S(0)
+        mbar_wait(&kv_full[stage], kv_phase);
+        tc_fence_after();
+        for (int g = 0; g < nq; ++g) issue_s(g, stage);
+        for (int j = 0; j < J; ++j) {
+          int nstage = stage + 1;
+          uint32_t nphase = kv_phase;
+          if (nstage == AT_STAGES) { nstage = 0; nphase ^= 1; }
+          for (int g = 0; g < nq; ++g) {
+            mbar_wait(&p_full[g], pfull_cnt[g] & 1);
+            ++pfull_cnt[g];
+            tc_fence_after();
+            const uint32_t tO = tmem_base + 256 + g * 128 + (j & 1) * 64;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t da = make_desc_k128(smem_u32(sP + g * AT_PBYTES + kb * 128 * 128));
+              const uint64_t db = make_desc_k128(smem_u32(sV + stage * AT_VBYTES + kb * 64 * 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_f16(tO, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_o, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&o_full[g]);
+            if (j + 1 < J) {
+              if (g == 0) { mbar_wait(&kv_full[nstage], nphase); tc_fence_after(); }
+              issue_s(g, nstage);
+            }
+          }
+          tc_commit(&kv_empty[stage]);   // K_j / V_j are free once every MMA issued so far has retired
+          stage = nstage;
+          kv_phase = nphase;
+        }
+        for (int g = 0; g < nq; ++g) tc_commit(&q_free[g]);
+      }
+    }
+  } else {
+    // ===================== softmax / output warps =====================
+    const int g = (warp - 2) >> 2;          // query tile of the pair
+    const int q4 = warp & 3;                // TMEM lane quarter
+    const int row = q4 * 32 + lane;
+    const uint32_t tS = tmem_base + g * 128 + (static_cast<uint32_t>(q4 * 32) << 16);
+    const uint32_t tO = tmem_base + 256 + g * 128 + (static_cast<uint32_t>(q4 * 32) << 16);
+    const uint32_t sP_row = smem_u32(sP + g * AT_PBYTES) + row * 128;
+    const uint32_t sP_base = smem_u32(sP + g * AT_PBYTES);
+    uint32_t sfull_cnt = 0, ofull_cnt = 0;
+    for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
+      const int bh = static_cast<int>(item / args.npairs);
+      const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
+      const int q0 = (pair * 2 + g) * 128;
+      if (q0 >= args.ntok) continue;        // this group has no query tile in this item (warp-uniform)
+      float m = -INFINITY, l = 0.f, corr_prev = 0.f;
+      float o[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) o[i] = 0.f;
+      for (int j = 0; j < J; ++j) {
+        mbar_wait(&s_full[g], sfull_cnt & 1);
+        ++sfull_cnt;
+        tc_fence_after();
+        const int kbase = j * 128;
+        const bool tail = kbase + 128 > args.ntok;
+        // ---- pass 1: row max of the scaled scores
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int pc = 0; pc < 4; ++pc) {
+          uint32_t v[32];
+          tmem_ld32(tS + pc * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float val = __uint_as_float(v[c]) * args.scale_log2e;
+            if (tail && kbase + pc * 32 + c >= args.ntok) val = -INFINITY;
+            mx = fmaxf(mx, val);
+          }
+        }
+        const float m_new = fmaxf(m, mx);          // chunk 0 always has valid keys -> finite
+        const float corr = ex2(m - m_new);
+        m = m_new;
+        if (j > 0) {                               // PV_{j-1} retired: P smem is free, O[(j-1)&1] is valid
+          mbar_wait(&o_full[g], ofull_cnt & 1);
+          ++ofull_cnt;
+          tc_fence_after();
+        }
+        // ---- pass 2: P = exp2(s - m) -> 16-bit -> swizzled smem (A operand of the PV MMA)
+        float rs = 0.f;
+#pragma unroll 1
+        for (int pc = 0; pc < 4; ++pc) {
+          uint32_t v[32];
+          tmem_ld32(tS + pc * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float a = __uint_as_float(v[c]) * args.scale_log2e, b = __uint_as_float(v[c + 1]) * args.scale_log2e;
+            if (tail) {
+              if (kbase + pc * 32 + c >= args.ntok) a = -INFINITY;
+              if (kbase + pc * 32 + c + 1 >= args.ntok) b = -INFINITY;
+            }
+            const uint32_t w = TT::pack2(ex2(a - m_new), ex2(b - m_new));
+            const float2 f = TT::unpack2(w);       // the row sum uses the rounded probabilities, like the MMA
+            rs += f.x + f.y;
+            pk[c >> 1] = w;
+          }
+          // columns pc*32 .. +31 -> K-block pc>>1, 16-byte chunks (pc&1)*4 .. +3 of this row
+          const uint32_t base = sP_row + (pc >> 1) * (128 * 128);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int chunk = (pc & 1) * 4 + c4;
+            sts128a(base + ((chunk ^ (row & 7)) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);                   // S_g may be overwritten by the next Q K^T
+        fence_proxy_async();                       // make the generic-proxy P writes visible to the MMA (async proxy)
+        mbar_arrive(&p_full[g]);
+        l = l * corr + rs;
+        if (j > 0) {                               // absorb chunk j-1: O = O * corr_{j-1} + P_{j-1} V_{j-1}
+          const uint32_t t = tO + ((j - 1) & 1) * 64;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(t + h * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[h * 32 + c] = fmaf(o[h * 32 + c], corr_prev, __uint_as_float(v[c]));
+          }
+        }
+        corr_prev = corr;
+      }
+      // ---- last chunk
+      mbar_wait(&o_full[g], ofull_cnt & 1);
+      ++ofull_cnt;
+      tc_fence_after();
+      {
+        const uint32_t t = tO + ((J - 1) & 1) * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(t + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[h * 32 + c] = fmaf(o[h * 32 + c], corr_prev, __uint_as_float(v[c]));
+        }
+      }
+      tc_fence_before();
+      // ---- normalise, stage this warp's 32 rows through (now free) P smem, coalesced store to [B, ntok, heads*64]
+      const float inv = 1.f / l;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        sts128a(sP_row + ((c ^ (row & 7)) << 4), TT::pack2(o[8 * c] * inv, o[8 * c + 1] * inv),
+                TT::pack2(o[8 * c + 2] * inv, o[8 * c + 3] * inv), TT::pack2(o[8 * c + 4] * inv, o[8 * c + 5] * inv),
+                TT::pack2(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
+      __syncwarp();
+      const int b = bh / args.heads, hd = bh - b * args.heads;
+      const int D = args.heads * 64;
+      T* outp = reinterpret_cast<T*>(args.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = q4 * 32 + i * 4 + (lane >> 3);
+        const uint4 val = lds128a(sP_base + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+        const int t = q0 + rr;
+        if (t < args.ntok)
+          *reinterpret_cast<uint4*>(outp + (static_cast<long long>(b) * args.ntok + t) * D + hd * 64 + (lane & 7) * 8) = val;
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int make_map_3d(CUtensorMap* map, const void* base, int dtype, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_elems, uint64_t stride2_elems, uint32_t b0, uint32_t b1) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return encode_tensor_map(map, dtype, 3, base, dims, strides, box, estr);
+}
+
+extern "C" int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,
+                                int32_t ntok, int32_t npad, float scale, int32_t dtype, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!q || !k || !vt || !out) return set_error(-1, "b2u_attention_tc: null pointer");
+  if (npad % 8 || npad < ntok) return set_error(-1, "b2u_attention_tc: npad must be a multiple of 8 and >= ntok");
+  AttnMaps maps;
+  AttnArgs a{};
+  a.BH = B * heads;
+  a.heads = heads;
+  a.ntok = ntok;
+  a.nchunks = (ntok + 127) / 128;
+  a.npairs = (a.nchunks + 1) / 2;
+  a.items = static_cast<long long>(a.BH) * a.npairs;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  a.out = out;
+  int rc;
+  const uint64_t BH = static_cast<uint64_t>(a.BH);
+  if ((rc = make_map_3d(&maps.q, q, dtype, 64, ntok, BH, 64, static_cast<uint64_t>(ntok) * 64, 64, 128))) return rc;
+  if ((rc = make_map_3d(&maps.k, k, dtype, 64, ntok, BH, 64, static_cast<uint64_t>(ntok) * 64, 64, 128))) return rc;
+  if ((rc = make_map_3d(&maps.vt, vt, dtype, npad, 64, BH, npad, static_cast<uint64_t>(npad) * 64, 64, 64))) return rc;
+  static bool configured[2] = {false, false};
+  const int di = dtype == B2U_BF16 ? 1 : 0;
+  if (!configured[di]) {
+    cudaError_t e = dtype == B2U_BF16
+                        ? cudaFuncSetAttribute(attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)
+                        : cudaFuncSetAttribute(attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(attn_tc): %s", cudaGetErrorString(e));
+    configured[di] = true;
+  }
+  const int sms = num_sms();
+  const int grid = static_cast<int>(a.items < sms ? a.items : sms);
+  if (dtype == B2U_BF16) attn_tc_kernel<__nv_bfloat16><<<grid, 320, AT_SMEM, stream>>>(maps, a);
+  else attn_tc_kernel<__half><<<grid, 320, AT_SMEM, stream>>>(maps, a);
+  return check_launch("attention_tc");
+}
+
+}  // namespace b2u

@@ -32,6 +32,7 @@ struct GemmArgs {
   void* q;
   void* k;
   void* v;
+  int npad;  // > 0: V is written transposed as V^T [B, heads, 64, npad]
 };
 
 int num_sms();

@@ -422,10 +422,13 @@ extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   a.ntok = p->ntok; a.D = p->D; a.heads = p->heads; a.prefix = p->prefix;
   a.rope_sin = p->rope_sin; a.rope_cos = p->rope_cos;
   a.q = p->q; a.k = p->k; a.v = p->v;
+  a.npad = p->v_transposed ? p->npad : 0;
+  if (a.npad && (a.npad % 8 || a.npad < p->ntok)) return set_error(-1, "b2u_qkv_rope: bad npad");
   int rc;
   if ((rc = make_map_2d(&maps.a[0], p->A, a.M, p->D, p->lda, BM, p->dtype))) return rc;
   if ((rc = make_map_2d(&maps.b, p->Wp, a.N, p->D, p->ldw, bn, p->dtype))) return rc;
   a.m_tiles = static_cast<int>((static_cast<long long>(a.M) + BM - 1) / BM);
+  if (a.npad && !v2) return set_error(-1, "b2u_qkv_rope: V^T output needs the v2 GEMM kernel");
   return run_gemm(true, bn, p->dtype, maps, a, stream);
 }
 

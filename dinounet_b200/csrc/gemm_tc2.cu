@@ -261,6 +261,15 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             x[j] = TT::to_f(TT::from_f(__uint_as_float(v0[j]) + s_bias[g * 64 + j]));
             x[32 + j] = TT::to_f(TT::from_f(__uint_as_float(v1r[j]) + s_bias[g * 64 + 32 + j]));
           }
+          if (which == 2 && args.npad > 0) {
+            // V^T [B, heads, 64, npad]: lane = token, loop over d -> each store instruction writes 32 consecutive keys
+            if (v1) {
+              T* dst = reinterpret_cast<T*>(args.v) + (static_cast<long long>(b1) * args.heads + head) * 64 * args.npad + t1;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) dst[static_cast<long long>(j) * args.npad] = TT::from_f(x[j]);
+            }
+            continue;   // warp-uniform
+          }
           uint32_t packed[32];
           if (which < 2 && rot) {
 #pragma unroll

@@ -55,7 +55,8 @@ class Plan:
 
 class ForwardEngine:
     def __init__(self, variant: str, params: Dict[str, torch.Tensor], num_classes: int, device: torch.device,
-                 vit_dtype: str = "bf16", rest_dtype: str = "fp16", features=(32, 64, 128, 256)):
+                 vit_dtype: str = "bf16", rest_dtype: str = "fp16", features=(32, 64, 128, 256),
+                 attn_impl: str = "tc"):
         if variant not in cfg.VARIANTS:
             raise ValueError(f"Unknown model: {variant}")
         self.v = cfg.VARIANTS[variant]
@@ -70,6 +71,7 @@ class ForwardEngine:
         self.vt, self.rt = _CODE[vit_dtype], _CODE[rest_dtype]
         self.tv, self.tr = _TORCH16[self.vt], _TORCH16[self.rt]
         self.features = tuple(features)
+        self.attn_impl = attn_impl   # "tc" = tcgen05/TMEM kernel (default), "mma" = first-generation mma.sync kernel
         self.w: Dict[str, torch.Tensor] = {}
         self._plans: Dict[Tuple[int, int], Tuple[Plan, dict]] = {}
         self._graphs: Dict[Tuple[int, int], object] = {}
@@ -261,7 +263,12 @@ class ForwardEngine:
         Ape = buf("Ape", (B * P, 768), tv)
         X = buf("X", (T, D), torch.float32)
         Y = buf("Y", (T, D), tv)
-        Q, K_, V = buf("Q", (B, Hh, N, 64), tv), buf("K", (B, Hh, N, 64), tv), buf("V", (B, Hh, N, 64), tv)
+        npad = (N + 7) // 8 * 8
+        Q, K_ = buf("Q", (B, Hh, N, 64), tv), buf("K", (B, Hh, N, 64), tv)
+        if self.attn_impl == "tc":   # V^T with zeroed padding columns (never written by the QKV epilogue)
+            V = bufs["V"] = torch.zeros((B, Hh, 64, npad), dtype=tv, device=dev)
+        else:
+            V = buf("V", (B, Hh, N, 64), tv)
         O = buf("O", (T, D), tv)
         Hid = buf("Hid", (T, v.ffn_hidden), tv)
         taps = [buf(f"tap{k}", (B * P, D), torch.float32) for k in range(4)]
@@ -282,9 +289,13 @@ class ForwardEngine:
             qp.bias = _ptr(w.get(f"b{i}.qkvb"))
             qp.rope_sin, qp.rope_cos = _ptr(sin), _ptr(cos)
             qp.q, qp.k, qp.v, qp.dtype = _ptr(Q), _ptr(K_), _ptr(V), vt
+            qp.v_transposed, qp.npad = (1, npad) if self.attn_impl == "tc" else (0, 0)
             plan.keep.append(qp)
             plan.add(f"b{i}.qkv", lib.b2u_qkv_rope, C.byref(qp))
-            plan.add(f"b{i}.attn", lib.b2u_attention, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, 64 ** -0.5, vt)
+            if self.attn_impl == "tc":
+                plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 64 ** -0.5, vt)
+            else:
+                plan.add(f"b{i}.attn", lib.b2u_attention, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, 64 ** -0.5, vt)
             self._gemm(plan, f"b{i}.proj", O, T, D, D, w[f"b{i}.proj"], D, X, D, vt, out_fp32=True, bias=w[f"b{i}.projb"],
                        scale=w[f"b{i}.ls1"], residual=X, ldres=D)
             plan.add(f"b{i}.ln2", lib.b2u_layernorm, _ptr(X), _ptr(Y), _ptr(w[f"b{i}.n2w"]), _ptr(w[f"b{i}.n2b"]), T, D,

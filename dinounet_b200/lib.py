@@ -48,6 +48,7 @@ class QkvParams(C.Structure):
         ("A", C.c_void_p), ("lda", C.c_int64), ("Wp", C.c_void_p), ("ldw", C.c_int64),
         ("bias", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_cos", C.c_void_p),
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("dtype", C.c_int32),
+        ("v_transposed", C.c_int32), ("npad", C.c_int32),
     ]
 
 
@@ -58,6 +59,7 @@ SIGNATURES = {
     "b2u_gemm": [C.POINTER(GemmParams), vp],
     "b2u_qkv_rope": [C.POINTER(QkvParams), vp],
     "b2u_attention": [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
+    "b2u_attention_tc": [vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp],
     "b2u_layernorm": [vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp],
     "b2u_cast_rows": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "b2u_patchify": [vp, vp, i32, i32, i32, vp],

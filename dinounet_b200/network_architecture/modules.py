@@ -493,6 +493,7 @@ class DinoUNet(nn.Module):
     #: 16-bit types of the kernel path: ViT GEMMs / everything else (the reference's inner bf16 / outer fp16 autocast)
     vit_dtype = "bf16"
     rest_dtype = "fp16"
+    attn_impl = "tc"
 
     def __init__(self, network_config: dict = None, input_channels: int = None, num_classes: int = None,
                  dinov3_pretrained_path: str = "dinounet/checkpoints/dinov3_vits16_pretrain_lvd1689m-08c60483.pth",
@@ -577,7 +578,7 @@ class DinoUNet(nn.Module):
         if self._engine is None or self._engine.device != device:
             sd = {k: t for k, t in self.state_dict().items() if not k.startswith("decoder.encoder.")}
             self._engine = ForwardEngine(self.dinov3_model_name, sd, self.num_classes, device, self.vit_dtype,
-                                         self.rest_dtype, tuple(self.encoder.target_channels))
+                                         self.rest_dtype, tuple(self.encoder.target_channels), self.attn_impl)
         return self._engine
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -91,6 +91,8 @@ typedef struct b2u_qkv_params {
   void* k;
   void* v;
   int32_t dtype;
+  int32_t v_transposed; /* 1: write V as V^T [B, heads, 64, npad] (keys contiguous) for b2u_attention_tc */
+  int32_t npad;         /* row length of V^T: multiple of 8, >= ntok; columns >= ntok are never written (keep them 0) */
 } b2u_qkv_params;
 
 int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream);
@@ -99,6 +101,11 @@ int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream);
  *   q,k,v [B, heads, ntok, 64] -> out [B, ntok, heads*64]. */
 int b2u_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t heads, int32_t ntok,
                   float scale, int32_t dtype, b2u_stream_t stream);
+
+/* tcgen05 / TMEM flash attention (same math as b2u_attention): q,k [B, heads, ntok, 64], vt = V^T [B, heads, 64, npad]
+ * with zero padding columns (see b2u_qkv_params.v_transposed) -> out [B, ntok, heads*64]. */
+int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads, int32_t ntok,
+                     int32_t npad, float scale, int32_t dtype, b2u_stream_t stream);
 
 /* LayerNorm over the last dim (block.py:193-194, vision_transformer.py:300, dinov3_adapter.py:142-148):
  *   in fp32 [rows_sel, D] -> out (16-bit or fp32).  Row selection: for output row r,

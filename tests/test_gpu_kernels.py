@@ -163,6 +163,56 @@ def test_qkv_rope_and_attention(gemm_impl, dtype):
     assert rel_err(out, ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -8), rel_err(out, ref)
 
 
+@pytest.mark.parametrize("dtype", [L.BF16, L.F16])
+@pytest.mark.parametrize("B,Hh,N", [(1, 3, 1029), (2, 6, 261), (3, 2, 128), (1, 1, 700)])
+def test_attention_tcgen05(dtype, B, Hh, N):
+    """tcgen05/TMEM attention (V consumed as zero-padded V^T) == SDPA; QKV epilogue's V^T store == transpose."""
+    td = TD[dtype]
+    lib = L.load()
+    q, k, v = (_rand(B, Hh, N, 64, dt=td, seed=s) for s in range(3))
+    npad = (N + 7) // 8 * 8
+    vt = torch.zeros(B, Hh, 64, npad, device=DEV, dtype=td)
+    vt[..., :N] = v.transpose(2, 3)
+    out = torch.full((B, N, Hh * 64), float("nan"), device=DEV, dtype=td)
+    L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out), B, Hh, N, npad, 0.125, dtype, stream()), "attention_tc")
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, Hh * 64)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -8), rel_err(out, ref)
+    # second launch on the same buffers (persistent-loop barrier phases must be clean at exit)
+    out2 = torch.empty_like(out)
+    L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out2), B, Hh, N, npad, 0.125, dtype, stream()), "attention_tc")
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
+def test_qkv_vt_store_matches_transpose():
+    dtype, td = L.BF16, torch.bfloat16
+    B, h, D, Hh = 2, 8, 384, 6
+    N = h * h + 5
+    npad = (N + 7) // 8 * 8
+    lib = L.load()
+    Y = _rand(B * N, D, dt=td)
+    Wq = _rand(3 * D, D, dt=td, scale=D ** -0.5, seed=1)
+    periods = 100.0 ** (2 * torch.arange(16, dtype=torch.float32) / 32)
+    sin, cos = [t.to(DEV).contiguous() for t in O.rope_sincos(periods, h, h)]
+    outs = []
+    for vt_mode in (0, 1):
+        q, k = (torch.empty(B, Hh, N, 64, device=DEV, dtype=td) for _ in range(2))
+        v = torch.zeros((B, Hh, 64, npad) if vt_mode else (B, Hh, N, 64), device=DEV, dtype=td)
+        p = L.QkvParams()
+        p.B, p.ntok, p.D, p.heads, p.prefix = B, N, D, Hh, 5
+        p.A, p.lda, p.Wp, p.ldw, p.bias = P(Y), D, P(Wq), D, None
+        p.rope_sin, p.rope_cos, p.q, p.k, p.v, p.dtype = P(sin), P(cos), P(q), P(k), P(v), dtype
+        p.v_transposed, p.npad = vt_mode, npad
+        L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv")
+        torch.cuda.synchronize()
+        outs.append((q, k, v))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[1][2][..., :N], outs[0][2].transpose(2, 3))
+    assert outs[1][2][..., N:].abs().max() == 0
+
+
 def test_attention_1029_tokens():
     dtype, td = L.BF16, torch.bfloat16
     B, Hh, N = 1, 3, 1029
