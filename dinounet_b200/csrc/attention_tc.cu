@@ -208,55 +208,78 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         tc_fence_after();
         const int kbase = j * 128;
         const bool tail = kbase + 128 > args.ntok;
-        // ---- pass 1: row max of the scaled scores
+        // ---- pass 1: row max of the raw scores (scale > 0, applied once), TMEM loads software-pipelined
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int pc = 0; pc < 4; ++pc) {
-          uint32_t v[32];
-          tmem_ld32(tS + pc * 32, v);
-          tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32];
+          auto red = [&](const uint32_t (&v)[32], int pc) {
+            if (!tail) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float val = __uint_as_float(v[c]) * args.scale_log2e;
-            if (tail && kbase + pc * 32 + c >= args.ntok) val = -INFINITY;
-            mx = fmaxf(mx, val);
-          }
+              for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (kbase + pc * 32 + c < args.ntok) mx = fmaxf(mx, __uint_as_float(v[c]));
+            }
+          };
+          tmem_ld32(tS, va);
+          tmem_ld_wait();
+          tmem_ld32(tS + 32, vb);
+          red(va, 0);
+          tmem_ld_wait();
+          tmem_ld32(tS + 64, va);
+          red(vb, 1);
+          tmem_ld_wait();
+          tmem_ld32(tS + 96, vb);
+          red(va, 2);
+          tmem_ld_wait();
+          red(vb, 3);
         }
-        const float m_new = fmaxf(m, mx);          // chunk 0 always has valid keys -> finite
+        const float m_new = fmaxf(m, mx * args.scale_log2e);   // chunk 0 always has valid keys -> finite
         const float corr = ex2(m - m_new);
         m = m_new;
-        if (j > 0) {                               // PV_{j-1} retired: P smem is free, O[(j-1)&1] is valid
-          mbar_wait(&o_full[g], ofull_cnt & 1);
-          ++ofull_cnt;
-          tc_fence_after();
-        }
-        // ---- pass 2: P = exp2(s - m) -> 16-bit -> swizzled smem (A operand of the PV MMA)
+        // ---- pass 2: P = exp2(s*scale - m) -> 16-bit -> swizzled smem (A operand of the PV MMA)
         float rs = 0.f;
-#pragma unroll 1
-        for (int pc = 0; pc < 4; ++pc) {
-          uint32_t v[32];
-          tmem_ld32(tS + pc * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld32(tS, va);                        // issued before the o_full wait: latency overlaps it
+          if (j > 0) {                              // PV_{j-1} retired: P smem is free, O[(j-1)&1] is valid
+            mbar_wait(&o_full[g], ofull_cnt & 1);
+            ++ofull_cnt;
+            tc_fence_after();
+          }
+          auto emit = [&](const uint32_t (&v)[32], int pc) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float a = __uint_as_float(v[c]) * args.scale_log2e, b = __uint_as_float(v[c + 1]) * args.scale_log2e;
-            if (tail) {
-              if (kbase + pc * 32 + c >= args.ntok) a = -INFINITY;
-              if (kbase + pc * 32 + c + 1 >= args.ntok) b = -INFINITY;
+            for (int c = 0; c < 32; c += 2) {
+              float a = ex2(fmaf(__uint_as_float(v[c]), args.scale_log2e, -m_new));
+              float b = ex2(fmaf(__uint_as_float(v[c + 1]), args.scale_log2e, -m_new));
+              if (tail) {
+                if (kbase + pc * 32 + c >= args.ntok) a = 0.f;
+                if (kbase + pc * 32 + c + 1 >= args.ntok) b = 0.f;
+              }
+              rs += a + b;                          // fp32 row sum of the un-rounded probabilities (as flash-attention)
+              pk[c >> 1] = TT::pack2(a, b);
             }
-            const uint32_t w = TT::pack2(ex2(a - m_new), ex2(b - m_new));
-            const float2 f = TT::unpack2(w);       // the row sum uses the rounded probabilities, like the MMA
-            rs += f.x + f.y;
-            pk[c >> 1] = w;
-          }
-          // columns pc*32 .. +31 -> K-block pc>>1, 16-byte chunks (pc&1)*4 .. +3 of this row
-          const uint32_t base = sP_row + (pc >> 1) * (128 * 128);
+            // columns pc*32 .. +31 -> K-block pc>>1, 16-byte chunks (pc&1)*4 .. +3 of this row
+            const uint32_t base = sP_row + (pc >> 1) * (128 * 128);
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int chunk = (pc & 1) * 4 + c4;
-            sts128a(base + ((chunk ^ (row & 7)) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
-          }
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int chunk = (pc & 1) * 4 + c4;
+              sts128a(base + ((chunk ^ (row & 7)) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+            }
+          };
+          tmem_ld_wait();
+          tmem_ld32(tS + 32, vb);
+          emit(va, 0);
+          tmem_ld_wait();
+          tmem_ld32(tS + 64, va);
+          emit(vb, 1);
+          tmem_ld_wait();
+          tmem_ld32(tS + 96, vb);
+          emit(va, 2);
+          tmem_ld_wait();
+          emit(vb, 3);
         }
         tc_fence_before();
         mbar_arrive(&s_free[g]);                   // S_g may be overwritten by the next Q K^T
