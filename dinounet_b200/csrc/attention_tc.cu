@@ -2,14 +2,15 @@
 //
 // Persistent CTAs (1 per SM, 320 threads); one work item = (batch*head, pair of 128-row query tiles):
 //   warp 0    : TMA producer — Q tiles (once per item), K chunk [128 keys x 64] + V^T chunk [64 x 128 keys], 3-stage ring
-//   warp 1    : MMA issuer   — S_g = Q_g K^T  (M128 N128 K64, 4 x tcgen05.mma) into TMEM,
-//                              O_g[j&1] = P_g V (M128 N64 K128, 8 x tcgen05.mma) into a double-buffered TMEM chunk
+//   warp 1    : MMA issuer   — S_g(j) = Q_g K_j^T (M128 N128 K64, 4 x tcgen05.mma) into TMEM buffer X_g[j&1],
+//                              O_g(j) = P_g V_j   (M128 N64 K128, 8 x tcgen05.mma) into columns [0,64) of the same buffer
+//                              (dead once the softmax has read S_g(j)), so S(j+1) is produced while softmax(j) runs
 //   warps 2-5 : softmax group A (query tile 0), warps 6-9: softmax group B (query tile 1), one thread per query row:
 //               pass 1 tcgen05.ld S -> row max; pass 2 tcgen05.ld S -> exp2 -> 16-bit P into 128B-swizzled smem
 //               (the A operand of the PV MMA); then absorb the previous chunk's P V product from TMEM into fp32
 //               registers with the online-softmax correction.  While group A does softmax the tensor core works for B.
 // Every MMA operand is K-major SW128 (the layout the GEMM kernel already uses): V is consumed as V^T [B,H,64,npad]
-// (written transposed by the QKV epilogue), so no MN-major descriptors are needed.  TMEM: S 2x128 + O 2x2x64 = 512 cols.
+// (written transposed by the QKV epilogue), so no MN-major descriptors are needed.  TMEM: 2 groups x 2 buffers x 128 = 512 cols.
 // Replaces F.scaled_dot_product_attention at dinounet/dinov3/layers/attention.py:116.
 #include "common.cuh"
 #include "../../include/dinounet_b200.h"
@@ -28,7 +29,7 @@ struct AttnArgs {
   void* out;
 };
 
-constexpr int AT_STAGES = 3;
+constexpr int AT_STAGES = 4;
 constexpr int AT_QBYTES = 128 * 128;        // 128 rows x 64 x 2B
 constexpr int AT_PBYTES = 2 * 128 * 128;    // two K-blocks of [128 x 64]
 constexpr int AT_KBYTES = 128 * 128;
@@ -70,9 +71,9 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   uint64_t* q_free = q_full + 2;           // [2]
   uint64_t* kv_full = q_free + 2;          // [stages]
   uint64_t* kv_empty = kv_full + AT_STAGES;
-  uint64_t* s_full = kv_empty + AT_STAGES; // [2]
-  uint64_t* s_free = s_full + 2;           // [2]
-  uint64_t* p_full = s_free + 2;           // [2]
+  uint64_t* s_full = kv_empty + AT_STAGES; // [2 groups][2 buffers]
+  uint64_t* x_free = s_full + 4;           // [2][2]
+  uint64_t* p_full = x_free + 4;           // [2]
   uint64_t* o_full = p_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     tma_prefetch_desc(&maps.vt);
     for (int g = 0; g < 2; ++g) {
       mbar_init(&q_full[g], 1); mbar_init(&q_free[g], 1);
-      mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 128);
+      mbar_init(&s_full[2 * g], 1); mbar_init(&s_full[2 * g + 1], 1);
+      mbar_init(&x_free[2 * g], 128); mbar_init(&x_free[2 * g + 1], 128);
       mbar_init(&p_full[g], 128); mbar_init(&o_full[g], 1);
     }
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_g at g*128 ; O_g[buf] at 256 + g*128 + buf*64
+  // TMEM columns: X_g[b] at g*256 + b*128 (S_g(j) for j&1 == b, then O_g(j) in its first 64 columns)
   const int J = args.nchunks;
 
   if (warp == 0) {
@@ -132,36 +134,48 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       constexpr uint32_t idesc_o = make_idesc_f16(TT::kFmt, 128, 64);
       int stage = 0;
       uint32_t kv_phase = 0;
-      uint32_t qfull_cnt[2] = {0, 0}, sfree_cnt[2] = {0, 0}, pfull_cnt[2] = {0, 0};
-      auto issue_s = [&](int g, int st) {
-        mbar_wait(&s_free[g], (sfree_cnt[g] & 1) ^ 1);   // softmax g has finished reading the previous S_g
-        ++sfree_cnt[g];
+      uint32_t qfull_cnt[2] = {0, 0}, pfull_cnt[2] = {0, 0};
+      uint32_t xfree_cnt[2][2] = {{0, 0}, {0, 0}};
+      auto issue_s = [&](int g, int jj, int st) {     // S_g(jj) into X_g[jj & 1]
+        const int bfr = jj & 1;
+        mbar_wait(&x_free[2 * g + bfr], (xfree_cnt[g][bfr] & 1) ^ 1);   // softmax g has absorbed the previous occupant
+        ++xfree_cnt[g][bfr];
         tc_fence_after();
         const uint64_t da = make_desc_k128(smem_u32(sQ + g * AT_QBYTES));
         const uint64_t db = make_desc_k128(smem_u32(sK + st * AT_KBYTES));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tmem_base + g * 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_s, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[g]);
+          tc_mma_f16(tmem_base + g * 256 + bfr * 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(&s_full[2 * g + bfr]);
+      };
+      auto next_stage = [&](int st, uint32_t ph, int& nst, uint32_t& nph) {
+        nst = st + 1; nph = ph;
+        if (nst == AT_STAGES) { nst = 0; nph ^= 1; }
       };
       for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
         const int bh = static_cast<int>(item / args.npairs);
         const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
         const int nq = ((pair * 2 + 1) * 128 < args.ntok) ? 2 : 1;
         for (int g = 0; g < nq; ++g) { mbar_wait(&q_full[g], qfull_cnt[g] & 1); ++qfull_cnt[g]; }
-        // S(0)
+        // `stage`/`kv_phase` track chunk j (whose V the PV MMA uses); S runs one chunk ahead.
+        int st1; uint32_t ph1;
+        next_stage(stage, kv_phase, st1, ph1);
         mbar_wait(&kv_full[stage], kv_phase);
         tc_fence_after();
-        for (int g = 0; g < nq; ++g) issue_s(g, stage);
+        for (int g = 0; g < nq; ++g) issue_s(g, 0, stage);
+        if (J > 1) {
+          mbar_wait(&kv_full[st1], ph1);
+          tc_fence_after();
+          for (int g = 0; g < nq; ++g) issue_s(g, 1, st1);
+        }
         for (int j = 0; j < J; ++j) {
-          int nstage = stage + 1;
-          uint32_t nphase = kv_phase;
-          if (nstage == AT_STAGES) { nstage = 0; nphase ^= 1; }
+          int st2; uint32_t ph2;
+          next_stage(st1, ph1, st2, ph2);
           for (int g = 0; g < nq; ++g) {
-            mbar_wait(&p_full[g], pfull_cnt[g] & 1);
+            mbar_wait(&p_full[g], pfull_cnt[g] & 1);   // P_g(j) is in smem (and S_g(j) has been fully read)
             ++pfull_cnt[g];
             tc_fence_after();
-            const uint32_t tO = tmem_base + 256 + g * 128 + (j & 1) * 64;
+            const uint32_t tO = tmem_base + g * 256 + (j & 1) * 128;
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
               const uint64_t da = make_desc_k128(smem_u32(sP + g * AT_PBYTES + kb * 128 * 128));
@@ -171,14 +185,15 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
                 tc_mma_f16(tO, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_o, (kb | k) != 0 ? 1u : 0u);
             }
             tc_commit(&o_full[g]);
-            if (j + 1 < J) {
-              if (g == 0) { mbar_wait(&kv_full[nstage], nphase); tc_fence_after(); }
-              issue_s(g, nstage);
-            }
           }
           tc_commit(&kv_empty[stage]);   // K_j / V_j are free once every MMA issued so far has retired
-          stage = nstage;
-          kv_phase = nphase;
+          if (j + 2 < J) {               // S(j+2) reuses buffer j&1 once O(j) has been absorbed by the softmax
+            mbar_wait(&kv_full[st2], ph2);
+            tc_fence_after();
+            for (int g = 0; g < nq; ++g) issue_s(g, j + 2, st2);
+          }
+          stage = st1; kv_phase = ph1;
+          st1 = st2; ph1 = ph2;
         }
         for (int g = 0; g < nq; ++g) tc_commit(&q_free[g]);
       }
@@ -188,11 +203,10 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     const int g = (warp - 2) >> 2;          // query tile of the pair
     const int q4 = warp & 3;                // TMEM lane quarter
     const int row = q4 * 32 + lane;
-    const uint32_t tS = tmem_base + g * 128 + (static_cast<uint32_t>(q4 * 32) << 16);
-    const uint32_t tO = tmem_base + 256 + g * 128 + (static_cast<uint32_t>(q4 * 32) << 16);
+    const uint32_t tX = tmem_base + g * 256 + (static_cast<uint32_t>(q4 * 32) << 16);
     const uint32_t sP_row = smem_u32(sP + g * AT_PBYTES) + row * 128;
     const uint32_t sP_base = smem_u32(sP + g * AT_PBYTES);
-    uint32_t sfull_cnt = 0, ofull_cnt = 0;
+    uint32_t sfull_cnt[2] = {0, 0}, ofull_cnt = 0;
     for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
       const int bh = static_cast<int>(item / args.npairs);
       const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
@@ -203,8 +217,9 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 64; ++i) o[i] = 0.f;
       for (int j = 0; j < J; ++j) {
-        mbar_wait(&s_full[g], sfull_cnt & 1);
-        ++sfull_cnt;
+        const uint32_t tS = tX + (j & 1) * 128;
+        mbar_wait(&s_full[2 * g + (j & 1)], sfull_cnt[j & 1] & 1);
+        ++sfull_cnt[j & 1];
         tc_fence_after();
         const int kbase = j * 128;
         const bool tail = kbase + 128 > args.ntok;
@@ -242,12 +257,23 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         float rs = 0.f;
         {
           uint32_t va[32], vb[32];
-          tmem_ld32(tS, va);                        // issued before the o_full wait: latency overlaps it
-          if (j > 0) {                              // PV_{j-1} retired: P smem is free, O[(j-1)&1] is valid
+          if (j > 0) {                              // PV_{j-1} retired: P smem is free, O(j-1) sits in X[(j-1)&1][0:64)
             mbar_wait(&o_full[g], ofull_cnt & 1);
             ++ofull_cnt;
             tc_fence_after();
+            const uint32_t t = tX + ((j - 1) & 1) * 128;
+            tmem_ld32(t, va);
+            tmem_ld32(t + 32, vb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {          // absorb: O = O * corr_{j-1} + P_{j-1} V_{j-1}
+              o[c] = fmaf(o[c], corr_prev, __uint_as_float(va[c]));
+              o[32 + c] = fmaf(o[32 + c], corr_prev, __uint_as_float(vb[c]));
+            }
+            tc_fence_before();
+            mbar_arrive(&x_free[2 * g + ((j - 1) & 1)]);   // buffer (j-1)&1 may now receive S(j+1)
           }
+          tmem_ld32(tS, va);
           auto emit = [&](const uint32_t (&v)[32], int pc) {
             uint32_t pk[16];
 #pragma unroll
@@ -281,22 +307,10 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
           tmem_ld_wait();
           emit(vb, 3);
         }
-        tc_fence_before();
-        mbar_arrive(&s_free[g]);                   // S_g may be overwritten by the next Q K^T
+        tc_fence_before();                         // all reads of S_g(j) done: PV(j) may overwrite X[j&1][0:64)
         fence_proxy_async();                       // make the generic-proxy P writes visible to the MMA (async proxy)
         mbar_arrive(&p_full[g]);
         l = l * corr + rs;
-        if (j > 0) {                               // absorb chunk j-1: O = O * corr_{j-1} + P_{j-1} V_{j-1}
-          const uint32_t t = tO + ((j - 1) & 1) * 64;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld32(t + h * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) o[h * 32 + c] = fmaf(o[h * 32 + c], corr_prev, __uint_as_float(v[c]));
-          }
-        }
         corr_prev = corr;
       }
       // ---- last chunk
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       ++ofull_cnt;
       tc_fence_after();
       {
-        const uint32_t t = tO + ((J - 1) & 1) * 64;
+        const uint32_t t = tX + ((J - 1) & 1) * 128;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
@@ -315,6 +329,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         }
       }
       tc_fence_before();
+      mbar_arrive(&x_free[2 * g + ((J - 1) & 1)]);
       // ---- normalise, stage this warp's 32 rows through (now free) P smem, coalesced store to [B, ntok, heads*64]
       const float inv = 1.f / l;
       __syncwarp();
