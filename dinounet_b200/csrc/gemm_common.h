@@ -33,6 +33,7 @@ struct GemmArgs {
   void* k;
   void* v;
   int npad;  // > 0: V is written transposed as V^T [B, heads, 64, npad]
+  int rope_h, rope_w;  // > 0: separable rope tables staged in smem
 };
 
 int num_sms();

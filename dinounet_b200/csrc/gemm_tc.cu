@@ -423,6 +423,12 @@ extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   a.rope_sin = p->rope_sin; a.rope_cos = p->rope_cos;
   a.q = p->q; a.k = p->k; a.v = p->v;
   a.npad = p->v_transposed ? p->npad : 0;
+  if (p->rope_w > 0 && v2) {
+    a.rope_w = p->rope_w;
+    a.rope_h = (p->ntok - p->prefix) / p->rope_w;
+    if (a.rope_h * a.rope_w != p->ntok - p->prefix || a.rope_h + a.rope_w > 128)
+      return set_error(-1, "b2u_qkv_rope: rope grid %d x %d does not match ntok/prefix or is too large", a.rope_h, a.rope_w);
+  }
   if (a.npad && (a.npad % 8 || a.npad < p->ntok)) return set_error(-1, "b2u_qkv_rope: bad npad");
   int rc;
   if ((rc = make_map_2d(&maps.a[0], p->A, a.M, p->D, p->lda, BM, p->dtype))) return rc;

@@ -18,14 +18,18 @@
 
 namespace b2u {
 
-template <int BN> struct Cfg2 {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+constexpr int kRopeBytes = 128 * 16 * 2 * 4;   // (rope_h + rope_w <= 128) rows x 16 angles x {sin, cos} fp32
+
+template <int BN, int EPI = 0> struct Cfg2 {
+  // the QKV variant trades one pipeline stage for the in-smem rope tables
+  static constexpr int kStages = (BN == 256) ? (EPI == 2 ? 3 : 4) : (BN == 128 ? (EPI == 2 ? 5 : 6) : 8);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 8 * 4096;        // 8 epilogue warps x (32 rows x 128 B)
   static constexpr int kBiasBytes = BN * 4;
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kRope = EPI == 2 ? kRopeBytes : 0;
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + kRope + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
@@ -87,13 +91,14 @@ __device__ __forceinline__ void act_vec(float (&f)[NV]) {
 // after the bias / after the affine (B2U_ACT_*), so the fully unrolled epilogue stays small enough for the I-cache.
 template <int BN, int EPI, int ACT1, int ACT2, typename T>
 __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
-  using C = Cfg2<BN>;
+  using C = Cfg2<BN, EPI>;
   using TT = T16<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
   float* s_bias = reinterpret_cast<float*>(staging + C::kStagingBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes + C::kBiasBytes);
+  float* s_rope = reinterpret_cast<float*>(staging + C::kStagingBytes + C::kBiasBytes);   // [h+w][32] = (sin16 | cos16)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes + C::kBiasBytes + C::kRope);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -111,6 +116,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
+  if constexpr (EPI == 2) {
+    if (args.rope_w > 0) {
+      // rows 0..h-1: angles that depend on the patch row (table columns 0..15 of patch (py, 0));
+      // rows h..h+w-1: angles that depend on the patch column (table columns 16..31 of patch (0, px))
+      const int n = (args.rope_h + args.rope_w) * 32;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = i >> 5, c = i & 31;
+        const bool is_cos = c >= 16;
+        const int a = c & 15;
+        const long long src = r < args.rope_h ? static_cast<long long>(r) * args.rope_w * 64 + a
+                                              : static_cast<long long>(r - args.rope_h) * 64 + 16 + a;
+        s_rope[i] = is_cos ? __ldg(args.rope_cos + src) : __ldg(args.rope_sin + src);
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -271,7 +291,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             continue;   // warp-uniform
           }
           uint32_t packed[32];
-          if (which < 2 && rot) {
+          if (which < 2 && rot && args.rope_w > 0) {
+            // separable tables from smem: angle j (<16) from the row table, (16..31) from the column table; cos/sin[j+32] == [j]
+            const int pidx = t1 - args.prefix;
+            const int py = pidx / args.rope_w, px = pidx - py * args.rope_w;
+            const uint32_t ry = smem_u32(s_rope) + py * 128, rx = smem_u32(s_rope) + (args.rope_h + px) * 128;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const uint32_t rbase_ = (j < 16 ? ry : rx) + (j & 15) * 4;
+              const float4 sn = lds128f(rbase_), cs = lds128f(rbase_ + 64);
+              packed[j / 2] = TT::pack2(x[j] * cs.x - x[j + 32] * sn.x, x[j + 1] * cs.y - x[j + 33] * sn.y);
+              packed[j / 2 + 1] = TT::pack2(x[j + 2] * cs.z - x[j + 34] * sn.z, x[j + 3] * cs.w - x[j + 35] * sn.w);
+              packed[16 + j / 2] = TT::pack2(x[j + 32] * cs.x + x[j] * sn.x, x[j + 33] * cs.y + x[j + 1] * sn.y);
+              packed[16 + j / 2 + 1] = TT::pack2(x[j + 34] * cs.z + x[j + 2] * sn.z, x[j + 35] * cs.w + x[j + 3] * sn.w);
+            }
+          } else if (which < 2 && rot) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 c_lo = *reinterpret_cast<const float4*>(cosr + j), s_lo = *reinterpret_cast<const float4*>(sinr + j);
@@ -477,14 +511,14 @@ static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStrea
   auto kern = gemm_tc2_kernel<BN, EPI, ACT1, ACT2, T>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN, EPI>::kSmem);
     if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(e));
     configured = true;
   }
   const long long tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
   const int sms = num_sms();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kern<<<grid, 320, Cfg2<BN>::kSmem, stream>>>(maps, args);
+  kern<<<grid, 320, Cfg2<BN, EPI>::kSmem, stream>>>(maps, args);
   return check_launch("gemm_tc2");
 }
 

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "../../include/dinounet_b200.h"
 #include "host_util.h"
+#include "gemm_common.h"
 
 namespace b2u {
 
@@ -74,11 +75,141 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const T* __restrict__ val
   for (int j = 0; j < HALF; j += 2) *reinterpret_cast<uint32_t*>(dst + j) = T16<T>::pack2(acc[j], acc[j + 1]);
 }
 
+// ---- v2: value slab of HPC heads of one image staged in shared memory -------------------------------------------------
+// CTA = (query slice, head group, image).  The HPC heads' value maps ([Hv*Wv, dh] each, 16-bit) are copied once into
+// smem (coalesced 16 B loads), then every thread owns one (query, head) pair: it reads its 8 offsets + 4 logits
+// (three float4 from the fp32 offaw row), runs the softmax / location prologue, gathers 4 points x 4 corners x dh
+// channels from SHARED memory with 16-byte loads and writes dh contiguous 16-bit outputs.  HBM traffic is the
+// algorithmic minimum (offaw + out + value once per CTA); the random gather never leaves the SM.
+template <typename T, int DH, int HPC>
+__global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ value, const float* __restrict__ offaw,
+                                                        T* __restrict__ out, int Hv, int Wv, int heads, int qsplit) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  T* slab = reinterpret_cast<T*>(sm_raw);                 // [HW][HPC*DH]
+  const int HW = Hv * Wv;
+  const int Lq = (HW * 21) / 4;
+  const int b = blockIdx.z, hg = blockIdx.y;
+  constexpr int ROW = HPC * DH;                           // elements per position in the slab
+  // ---- stage the slab: value[b, pos, hg*HPC .. +HPC, :] -> slab[pos][:]  (ROW*2 bytes contiguous per position)
+  {
+    constexpr int V16 = ROW * 2 / 16;                     // 16-byte vectors per position
+    const uint4* src = reinterpret_cast<const uint4*>(value + (static_cast<long long>(b) * HW * heads + hg * HPC) * DH);
+    uint4* dst = reinterpret_cast<uint4*>(slab);
+    const int src_stride = heads * DH * 2 / 16;           // vectors between consecutive positions
+    for (int i = threadIdx.x; i < HW * V16; i += 256) {
+      const int pos = i / V16, v = i - pos * V16;
+      dst[i] = __ldg(src + static_cast<long long>(pos) * src_stride + v);
+    }
+  }
+  __syncthreads();
+  const int per = (Lq + qsplit - 1) / qsplit;
+  const int q_begin = blockIdx.x * per;
+  const int q_end = min(Lq, q_begin + per);
+  for (int w = q_begin * HPC + threadIdx.x; w < q_end * HPC; w += 256) {
+    const int q = w / HPC, hl = w - q * HPC;
+    const int head = hg * HPC + hl;
+    int qq = q, gh = 2 * Hv, gw = 2 * Wv;
+    if (qq >= 4 * HW) { qq -= 4 * HW; gh = Hv; gw = Wv; if (qq >= HW) { qq -= HW; gh = Hv / 2; gw = Wv / 2; } }
+    const int qy = qq / gw, qx = qq - qy * gw;
+    const float refx = (qx + 0.5f) / gw, refy = (qy + 0.5f) / gh;
+    const long long qg = static_cast<long long>(b) * Lq + q;
+    const float* row = offaw + qg * (heads * 12);
+    const float4 o0 = __ldg(reinterpret_cast<const float4*>(row + head * 8));
+    const float4 o1 = __ldg(reinterpret_cast<const float4*>(row + head * 8 + 4));
+    const float4 lg = __ldg(reinterpret_cast<const float4*>(row + heads * 8 + head * 4));
+    const float mx = fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w));
+    float wgt[4] = {__expf(lg.x - mx), __expf(lg.y - mx), __expf(lg.z - mx), __expf(lg.w - mx)};
+    const float inv = 1.f / (wgt[0] + wgt[1] + wgt[2] + wgt[3]);
+    const float ox[4] = {o0.x, o0.z, o1.x, o1.z}, oy[4] = {o0.y, o0.w, o1.y, o1.w};
+    float acc[DH];
+#pragma unroll
+    for (int j = 0; j < DH; ++j) acc[j] = 0.f;
+    const T* hb = slab + hl * DH;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float aw = wgt[p] * inv;
+      const float px = (refx + ox[p] / Wv) * Wv - 0.5f;
+      const float py = (refy + oy[p] / Hv) * Hv - 0.5f;
+      const float fx = floorf(px), fy = floorf(py);
+      const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+      const float lx = px - fx, ly = py - fy;
+      const float cw[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int yy = y0 + (c >> 1), xx = x0 + (c & 1);
+        if (yy < 0 || yy >= Hv || xx < 0 || xx >= Wv) continue;
+        const float wt = aw * cw[c];
+        const T* src = hb + (yy * Wv + xx) * ROW;
+        if constexpr (DH % 8 == 0) {
+#pragma unroll
+          for (int j = 0; j < DH; j += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(src + j);
+            const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
+            acc[j] = fmaf(wt, a0.x, acc[j]); acc[j + 1] = fmaf(wt, a0.y, acc[j + 1]);
+            acc[j + 2] = fmaf(wt, a1.x, acc[j + 2]); acc[j + 3] = fmaf(wt, a1.y, acc[j + 3]);
+            acc[j + 4] = fmaf(wt, a2.x, acc[j + 4]); acc[j + 5] = fmaf(wt, a2.y, acc[j + 5]);
+            acc[j + 6] = fmaf(wt, a3.x, acc[j + 6]); acc[j + 7] = fmaf(wt, a3.y, acc[j + 7]);
+          }
+        } else {   // DH = 12: 8-byte loads
+#pragma unroll
+          for (int j = 0; j < DH; j += 4) {
+            const uint2 u = *reinterpret_cast<const uint2*>(src + j);
+            const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y);
+            acc[j] = fmaf(wt, a0.x, acc[j]); acc[j + 1] = fmaf(wt, a0.y, acc[j + 1]);
+            acc[j + 2] = fmaf(wt, a1.x, acc[j + 2]); acc[j + 3] = fmaf(wt, a1.y, acc[j + 3]);
+          }
+        }
+      }
+    }
+    T* dst = out + qg * (heads * DH) + head * DH;
+    if constexpr (DH % 8 == 0) {
+#pragma unroll
+      for (int j = 0; j < DH; j += 8)
+        *reinterpret_cast<uint4*>(dst + j) = make_uint4(T16<T>::pack2(acc[j], acc[j + 1]), T16<T>::pack2(acc[j + 2], acc[j + 3]),
+                                                        T16<T>::pack2(acc[j + 4], acc[j + 5]), T16<T>::pack2(acc[j + 6], acc[j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < DH; j += 4)
+        *reinterpret_cast<uint2*>(dst + j) = make_uint2(T16<T>::pack2(acc[j], acc[j + 1]), T16<T>::pack2(acc[j + 2], acc[j + 3]));
+    }
+  }
+}
+
+template <typename T, int DH, int HPC>
+static int launch_msda_smem(const void* value, const float* offaw, void* out, int B, int Hv, int Wv, int heads,
+                            cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(Hv) * Wv * HPC * DH * 2;
+  auto kern = msda_smem_kernel<T, DH, HPC>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(msda_smem): %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const int groups = heads / HPC;
+  // enough CTAs for ~2 waves of 148 SMs; each re-stages its slab from L2
+  int qsplit = (2 * num_sms() + B * groups - 1) / (B * groups);
+  if (qsplit < 1) qsplit = 1;
+  dim3 grid(qsplit, groups, B);
+  kern<<<grid, 256, smem, stream>>>(static_cast<const T*>(value), offaw, static_cast<T*>(out), Hv, Wv, heads, qsplit);
+  return check_launch("msda_forward(smem)");
+}
+
 extern "C" int b2u_msda_forward(const void* value, const float* offaw, void* out, int32_t B, int32_t Hv, int32_t Wv,
                                 int32_t heads, int32_t dh, int32_t points, int32_t dtype, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (heads != 16 || points != 4) return set_error(-1, "b2u_msda_forward: built for 16 heads x 4 points (dinounet_training.py:758-759)");
   if ((Hv & 1) || (Wv & 1)) return set_error(-1, "b2u_msda_forward: value map must have even size");
+  // shared-memory slab path (default): per CTA HPC heads x Hv*Wv positions x dh channels must fit in 200 KB
+  if (get_option(1) == 0) {
+    const size_t per_head = static_cast<size_t>(Hv) * Wv * dh * 2;
+#define B2U_MSDA_SMEM(DH_, HPC_)                                                                                          \
+    if (dh == DH_ && per_head * HPC_ <= 200 * 1024)                                                                        \
+      return dtype == B2U_BF16 ? launch_msda_smem<__nv_bfloat16, DH_, HPC_>(value, offaw, out, B, Hv, Wv, heads, stream) \
+                               : launch_msda_smem<__half, DH_, HPC_>(value, offaw, out, B, Hv, Wv, heads, stream);
+    B2U_MSDA_SMEM(12, 8) B2U_MSDA_SMEM(24, 4) B2U_MSDA_SMEM(32, 2) B2U_MSDA_SMEM(12, 2) B2U_MSDA_SMEM(24, 1) B2U_MSDA_SMEM(32, 1)
+#undef B2U_MSDA_SMEM
+  }
   const long long nq = static_cast<long long>(B) * ((Hv * Wv * 21) / 4);
   const int grid = static_cast<int>((nq + 7) / 8);
 #define B2U_MSDA(HALF_)                                                                                               \

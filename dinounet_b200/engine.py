@@ -290,6 +290,7 @@ class ForwardEngine:
             qp.rope_sin, qp.rope_cos = _ptr(sin), _ptr(cos)
             qp.q, qp.k, qp.v, qp.dtype = _ptr(Q), _ptr(K_), _ptr(V), vt
             qp.v_transposed, qp.npad = (1, npad) if self.attn_impl == "tc" else (0, 0)
+            qp.rope_w = h
             plan.keep.append(qp)
             plan.add(f"b{i}.qkv", lib.b2u_qkv_rope, C.byref(qp))
             if self.attn_impl == "tc":

@@ -48,7 +48,7 @@ class QkvParams(C.Structure):
         ("A", C.c_void_p), ("lda", C.c_int64), ("Wp", C.c_void_p), ("ldw", C.c_int64),
         ("bias", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_cos", C.c_void_p),
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("dtype", C.c_int32),
-        ("v_transposed", C.c_int32), ("npad", C.c_int32),
+        ("v_transposed", C.c_int32), ("npad", C.c_int32), ("rope_w", C.c_int32),
     ]
 
 

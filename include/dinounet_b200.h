@@ -93,6 +93,9 @@ typedef struct b2u_qkv_params {
   int32_t dtype;
   int32_t v_transposed; /* 1: write V as V^T [B, heads, 64, npad] (keys contiguous) for b2u_attention_tc */
   int32_t npad;         /* row length of V^T: multiple of 8, >= ntok; columns >= ntok are never written (keep them 0) */
+  int32_t rope_w;       /* > 0: the rope tables describe an (ntok-prefix)/rope_w x rope_w patch grid with separable angles
+                           (rope_position_encoding.py:99-104: first 16 of 32 angles depend on the row, last 16 on the column,
+                           tiled twice) -> the kernel keeps compact per-row / per-column tables in shared memory */
 } b2u_qkv_params;
 
 int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream);
@@ -199,7 +202,8 @@ int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream);
 
 /* Tuning / A-B switches.  key 0 (B2U_OPT_GEMM_IMPL): 0 = persistent 128x256-tile tcgen05 kernel (default),
  * 1 = the first-generation one-tile-per-CTA kernel. */
-enum { B2U_OPT_GEMM_IMPL = 0 };
+/* key 1 (B2U_OPT_MSDA_IMPL): 0 = shared-memory value-slab gather (default), 1 = first-generation warp-per-query kernel. */
+enum { B2U_OPT_GEMM_IMPL = 0, B2U_OPT_MSDA_IMPL = 1 };
 int b2u_set_option(int32_t key, int32_t value);
 
 const char* b2u_last_error(void);

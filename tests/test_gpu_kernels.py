@@ -150,6 +150,12 @@ def test_qkv_rope_and_attention(gemm_impl, dtype):
     p.rope_sin, p.rope_cos, p.q, p.k, p.v, p.dtype = P(sin), P(cos), P(q), P(k), P(v), dtype
     L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv")
     torch.cuda.synchronize()
+    if gemm_impl == "v2":   # separable in-smem rope tables must give bit-identical q/k
+        q2, k2, v2_ = (torch.full((B, Hh, N, 64), float("nan"), device=DEV, dtype=td) for _ in range(3))
+        p.q, p.k, p.v, p.rope_w = P(q2), P(k2), P(v2_), h
+        L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv(smem rope)")
+        torch.cuda.synchronize()
+        assert torch.equal(q, q2) and torch.equal(k, k2) and torch.equal(v, v2_)
     qkv = (Y.float() @ Wq.float().t() + bias).to(td)
     qr, kr, vr = [t.transpose(1, 2) for t in torch.unbind(qkv.reshape(B, N, 3, Hh, 64), 2)]
     qr, kr = O._rope(qr, sin, cos), O._rope(kr, sin, cos)
@@ -283,8 +289,9 @@ def test_dwconv_three_planes_gelu():
     assert rel_err(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("dh", [12, 24, 32])
-def test_msda_forward_matches_reference_sampling(dh):
+def test_msda_forward_matches_reference_sampling(dh, impl):
     """the op the reference itself pins in ops/test.py: CUDA sampling == grid_sample formulation."""
     lib = L.load()
     B, Hv, heads, pts = 2, 16, 16, 4
@@ -292,9 +299,13 @@ def test_msda_forward_matches_reference_sampling(dh):
     Lq = 21 * HW // 4
     value = _rand(B, HW, heads, dh, dt=torch.float16)
     offaw = torch.cat([_rand(B * Lq, 128, scale=3.0, seed=1), _rand(B * Lq, 64, seed=2)], 1).contiguous()
-    out = torch.empty(B * Lq, heads * dh, device=DEV, dtype=torch.float16)
-    L.check(lib.b2u_msda_forward(P(value), P(offaw), P(out), B, Hv, Hv, heads, dh, pts, L.F16, stream()), "msda")
-    torch.cuda.synchronize()
+    out = torch.full((B * Lq, heads * dh), float("nan"), device=DEV, dtype=torch.float16)
+    lib.b2u_set_option(1, impl)     # 0 = shared-memory slab kernel, 1 = warp-per-query kernel
+    try:
+        L.check(lib.b2u_msda_forward(P(value), P(offaw), P(out), B, Hv, Hv, heads, dh, pts, L.F16, stream()), "msda")
+        torch.cuda.synchronize()
+    finally:
+        lib.b2u_set_option(1, 0)
     ref_pts = O.reference_points([(2 * Hv, 2 * Hv), (Hv, Hv), (Hv // 2, Hv // 2)], DEV)
     off = offaw[:, :128].view(B, Lq, heads, 1, pts, 2)
     aw = F.softmax(offaw[:, 128:].view(B, Lq, heads, pts), -1).view(B, Lq, heads, 1, pts)
