@@ -378,11 +378,80 @@ __global__ void tail_fuse_kernel(const void* __restrict__ base, int base_fp32, l
   o.store(out + pix * D + c8 * 8);
 }
 
+// Integer up-scaling (S = 2, 4): one thread per SOURCE cell (between tap rows cy, cy+1 and columns cx, cx+1) and 8
+// channels.  The 4 corner vectors are loaded once and reused for the S x S output pixels whose bilinear footprint is that
+// cell (output rows S*cy + S/2 + t, t < S, weight (t + 0.5) / S; border cells clamp, which reproduces PyTorch's
+// src = max((dst + 0.5) / S - 0.5, 0) rule), so the fp32 tap traffic drops by S^2 compared to the per-output gather.
+template <typename T, int S>
+__global__ void tail_fuse_up_kernel(const void* __restrict__ base, int base_fp32, long long base_bstride,
+                                    const float* __restrict__ tap, T* __restrict__ out, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int B, int Ht, int Wt, int D8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int CW = Wt + 1, CH = Ht + 1;
+  const long long total = static_cast<long long>(B) * CH * CW * D8;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % D8);
+  const long long cell = i / D8;
+  const int cx = static_cast<int>(cell % CW) - 1, cy = static_cast<int>((cell / CW) % CH) - 1;
+  const int b = static_cast<int>(cell / (static_cast<long long>(CW) * CH));
+  const int D = D8 * 8, H = S * Ht, W = S * Wt;
+  const int y0 = max(cy, 0), y1 = min(cy + 1, Ht - 1), x0 = max(cx, 0), x1 = min(cx + 1, Wt - 1);
+  const float* tb = tap + static_cast<long long>(b) * Ht * Wt * D + c8 * 8;
+  float c00[8], c01[8], c10[8], c11[8], sc[8], sh[8];
+  auto ld8 = [](const float* p, float (&f)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], c = reinterpret_cast<const float4*>(p)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = c.x; f[5] = c.y; f[6] = c.z; f[7] = c.w;
+  };
+  ld8(tb + (static_cast<long long>(y0) * Wt + x0) * D, c00);
+  ld8(tb + (static_cast<long long>(y0) * Wt + x1) * D, c01);
+  ld8(tb + (static_cast<long long>(y1) * Wt + x0) * D, c10);
+  ld8(tb + (static_cast<long long>(y1) * Wt + x1) * D, c11);
+  ld8(scale + c8 * 8, sc);
+  ld8(shift + c8 * 8, sh);
+#pragma unroll
+  for (int ty = 0; ty < S; ++ty) {
+    const int y = S * cy + S / 2 + ty;
+    if (y < 0 || y >= H) continue;
+    const float ly = (ty + 0.5f) / S;
+#pragma unroll
+    for (int tx = 0; tx < S; ++tx) {
+      const int x = S * cx + S / 2 + tx;
+      if (x < 0 || x >= W) continue;
+      const float lx = (tx + 0.5f) / S;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      float f[8];
+      const long long pix = (static_cast<long long>(y) * W + x);
+      if (base_fp32) {
+        ld8(reinterpret_cast<const float*>(base) + static_cast<long long>(b) * base_bstride + pix * D + c8 * 8, f);
+      } else {
+        Vec8<T> v;
+        v.load(reinterpret_cast<const T*>(base) + static_cast<long long>(b) * base_bstride + pix * D + c8 * 8);
+        v.to_float(f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        f[j] = (f[j] + (w00 * c00[j] + w01 * c01[j] + w10 * c10[j] + w11 * c11[j])) * sc[j] + sh[j];
+      Vec8<T> o;
+      o.from_float(f);
+      o.store(out + (static_cast<long long>(b) * H * W + pix) * D + c8 * 8);
+    }
+  }
+}
+
 extern "C" int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_batch_stride, const float* tap, void* out,
                              const float* scale, const float* shift, int32_t B, int32_t H, int32_t W, int32_t Ht,
                              int32_t Wt, int32_t D, int32_t dtype, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (D % 8) return set_error(-1, "b2u_tail_fuse: D %% 8 != 0");
+  if ((H == 4 * Ht && W == 4 * Wt) || (H == 2 * Ht && W == 2 * Wt)) {
+    const long long cells = static_cast<long long>(B) * (Ht + 1) * (Wt + 1) * (D / 8);
+    if (H == 4 * Ht) {
+      B2U_DISPATCH_T(dtype, (tail_fuse_up_kernel<T, 4><<<blocks_for(cells, 256), 256, 0, stream>>>(base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, Ht, Wt, D / 8)));
+    } else {
+      B2U_DISPATCH_T(dtype, (tail_fuse_up_kernel<T, 2><<<blocks_for(cells, 256), 256, 0, stream>>>(base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, Ht, Wt, D / 8)));
+    }
+    return check_launch("tail_fuse(up)");
+  }
   const long long total = static_cast<long long>(B) * H * W * (D / 8);
   B2U_DISPATCH_T(dtype, (tail_fuse_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, H, W, Ht, Wt, D / 8)));
   return check_launch("tail_fuse");
