@@ -58,7 +58,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 template <typename T>
-__global__ void __maxnreg__(200) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
+__global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
   using TT = T16<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -297,28 +297,28 @@ __global__ void __maxnreg__(200) attn_tc_kernel(const __grid_constant__ AttnMaps
           // probabilities stay exact as long as the chunk max does not exceed m by more than 2^8; otherwise (rare) the
           // whole warp recomputes the chunk against the new max.
           float mx = -INFINITY;
-          uint32_t pk0[16], pk[16];
-          tmem_ld32(tS, va);
-          tmem_ld_wait();
-          tmem_ld32(tS + 32, vb);
-          expo(va, 0, m, pk0, mx);                  // piece 0 computed while PV_{j-1} is still in flight
+          uint32_t pk[16];
           mbar_wait(&o_full[g], ofull_cnt & 1);     // PV_{j-1} retired: P smem is free, O(j-1) sits in X[(j-1)&1][0:64)
           ++ofull_cnt;
           tc_fence_after();
           {
             const uint32_t t = tX + ((j - 1) & 1) * 128;
             tmem_ld32(t, va);
-            tmem_ld_wait();                         // (also completes piece 1 in vb)
-#pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], corr_prev, __uint_as_float(va[c]));
-            tmem_ld32(t + 32, va);
+            tmem_ld32(t + 32, vb);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) o[32 + c] = fmaf(o[32 + c], corr_prev, __uint_as_float(va[c]));
+            for (int c = 0; c < 32; ++c) {          // absorb: O = O * corr_{j-1} + P_{j-1} V_{j-1}
+              o[c] = fmaf(o[c], corr_prev, __uint_as_float(va[c]));
+              o[32 + c] = fmaf(o[32 + c], corr_prev, __uint_as_float(vb[c]));
+            }
             tc_fence_before();
             mbar_arrive(&x_free[2 * g + ((j - 1) & 1)]);   // buffer (j-1)&1 may now receive S(j+1)
           }
-          put(pk0, 0);
+          tmem_ld32(tS, va);
+          tmem_ld_wait();
+          tmem_ld32(tS + 32, vb);
+          expo(va, 0, m, pk, mx); put(pk, 0);
+          tmem_ld_wait();
           tmem_ld32(tS + 64, va);
           expo(vb, 1, m, pk, mx); put(pk, 1);
           tmem_ld_wait();
