@@ -223,59 +223,19 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         tc_fence_after();
         const int kbase = j * 128;
         const bool tail = kbase + 128 > args.ntok;
-        uint32_t va[32], vb[32];
-        float rs = 0.f, corr = 1.f;
-        // exp2(s*scale - mref) for 32 columns -> packed 16-bit probabilities; tracks the raw row max and the row sum
-        auto expo = [&](const uint32_t (&v)[32], int pc, float mref, uint32_t (&pk)[16], float& mx) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float s0 = __uint_as_float(v[c]), s1 = __uint_as_float(v[c + 1]);
-            float a = ex2(fmaf(s0, args.scale_log2e, -mref));
-            float b = ex2(fmaf(s1, args.scale_log2e, -mref));
-            if (!tail) {
-              mx = fmaxf(mx, fmaxf(s0, s1));
-            } else {
-              if (kbase + pc * 32 + c < args.ntok) mx = fmaxf(mx, s0); else a = 0.f;
-              if (kbase + pc * 32 + c + 1 < args.ntok) mx = fmaxf(mx, s1); else b = 0.f;
-            }
-            rs += a + b;                            // fp32 row sum of the un-rounded probabilities (as flash-attention)
-            pk[c >> 1] = TT::pack2(a, b);
-          }
-        };
-        // columns pc*32 .. +31 of this row -> K-block pc>>1, 16-byte chunks (pc&1)*4 .. +3 (128B-swizzled A operand)
-        auto put = [&](const uint32_t (&pk)[16], int pc) {
-          const uint32_t base = sP_row + (pc >> 1) * (128 * 128);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int chunk = (pc & 1) * 4 + c4;
-            sts128a(base + ((chunk ^ (row & 7)) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
-          }
-        };
-        // full (re)computation of P_j with reference mref (TMEM loads software-pipelined)
-        auto full_pass = [&](float mref) {
-          float dummy = -INFINITY;
-          uint32_t pk[16];
-          rs = 0.f;
-          tmem_ld32(tS, va);
-          tmem_ld_wait();
-          tmem_ld32(tS + 32, vb);
-          expo(va, 0, mref, pk, dummy); put(pk, 0);
-          tmem_ld_wait();
-          tmem_ld32(tS + 64, va);
-          expo(vb, 1, mref, pk, dummy); put(pk, 1);
-          tmem_ld_wait();
-          tmem_ld32(tS + 96, vb);
-          expo(va, 2, mref, pk, dummy); put(pk, 2);
-          tmem_ld_wait();
-          expo(vb, 3, mref, pk, dummy); put(pk, 3);
-        };
-        if (j == 0) {
-          // ---- first chunk: explicit max pass, then the exp pass
-          float mx = -INFINITY;
+        // ---- pass 1: row max of the raw scores (scale > 0, applied once), TMEM loads software-pipelined
+        float mx = -INFINITY;
+        {
+          uint32_t va[32], vb[32];
           auto red = [&](const uint32_t (&v)[32], int pc) {
+            if (!tail) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (!tail || kbase + pc * 32 + c < args.ntok) mx = fmaxf(mx, __uint_as_float(v[c]));
+              for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (kbase + pc * 32 + c < args.ntok) mx = fmaxf(mx, __uint_as_float(v[c]));
+            }
           };
           tmem_ld32(tS, va);
           tmem_ld_wait();
@@ -289,19 +249,18 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
           red(va, 2);
           tmem_ld_wait();
           red(vb, 3);
-          m = mx * args.scale_log2e;                // chunk 0 always holds valid keys -> finite
-          corr = 0.f;                               // nothing accumulated yet
-          full_pass(m);
-        } else {
-          // ---- later chunks: ONE optimistic pass with the current reference max m (FA4-style lazy rescaling): the
-          // probabilities stay exact as long as the chunk max does not exceed m by more than 2^8; otherwise (rare) the
-          // whole warp recomputes the chunk against the new max.
-          float mx = -INFINITY;
-          uint32_t pk[16];
-          mbar_wait(&o_full[g], ofull_cnt & 1);     // PV_{j-1} retired: P smem is free, O(j-1) sits in X[(j-1)&1][0:64)
-          ++ofull_cnt;
-          tc_fence_after();
-          {
+        }
+        const float m_new = fmaxf(m, mx * args.scale_log2e);   // chunk 0 always has valid keys -> finite
+        const float corr = ex2(m - m_new);
+        m = m_new;
+        // ---- pass 2: P = exp2(s*scale - m) -> 16-bit -> swizzled smem (A operand of the PV MMA)
+        float rs = 0.f;
+        {
+          uint32_t va[32], vb[32];
+          if (j > 0) {                              // PV_{j-1} retired: P smem is free, O(j-1) sits in X[(j-1)&1][0:64)
+            mbar_wait(&o_full[g], ofull_cnt & 1);
+            ++ofull_cnt;
+            tc_fence_after();
             const uint32_t t = tX + ((j - 1) & 1) * 128;
             tmem_ld32(t, va);
             tmem_ld32(t + 32, vb);
@@ -315,24 +274,38 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
             mbar_arrive(&x_free[2 * g + ((j - 1) & 1)]);   // buffer (j-1)&1 may now receive S(j+1)
           }
           tmem_ld32(tS, va);
+          auto emit = [&](const uint32_t (&v)[32], int pc) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              float a = ex2(fmaf(__uint_as_float(v[c]), args.scale_log2e, -m_new));
+              float b = ex2(fmaf(__uint_as_float(v[c + 1]), args.scale_log2e, -m_new));
+              if (tail) {
+                if (kbase + pc * 32 + c >= args.ntok) a = 0.f;
+                if (kbase + pc * 32 + c + 1 >= args.ntok) b = 0.f;
+              }
+              rs += a + b;                          // fp32 row sum of the un-rounded probabilities (as flash-attention)
+              pk[c >> 1] = TT::pack2(a, b);
+            }
+            // columns pc*32 .. +31 -> K-block pc>>1, 16-byte chunks (pc&1)*4 .. +3 of this row
+            const uint32_t base = sP_row + (pc >> 1) * (128 * 128);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int chunk = (pc & 1) * 4 + c4;
+              sts128a(base + ((chunk ^ (row & 7)) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+            }
+          };
           tmem_ld_wait();
           tmem_ld32(tS + 32, vb);
-          expo(va, 0, m, pk, mx); put(pk, 0);
+          emit(va, 0);
           tmem_ld_wait();
           tmem_ld32(tS + 64, va);
-          expo(vb, 1, m, pk, mx); put(pk, 1);
+          emit(vb, 1);
           tmem_ld_wait();
           tmem_ld32(tS + 96, vb);
-          expo(va, 2, m, pk, mx); put(pk, 2);
+          emit(va, 2);
           tmem_ld_wait();
-          expo(vb, 3, m, pk, mx); put(pk, 3);
-          const float m_cand = mx * args.scale_log2e;
-          if (__any_sync(0xffffffffu, m_cand > m + 8.0f)) {
-            const float m_new = fmaxf(m, m_cand);
-            corr = ex2(m - m_new);
-            m = m_new;
-            full_pass(m);
-          }
+          emit(vb, 3);
         }
         tc_fence_before();                         // all reads of S_g(j) done: PV(j) may overwrite X[j&1][0:64)
         fence_proxy_async();                       // make the generic-proxy P writes visible to the MMA (async proxy)
