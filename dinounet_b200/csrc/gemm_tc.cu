@@ -381,7 +381,21 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
     m_tiles = static_cast<long long>(p->B) * a.tiles_x * a.tiles_y;
     a.M = p->B * a.Ho * a.Wo;
     const int64_t C = p->C;
-    if (stride == 1) {
+    // halo-reuse mode (option 2 != 0 disables): stride 1, <= 64 input channels, <= 64 output channels, rows of >= 128 px.
+    // One [3 x 130 px] halo box per 128-pixel output row segment feeds all 9 taps (3x instead of 9x L2 -> SM traffic).
+    const int halo_opt = get_option(2);
+    if (v2 && halo_opt != 1 && stride == 1 && p->C <= 64 && p->N <= 64 && a.Wo % 128 == 0) {
+      a.conv = 3;
+      a.TW = 128; a.TH = 1; a.tiles_x = a.Wo / 128; a.tiles_y = a.Ho;
+      m_tiles = static_cast<long long>(p->B) * a.tiles_x * a.tiles_y;
+      a.halo_stages = bn <= 32 ? 3 : 2;
+      a.halo_base_offset = halo_opt == 2 ? 0 : 1;
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p->Win, (cuuint64_t)p->Hin, (cuuint64_t)p->B};
+      cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * p->Win * 2, (cuuint64_t)C * p->Win * p->Hin * 2};
+      cuuint32_t box[4] = {BK, 130, 3, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      if ((rc = encode_tensor_map(&maps.a[0], p->dtype, 4, p->A, dims, strides, box, estr))) return rc;
+    } else if (stride == 1) {
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p->Win, (cuuint64_t)p->Hin, (cuuint64_t)p->B};
       cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * p->Win * 2, (cuuint64_t)C * p->Win * p->Hin * 2};
       cuuint32_t box[4] = {BK, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};

@@ -18,6 +18,10 @@
 
 namespace b2u {
 
+constexpr int kHaloW = 130;                           // 128 output pixels + 1 halo pixel on each side
+constexpr int kHaloBytes = 3 * kHaloW * 128;           // one TMA box: 3 rows x 130 px x 64 ch x 2 B
+constexpr int kHaloStageBytes = 49 * 1024;             // box rounded up to the 1024 B swizzle period
+
 constexpr int kRopeBytes = 128 * 16 * 2 * 4;   // (rope_h + rope_w <= 128) rows x 16 angles x {sin, cos} fp32
 
 template <int BN, int EPI = 0> struct Cfg2 {
@@ -30,6 +34,8 @@ template <int BN, int EPI = 0> struct Cfg2 {
   static constexpr int kBiasBytes = BN * 4;
   static constexpr int kRope = EPI == 2 ? kRopeBytes : 0;
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + kRope + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kHaloStages = BN <= 32 ? 3 : 2;
+  static constexpr int kSmemHalo = kHaloStages * kHaloStageBytes + 9 * kBBytes + kStagingBytes + kBiasBytes + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
@@ -95,14 +101,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   using TT = T16<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  // conv == 3 ("halo" mode): stages hold one [3 rows][130 px][128 B] input halo each, followed by the 9 resident weight
+  // taps; otherwise the {A, W} k-block ring of Cfg2.  (Barrier arrays are sized for the larger stage count.)
+  const bool halo = args.conv == 3;
+  const int nstages = halo ? args.halo_stages : C::kStages;
+  const int stage_bytes = halo ? kHaloStageBytes : C::kStageBytes;
+  uint8_t* s_wtaps = smem + nstages * stage_bytes;                       // halo mode only: 9 x [BN x 128 B]
+  uint8_t* staging = s_wtaps + (halo ? 9 * C::kBBytes : 0);
   float* s_bias = reinterpret_cast<float*>(staging + C::kStagingBytes);
   float* s_rope = reinterpret_cast<float*>(staging + C::kStagingBytes + C::kBiasBytes);   // [h+w][32] = (sin16 | cos16)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes + C::kBiasBytes + C::kRope);
-  uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,7 +124,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(w_bar, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
     fence_mbar_init();
   }
@@ -141,6 +155,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (halo) {   // the 9 weight taps stay resident in smem for the whole kernel (n_tiles == 1)
+        mbar_expect_tx(w_bar, 9 * C::kBBytes);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_wtaps + tap * C::kBBytes, &maps.b, w_bar, tap * BK, 0);
+      }
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = static_cast<int>(tile % args.n_tiles);
         const int mt = static_cast<int>(tile / args.n_tiles);
@@ -151,6 +169,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           const int r = mt - img * per_img;
           y0 = (r / args.tiles_x) * args.TH;
           x0 = (r % args.tiles_x) * args.TW;
+        }
+        if (halo) {
+          // one TMA box per tile: channels [0,64) x pixels [x0-1, x0+129) x rows [y0-1, y0+2) (OOB = zero padding)
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kHaloBytes);
+          tma_load_4d(smem + stage * stage_bytes, &maps.a[0], &full_bar[stage], 0, x0 - 1, y0 - 1, img);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          continue;
         }
         for (int kb = 0; kb < args.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -188,6 +214,28 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
+        if (halo) {
+          if (it == 0) { mbar_wait(w_bar, 0); }
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sH = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sW = smem_u32(s_wtaps);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            // A = 128 consecutive pixels of halo row dy starting at pixel dx: a shifted window of the swizzled halo tile;
+            // its start is only 128 B-aligned, so the descriptor carries the swizzle phase in base_offset
+            const uint32_t aaddr = sH + (dy * kHaloW + dx) * 128;
+            uint64_t da = make_desc_k128(aaddr);
+            if (args.halo_base_offset) da |= static_cast<uint64_t>((aaddr >> 7) & 7) << 49;
+            const uint64_t db = make_desc_k128(sW + tap * C::kBBytes);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_f16(tacc, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (tap | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        } else {
         for (int kb = 0; kb < args.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -199,6 +247,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             tc_mma_f16(tacc, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
         }
         tc_commit(&tfull_bar[buf]);
       }
@@ -510,15 +559,18 @@ template <int BN, int EPI, int ACT1, int ACT2, typename T>
 static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
   auto kern = gemm_tc2_kernel<BN, EPI, ACT1, ACT2, T>;
   static bool configured = false;
+  constexpr int kMaxSmem = (BN <= 64 && Cfg2<BN, EPI>::kSmemHalo > Cfg2<BN, EPI>::kSmem) ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN, EPI>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(e));
     configured = true;
   }
+  if (args.conv == 3 && (BN > 64 || args.halo_stages != Cfg2<BN, EPI>::kHaloStages))
+    return set_error(-3, "gemm_tc2: halo conv mode needs BLOCK_N <= 64");
   const long long tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
   const int sms = num_sms();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kern<<<grid, 320, Cfg2<BN, EPI>::kSmem, stream>>>(maps, args);
+  kern<<<grid, 320, args.conv == 3 ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem, stream>>>(maps, args);
   return check_launch("gemm_tc2");
 }
 

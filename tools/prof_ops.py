@@ -50,6 +50,8 @@ elif op == "conv":   # decoder 512^2 conv 64 -> 32
 else:
     raise SystemExit("unknown op")
 
+if len(sys.argv) > 3:
+    lib.b2u_set_option(int(sys.argv[3]), int(sys.argv[4]))
 for _ in range(reps):
     run()
 torch.cuda.synchronize()
