@@ -34,7 +34,7 @@ struct GemmArgs {
   void* v;
   int npad;  // > 0: V is written transposed as V^T [B, heads, 64, npad]
   int rope_h, rope_w;  // > 0: separable rope tables staged in smem
-  int halo_stages, halo_base_offset;  // conv == 3 (halo-reuse 3x3 mode)
+  int halo_stages;  // conv == 3 (halo-reuse 3x3 mode)
 };
 
 int num_sms();

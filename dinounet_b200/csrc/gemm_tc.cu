@@ -389,7 +389,6 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
       a.TW = 128; a.TH = 1; a.tiles_x = a.Wo / 128; a.tiles_y = a.Ho;
       m_tiles = static_cast<long long>(p->B) * a.tiles_x * a.tiles_y;
       a.halo_stages = bn <= 32 ? 3 : 2;
-      a.halo_base_offset = halo_opt == 2 ? 0 : 1;
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p->Win, (cuuint64_t)p->Hin, (cuuint64_t)p->B};
       cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * p->Win * 2, (cuuint64_t)C * p->Win * p->Hin * 2};
       cuuint32_t box[4] = {BK, 130, 3, 1};

@@ -223,11 +223,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const int dy = tap / 3, dx = tap - dy * 3;
-            // A = 128 consecutive pixels of halo row dy starting at pixel dx: a shifted window of the swizzled halo tile;
-            // its start is only 128 B-aligned, so the descriptor carries the swizzle phase in base_offset
+            // A = 128 consecutive pixels of halo row dy starting at pixel dx: a shifted window of the swizzled halo tile.
+            // Its start is only 128 B-aligned; measured on B200 (tools/halo_probe.py): the 128B swizzle is a function of the
+            // absolute smem address, so the descriptor needs NO base_offset (setting it to (addr>>7)&7 gives wrong data).
             const uint32_t aaddr = sH + (dy * kHaloW + dx) * 128;
-            uint64_t da = make_desc_k128(aaddr);
-            if (args.halo_base_offset) da |= static_cast<uint64_t>((aaddr >> 7) & 7) << 49;
+            const uint64_t da = make_desc_k128(aaddr);
             const uint64_t db = make_desc_k128(sW + tap * C::kBBytes);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)

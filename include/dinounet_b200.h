@@ -204,7 +204,7 @@ int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream);
  * 1 = the first-generation one-tile-per-CTA kernel. */
 /* key 1 (B2U_OPT_MSDA_IMPL): 0 = shared-memory value-slab gather (default), 1 = first-generation warp-per-query kernel. */
 /* key 2 (B2U_OPT_CONV_HALO): 0 = 3x3 convs with <= 64 in/out channels and >= 128-px rows use the halo-reuse mode
- * (default), 1 = always the per-tap TMA walk, 2 = halo mode without descriptor base_offset (bring-up experiment). */
+ * (default), 1 = always the per-tap TMA walk. */
 enum { B2U_OPT_GEMM_IMPL = 0, B2U_OPT_MSDA_IMPL = 1, B2U_OPT_CONV_HALO = 2 };
 int b2u_set_option(int32_t key, int32_t value);
 
