@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="dinounet_l", choices=["dinounet_s", "dinounet_b", "dinounet_l"])
@@ -49,7 +49,8 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clock / throttle-reason sampling (B200_PROFILING.md clocks line).  Started before the warm-up (the tool
+    needs ~1 s to emit its first line); `summary(t0, t1)` keeps only the samples that arrived inside the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -59,7 +60,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -68,20 +69,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
             self.proc.terminate()
             self.t.join(timeout=2)
 
-    def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.06 and r and r[0].isdigit()]
+        if not rows:   # region shorter than the sampling period: fall back to the samples nearest to it
+            rows = [r for t, r in self.rows if t0 - 0.5 <= t <= t1 + 0.5 and r and r[0].isdigit()]
+        sm = sorted(int(r[0]) for r in rows)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in rows)}
 
 
 def cpu_forward_patches_per_s(model, size, n_patches, threads=None):
@@ -174,7 +179,7 @@ def main():
             return gather_logits(logits, B * world)      # the ONE collective of the step (NCCL all-gather)
         return logits
 
-    with torch.no_grad():
+    with torch.no_grad(), ClockSampler(local) as clk:
         for i in range(W):
             step(i)
         torch.cuda.synchronize()
@@ -182,12 +187,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
-            e0.record()
-            for i in range(K):
-                step(i)
-            e1.record()
-            torch.cuda.synchronize()
+        t_region0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t_region1 = time.perf_counter()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -272,7 +278,7 @@ def main():
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                     "d2h_bytes_per_step": B * 2 * S * S * 4},
             "gpu_launches": K * n_kernels, "kernels_per_step": n_kernels,
-            "clocks": clk.summary(),
+            "clocks": clk.summary(t_region0, t_region1),
             "roofline": roof, "cpu_baseline": cpu,
             "model_tflops": value / world * total_flops / 1e12,
             "breakdown_ms": {k: round(v, 3) for k, v in list(breakdown.items())[:14]},
