@@ -251,7 +251,7 @@ def main():
             t_gemm = sum(fam.get(k, 0) for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2"))
             pk = peaks()
             ach = flops / (t_gemm * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*,bf16> (ViT qkv/proj/fc1/fc2, %d launches/step)" % (4 * v.depth),
+            roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel<256,EPI,ACT,%s> = persistent tcgen05 GEMM (ViT qkv/proj/fc1/fc2, %d launches/step)" % (a.vit_dtype, 4 * v.depth),
                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
                     "peak_source": pk["src"] + " (bf16 sustained)", "share_of_step": t_gemm / sum(fam.values())}
             if a.ops_out:
