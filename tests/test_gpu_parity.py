@@ -151,3 +151,17 @@ def test_cuda_graph_replay_matches_eager_launches():
         yg2, _ = eng.forward(x, use_graph=True)
     torch.cuda.synchronize()
     assert torch.equal(yg, y) and torch.equal(yg2, y)
+
+
+def test_streamed_predictor_matches_direct_forward():
+    from dinounet_b200.inference import StreamedPredictor
+    model = "dinounet_s"
+    sd = O.make_state_dict(model, 2, seed=0)
+    net = _net(model, sd)
+    xs = [O.make_input(2, 128, 10 + i).pin_memory() for i in range(5)]
+    with torch.no_grad():
+        direct = [net(x.cuda()).cpu() for x in xs]
+    outs = [y.clone() for y in StreamedPredictor(net).run(xs)]
+    assert len(outs) == 5 and all(torch.equal(a, b) for a, b in zip(outs, direct))
+    labs = [y.clone() for y in StreamedPredictor(net, want_labels=True).run(xs)]
+    assert all(torch.equal(l.long(), d.argmax(1)) for l, d in zip(labs, direct))
