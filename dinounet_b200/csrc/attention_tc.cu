@@ -24,6 +24,7 @@ struct alignas(64) AttnMaps {
 };
 struct AttnArgs {
   int BH, heads, ntok, npairs, nchunks;
+  int q_begin;   // first query row handled by this launch (rows [q_begin, ntok)); keys always span [0, ntok)
   long long items;
   float scale_log2e;
   void* out;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         const int bh = static_cast<int>(item / args.npairs);
         const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
         for (int g = 0; g < 2; ++g) {
-          const int q0 = (pair * 2 + g) * 128;
+          const int q0 = args.q_begin + (pair * 2 + g) * 128;
           if (q0 >= args.ntok) continue;
           mbar_wait(&q_free[g], (qfree_cnt[g] & 1) ^ 1);
           ++qfree_cnt[g];
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
         const int bh = static_cast<int>(item / args.npairs);
         const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
-        const int nq = ((pair * 2 + 1) * 128 < args.ntok) ? 2 : 1;
+        const int nq = (args.q_begin + (pair * 2 + 1) * 128 < args.ntok) ? 2 : 1;
         for (int g = 0; g < nq; ++g) { mbar_wait(&q_full[g], qfull_cnt[g] & 1); ++qfull_cnt[g]; }
         // `stage`/`kv_phase` track chunk j (whose V the PV MMA uses); S runs one chunk ahead.
         int st1; uint32_t ph1;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
       const int bh = static_cast<int>(item / args.npairs);
       const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
-      const int q0 = (pair * 2 + g) * 128;
+      const int q0 = args.q_begin + (pair * 2 + g) * 128;
       if (q0 >= args.ntok) continue;        // this group has no query tile in this item (warp-uniform)
       float m = -INFINITY, l = 0.f, corr_prev = 0.f;
       float o[64];
@@ -370,8 +371,98 @@ static int make_map_3d(CUtensorMap* map, const void* base, int dtype, uint64_t d
   return encode_tensor_map(map, dtype, 3, base, dims, strides, box, estr);
 }
 
+// ---- few-row companion (the cls/storage prefix rows): one warp per query row, exact fp32 softmax --------------------
+template <typename T>
+__global__ void __launch_bounds__(256) attn_rows_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                        const T* __restrict__ vt, T* __restrict__ out, int heads, int ntok,
+                                                        int npad, int row_begin, int nrows, float scale_log2e) {
+  extern __shared__ float sp[];                       // [warps][npad] un-normalised probabilities
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int bh = blockIdx.x;
+  const T* kb = k + static_cast<size_t>(bh) * ntok * 64;
+  const T* vb = vt + static_cast<size_t>(bh) * 64 * npad;
+  float* p = sp + warp * npad;
+  for (int r = warp; r < nrows; r += nw) {
+    const int t = row_begin + r;
+    const T* qr = q + (static_cast<size_t>(bh) * ntok + t) * 64;
+    float qf[64];
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(qr + j);
+      const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), d = T16<T>::unpack2(u.w);
+      qf[j] = a.x; qf[j + 1] = a.y; qf[j + 2] = b.x; qf[j + 3] = b.y; qf[j + 4] = c.x; qf[j + 5] = c.y; qf[j + 6] = d.x; qf[j + 7] = d.y;
+    }
+    float mx = -INFINITY;
+    for (int key = lane; key < ntok; key += 32) {
+      const T* kr = kb + static_cast<size_t>(key) * 64;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; j += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(kr + j);
+        const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), d = T16<T>::unpack2(u.w);
+        s = fmaf(qf[j], a.x, s); s = fmaf(qf[j + 1], a.y, s); s = fmaf(qf[j + 2], b.x, s); s = fmaf(qf[j + 3], b.y, s);
+        s = fmaf(qf[j + 4], c.x, s); s = fmaf(qf[j + 5], c.y, s); s = fmaf(qf[j + 6], d.x, s); s = fmaf(qf[j + 7], d.y, s);
+      }
+      s *= scale_log2e;
+      p[key] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int key = lane; key < ntok; key += 32) {
+      const float e = ex2(p[key] - mx);
+      const float er = T16<T>::to_f(T16<T>::from_f(e));   // the PV product uses 16-bit probabilities like the MMA path
+      p[key] = er;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int key = ntok + lane; key < npad; key += 32) p[key] = 0.f;   // padding keys contribute exactly zero
+    __syncwarp();
+    const int b = bh / heads, hd = bh - b * heads;
+    T* orow = out + (static_cast<size_t>(b) * ntok + t) * (heads * 64) + hd * 64;
+    for (int d = lane; d < 64; d += 32) {
+      const T* vr = vb + static_cast<size_t>(d) * npad;
+      float acc = 0.f;
+      for (int key = 0; key < npad; key += 8) {          // npad is a multiple of 8; V^T and p are zero in the padding
+        const uint4 u = *reinterpret_cast<const uint4*>(vr + key);
+        const float2 a = T16<T>::unpack2(u.x), bb = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), dd = T16<T>::unpack2(u.w);
+        const float* pp = p + key;
+        acc = fmaf(pp[0], a.x, acc); acc = fmaf(pp[1], a.y, acc); acc = fmaf(pp[2], bb.x, acc); acc = fmaf(pp[3], bb.y, acc);
+        acc = fmaf(pp[4], c.x, acc); acc = fmaf(pp[5], c.y, acc); acc = fmaf(pp[6], dd.x, acc); acc = fmaf(pp[7], dd.y, acc);
+      }
+      orow[d] = T16<T>::from_f(acc / sum);
+    }
+    __syncwarp();
+  }
+}
+
+extern "C" int b2u_attention_rows(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,
+                                  int32_t ntok, int32_t npad, int32_t row_begin, int32_t nrows, float scale, int32_t dtype,
+                                  b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!q || !k || !vt || !out) return set_error(-1, "b2u_attention_rows: null pointer");
+  if (nrows <= 0) return 0;
+  if (npad % 8 || npad < ntok || row_begin < 0 || row_begin + nrows > ntok) return set_error(-1, "b2u_attention_rows: bad range");
+  const int warps = nrows < 8 ? nrows : 8;
+  const size_t smem = static_cast<size_t>(warps) * npad * sizeof(float);
+  if (smem > 48 * 1024) return set_error(-1, "b2u_attention_rows: ntok too large for the few-row kernel");
+  const float sl2 = scale * 1.4426950408889634f;
+  if (dtype == B2U_BF16)
+    attn_rows_kernel<__nv_bfloat16><<<B * heads, warps * 32, smem, stream>>>(
+        static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(vt),
+        static_cast<__nv_bfloat16*>(out), heads, ntok, npad, row_begin, nrows, sl2);
+  else
+    attn_rows_kernel<__half><<<B * heads, warps * 32, smem, stream>>>(
+        static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(vt),
+        static_cast<__half*>(out), heads, ntok, npad, row_begin, nrows, sl2);
+  return check_launch("attention_rows");
+}
+
 extern "C" int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,
-                                int32_t ntok, int32_t npad, float scale, int32_t dtype, b2u_stream_t stream_) {
+                                int32_t ntok, int32_t npad, int32_t q_begin, float scale, int32_t dtype,
+                                b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!q || !k || !vt || !out) return set_error(-1, "b2u_attention_tc: null pointer");
   if (npad % 8 || npad < ntok) return set_error(-1, "b2u_attention_tc: npad must be a multiple of 8 and >= ntok");
@@ -380,8 +471,10 @@ extern "C" int b2u_attention_tc(const void* q, const void* k, const void* vt, vo
   a.BH = B * heads;
   a.heads = heads;
   a.ntok = ntok;
+  if (q_begin < 0 || q_begin >= ntok) return set_error(-1, "b2u_attention_tc: bad q_begin");
+  a.q_begin = q_begin;
   a.nchunks = (ntok + 127) / 128;
-  a.npairs = (a.nchunks + 1) / 2;
+  a.npairs = ((ntok - q_begin + 127) / 128 + 1) / 2;
   a.items = static_cast<long long>(a.BH) * a.npairs;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.out = out;

@@ -294,7 +294,11 @@ class ForwardEngine:
             plan.keep.append(qp)
             plan.add(f"b{i}.qkv", lib.b2u_qkv_rope, C.byref(qp))
             if self.attn_impl == "tc":
-                plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 64 ** -0.5, vt)
+                # the P patch-token rows fill whole 128-row tiles; the 5 cls/storage rows go to the few-row kernel
+                plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad,
+                         cfg.N_PREFIX, 64 ** -0.5, vt)
+                plan.add(f"b{i}.attnp", lib.b2u_attention_rows, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 0,
+                         cfg.N_PREFIX, 64 ** -0.5, vt)
             else:
                 plan.add(f"b{i}.attn", lib.b2u_attention, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, 64 ** -0.5, vt)
             self._gemm(plan, f"b{i}.proj", O, T, D, D, w[f"b{i}.proj"], D, X, D, vt, out_fp32=True, bias=w[f"b{i}.projb"],

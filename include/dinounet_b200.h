@@ -106,9 +106,16 @@ int b2u_attention(const void* q, const void* k, const void* v, void* out, int32_
                   float scale, int32_t dtype, b2u_stream_t stream);
 
 /* tcgen05 / TMEM flash attention (same math as b2u_attention): q,k [B, heads, ntok, 64], vt = V^T [B, heads, 64, npad]
- * with zero padding columns (see b2u_qkv_params.v_transposed) -> out [B, ntok, heads*64]. */
+ * with zero padding columns (see b2u_qkv_params.v_transposed) -> out [B, ntok, heads*64].  Only the query rows
+ * [q_begin, ntok) are produced (128-row tiles, two per work item); keys always span [0, ntok).  With q_begin = the
+ * number of cls/storage tokens the ViT's 1024 patch rows fill whole tiles and b2u_attention_rows does the prefix. */
 int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads, int32_t ntok,
-                     int32_t npad, float scale, int32_t dtype, b2u_stream_t stream);
+                     int32_t npad, int32_t q_begin, float scale, int32_t dtype, b2u_stream_t stream);
+
+/* Few-row attention (same layouts as b2u_attention_tc): query rows [row_begin, row_begin + nrows), one warp per row,
+ * fp32 softmax.  Meant for the handful of prefix-token rows. */
+int b2u_attention_rows(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads, int32_t ntok,
+                       int32_t npad, int32_t row_begin, int32_t nrows, float scale, int32_t dtype, b2u_stream_t stream);
 
 /* LayerNorm over the last dim (block.py:193-194, vision_transformer.py:300, dinov3_adapter.py:142-148):
  *   in fp32 [rows_sel, D] -> out (16-bit or fp32).  Row selection: for output row r,

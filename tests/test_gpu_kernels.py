@@ -207,14 +207,22 @@ def test_attention_tcgen05(dtype, B, Hh, N):
     vt = torch.zeros(B, Hh, 64, npad, device=DEV, dtype=td)
     vt[..., :N] = v.transpose(2, 3)
     out = torch.full((B, N, Hh * 64), float("nan"), device=DEV, dtype=td)
-    L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out), B, Hh, N, npad, 0.125, dtype, stream()), "attention_tc")
+    L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out), B, Hh, N, npad, 0, 0.125, dtype, stream()), "attention_tc")
     torch.cuda.synchronize()
     ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, Hh * 64)
     assert torch.isfinite(out.float()).all()
     assert rel_err(out, ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -8), rel_err(out, ref)
+    # split launch: rows [5, N) on the tcgen05 kernel + rows [0, 5) on the few-row kernel == the whole thing
+    if N > 5:
+        outs = torch.full_like(out, float("nan"))
+        L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(outs), B, Hh, N, npad, 5, 0.125, dtype, stream()), "attention_tc")
+        L.check(lib.b2u_attention_rows(P(q), P(k), P(vt), P(outs), B, Hh, N, npad, 0, 5, 0.125, dtype, stream()), "rows")
+        torch.cuda.synchronize()
+        assert torch.isfinite(outs.float()).all()
+        assert rel_err(outs, ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -8), rel_err(outs, ref)
     # second launch on the same buffers (persistent-loop barrier phases must be clean at exit)
     out2 = torch.empty_like(out)
-    L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out2), B, Hh, N, npad, 0.125, dtype, stream()), "attention_tc")
+    L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out2), B, Hh, N, npad, 0, 0.125, dtype, stream()), "attention_tc")
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
 
