@@ -371,70 +371,132 @@ static int make_map_3d(CUtensorMap* map, const void* base, int dtype, uint64_t d
   return encode_tensor_map(map, dtype, 3, base, dims, strides, box, estr);
 }
 
-// ---- few-row companion (the cls/storage prefix rows): one warp per query row, exact fp32 softmax --------------------
+// ---- few-row companion (the cls/storage prefix rows): one CTA per (batch, head), up to 8 query rows -----------------
+// phase 1: thread <-> key: each K row is read once (8 x 16 B) and dotted with all query rows (smem broadcast);
+// phase 2: exact fp32 softmax per row (block reductions); phase 3: thread <-> (d, key quarter) streams V^T rows
+// (keys contiguous) against the probabilities in smem; the 4 key quarters are reduced through smem.
+constexpr int AR_MAXROWS = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) attn_rows_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                         const T* __restrict__ vt, T* __restrict__ out, int heads, int ntok,
                                                         int npad, int row_begin, int nrows, float scale_log2e) {
-  extern __shared__ float sp[];                       // [warps][npad] un-normalised probabilities
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  extern __shared__ float smf[];
+  float* sq = smf;                                   // [8][64]
+  float* sp = sq + AR_MAXROWS * 64;                  // [8][npad]
+  float* red = sp + AR_MAXROWS * npad;               // [8][8]  per-warp partials, then [8] results in red[0..7]
+  float* so = red + AR_MAXROWS * 8 + AR_MAXROWS;     // [4][8][64]
+  float* res = red + AR_MAXROWS * 8;                 // [8] row max, later row sum
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.x;
   const T* kb = k + static_cast<size_t>(bh) * ntok * 64;
   const T* vb = vt + static_cast<size_t>(bh) * 64 * npad;
-  float* p = sp + warp * npad;
-  for (int r = warp; r < nrows; r += nw) {
-    const int t = row_begin + r;
-    const T* qr = q + (static_cast<size_t>(bh) * ntok + t) * 64;
-    float qf[64];
+  for (int i = tid; i < nrows * 64; i += 256)
+    sq[i] = T16<T>::to_f(q[(static_cast<size_t>(bh) * ntok + row_begin + (i >> 6)) * 64 + (i & 63)]);
+  __syncthreads();
+  // ---- phase 1: scores
+  float mx[AR_MAXROWS];
 #pragma unroll
-    for (int j = 0; j < 64; j += 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(qr + j);
+  for (int r = 0; r < AR_MAXROWS; ++r) mx[r] = -INFINITY;
+  for (int key = tid; key < ntok; key += 256) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * 64);
+    float sc[AR_MAXROWS];
+#pragma unroll
+    for (int r = 0; r < AR_MAXROWS; ++r) sc[r] = 0.f;
+#pragma unroll
+    for (int j8 = 0; j8 < 8; ++j8) {
+      const uint4 u = __ldg(kr + j8);
       const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), d = T16<T>::unpack2(u.w);
-      qf[j] = a.x; qf[j + 1] = a.y; qf[j + 2] = b.x; qf[j + 3] = b.y; qf[j + 4] = c.x; qf[j + 5] = c.y; qf[j + 6] = d.x; qf[j + 7] = d.y;
-    }
-    float mx = -INFINITY;
-    for (int key = lane; key < ntok; key += 32) {
-      const T* kr = kb + static_cast<size_t>(key) * 64;
-      float s = 0.f;
+      const float kv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
-      for (int j = 0; j < 64; j += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(kr + j);
-        const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), d = T16<T>::unpack2(u.w);
-        s = fmaf(qf[j], a.x, s); s = fmaf(qf[j + 1], a.y, s); s = fmaf(qf[j + 2], b.x, s); s = fmaf(qf[j + 3], b.y, s);
-        s = fmaf(qf[j + 4], c.x, s); s = fmaf(qf[j + 5], c.y, s); s = fmaf(qf[j + 6], d.x, s); s = fmaf(qf[j + 7], d.y, s);
+      for (int r = 0; r < AR_MAXROWS; ++r) {
+        if (r < nrows) {
+          const float* qq = sq + r * 64 + j8 * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sc[r] = fmaf(qq[e], kv[e], sc[r]);
+        }
       }
-      s *= scale_log2e;
-      p[key] = s;
-      mx = fmaxf(mx, s);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int key = lane; key < ntok; key += 32) {
-      const float e = ex2(p[key] - mx);
-      const float er = T16<T>::to_f(T16<T>::from_f(e));   // the PV product uses 16-bit probabilities like the MMA path
-      p[key] = er;
-      sum += e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    for (int key = ntok + lane; key < npad; key += 32) p[key] = 0.f;   // padding keys contribute exactly zero
-    __syncwarp();
-    const int b = bh / heads, hd = bh - b * heads;
-    T* orow = out + (static_cast<size_t>(b) * ntok + t) * (heads * 64) + hd * 64;
-    for (int d = lane; d < 64; d += 32) {
-      const T* vr = vb + static_cast<size_t>(d) * npad;
-      float acc = 0.f;
-      for (int key = 0; key < npad; key += 8) {          // npad is a multiple of 8; V^T and p are zero in the padding
-        const uint4 u = *reinterpret_cast<const uint4*>(vr + key);
-        const float2 a = T16<T>::unpack2(u.x), bb = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), dd = T16<T>::unpack2(u.w);
-        const float* pp = p + key;
-        acc = fmaf(pp[0], a.x, acc); acc = fmaf(pp[1], a.y, acc); acc = fmaf(pp[2], bb.x, acc); acc = fmaf(pp[3], bb.y, acc);
-        acc = fmaf(pp[4], c.x, acc); acc = fmaf(pp[5], c.y, acc); acc = fmaf(pp[6], dd.x, acc); acc = fmaf(pp[7], dd.y, acc);
+    for (int r = 0; r < AR_MAXROWS; ++r) {
+      if (r < nrows) {
+        const float v = sc[r] * scale_log2e;
+        sp[r * npad + key] = v;
+        mx[r] = fmaxf(mx[r], v);
       }
-      orow[d] = T16<T>::from_f(acc / sum);
     }
-    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < AR_MAXROWS; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+    if (lane == 0) red[r * 8 + warp] = mx[r];
+  }
+  __syncthreads();
+  if (tid < AR_MAXROWS) {
+    float m = red[tid * 8];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[tid * 8 + w]);
+    res[tid] = m;
+  }
+  __syncthreads();
+  // ---- phase 2: probabilities (16-bit rounded for the PV product, like the MMA path) and fp32 row sums
+  float sm[AR_MAXROWS];
+#pragma unroll
+  for (int r = 0; r < AR_MAXROWS; ++r) sm[r] = 0.f;
+  for (int key = tid; key < npad; key += 256) {
+#pragma unroll
+    for (int r = 0; r < AR_MAXROWS; ++r) {
+      if (r < nrows) {
+        float e = 0.f;
+        if (key < ntok) { e = ex2(sp[r * npad + key] - res[r]); sm[r] += e; }
+        sp[r * npad + key] = T16<T>::to_f(T16<T>::from_f(e));
+      }
+    }
+  }
+  __syncthreads();   // everyone has read res[] (row max) before it is reused for the sums
+#pragma unroll
+  for (int r = 0; r < AR_MAXROWS; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
+    if (lane == 0) red[r * 8 + warp] = sm[r];
+  }
+  __syncthreads();
+  if (tid < AR_MAXROWS) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[tid * 8 + w];
+    res[tid] = t;
+  }
+  // ---- phase 3: O[r][d] = sum_key p[r][key] * V^T[d][key]
+  {
+    const int d = tid & 63, part = tid >> 6;
+    const int per = ((npad / 8 + 3) / 4) * 8;                 // keys per quarter, multiple of 8
+    const int k0 = part * per, k1 = min(npad, k0 + per);
+    const T* vr = vb + static_cast<size_t>(d) * npad;
+    float acc[AR_MAXROWS];
+#pragma unroll
+    for (int r = 0; r < AR_MAXROWS; ++r) acc[r] = 0.f;
+    for (int key = k0; key < k1; key += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(vr + key));
+      const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), dd = T16<T>::unpack2(u.w);
+      const float vv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, dd.x, dd.y};
+#pragma unroll
+      for (int r = 0; r < AR_MAXROWS; ++r) {
+        if (r < nrows) {
+          const float* pp = sp + r * npad + key;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[r] = fmaf(pp[e], vv[e], acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < AR_MAXROWS; ++r) so[(part * AR_MAXROWS + r) * 64 + d] = acc[r];
+  }
+  __syncthreads();
+  const int b = bh / heads, hd = bh - b * heads;
+  for (int i = tid; i < nrows * 64; i += 256) {
+    const int r = i >> 6, d = i & 63;
+    const float v = so[(0 * AR_MAXROWS + r) * 64 + d] + so[(1 * AR_MAXROWS + r) * 64 + d] +
+                    so[(2 * AR_MAXROWS + r) * 64 + d] + so[(3 * AR_MAXROWS + r) * 64 + d];
+    out[(static_cast<size_t>(b) * ntok + row_begin + r) * (heads * 64) + hd * 64 + d] = T16<T>::from_f(v / res[r]);
   }
 }
 
@@ -445,16 +507,25 @@ extern "C" int b2u_attention_rows(const void* q, const void* k, const void* vt, 
   if (!q || !k || !vt || !out) return set_error(-1, "b2u_attention_rows: null pointer");
   if (nrows <= 0) return 0;
   if (npad % 8 || npad < ntok || row_begin < 0 || row_begin + nrows > ntok) return set_error(-1, "b2u_attention_rows: bad range");
-  const int warps = nrows < 8 ? nrows : 8;
-  const size_t smem = static_cast<size_t>(warps) * npad * sizeof(float);
-  if (smem > 48 * 1024) return set_error(-1, "b2u_attention_rows: ntok too large for the few-row kernel");
+  if (nrows > AR_MAXROWS) return set_error(-1, "b2u_attention_rows: at most 8 rows");
+  const size_t smem = (static_cast<size_t>(AR_MAXROWS) * (64 + npad + 8 + 1) + 4 * AR_MAXROWS * 64) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(-1, "b2u_attention_rows: ntok too large for the few-row kernel");
+  static bool configured[2] = {false, false};
+  const int di = dtype == B2U_BF16 ? 1 : 0;
+  if (!configured[di]) {
+    cudaError_t e = dtype == B2U_BF16
+                        ? cudaFuncSetAttribute(attn_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                        : cudaFuncSetAttribute(attn_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(attn_rows): %s", cudaGetErrorString(e));
+    configured[di] = true;
+  }
   const float sl2 = scale * 1.4426950408889634f;
   if (dtype == B2U_BF16)
-    attn_rows_kernel<__nv_bfloat16><<<B * heads, warps * 32, smem, stream>>>(
+    attn_rows_kernel<__nv_bfloat16><<<B * heads, 256, smem, stream>>>(
         static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(vt),
         static_cast<__nv_bfloat16*>(out), heads, ntok, npad, row_begin, nrows, sl2);
   else
-    attn_rows_kernel<__half><<<B * heads, warps * 32, smem, stream>>>(
+    attn_rows_kernel<__half><<<B * heads, 256, smem, stream>>>(
         static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(vt),
         static_cast<__half*>(out), heads, ntok, npad, row_begin, nrows, sl2);
   return check_launch("attention_rows");
