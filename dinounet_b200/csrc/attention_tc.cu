@@ -384,7 +384,6 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(const T* __restrict__ q,
   float* sq = smf;                                   // [8][64]
   float* sp = sq + AR_MAXROWS * 64;                  // [8][npad]
   float* red = sp + AR_MAXROWS * npad;               // [8][8]  per-warp partials, then [8] results in red[0..7]
-  float* so = red + AR_MAXROWS * 8 + AR_MAXROWS;     // [4][8][64]
   float* res = red + AR_MAXROWS * 8;                 // [8] row max, later row sum
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.x;
@@ -393,35 +392,39 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(const T* __restrict__ q,
   for (int i = tid; i < nrows * 64; i += 256)
     sq[i] = T16<T>::to_f(q[(static_cast<size_t>(bh) * ntok + row_begin + (i >> 6)) * 64 + (i & 63)]);
   __syncthreads();
-  // ---- phase 1: scores
+  // ---- phase 1: scores.  lane = (key-in-group-of-4, 16-byte chunk): every warp load is 512 contiguous bytes of K;
+  // the 8 lanes of a key reduce their partial dot products with shuffles.
   float mx[AR_MAXROWS];
 #pragma unroll
   for (int r = 0; r < AR_MAXROWS; ++r) mx[r] = -INFINITY;
-  for (int key = tid; key < ntok; key += 256) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * 64);
-    float sc[AR_MAXROWS];
+  {
+    const int kq = lane >> 3, ch = lane & 7;
+    float qv[AR_MAXROWS][8];
 #pragma unroll
-    for (int r = 0; r < AR_MAXROWS; ++r) sc[r] = 0.f;
+    for (int r = 0; r < AR_MAXROWS; ++r)
 #pragma unroll
-    for (int j8 = 0; j8 < 8; ++j8) {
-      const uint4 u = __ldg(kr + j8);
+      for (int e = 0; e < 8; ++e) qv[r][e] = r < nrows ? sq[r * 64 + ch * 8 + e] : 0.f;
+    for (int k0 = warp * 4; k0 < ntok; k0 += 32) {
+      const int key = k0 + kq;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (key < ntok) u = __ldg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(key) * 64) + ch);
       const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), d = T16<T>::unpack2(u.w);
       const float kv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
       for (int r = 0; r < AR_MAXROWS; ++r) {
         if (r < nrows) {
-          const float* qq = sq + r * 64 + j8 * 8;
+          float sc = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) sc[r] = fmaf(qq[e], kv[e], sc[r]);
+          for (int e = 0; e < 8; ++e) sc = fmaf(qv[r][e], kv[e], sc);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+          if (ch == 0 && key < ntok) {
+            const float v = sc * scale_log2e;
+            sp[r * npad + key] = v;
+            mx[r] = fmaxf(mx[r], v);
+          }
         }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < AR_MAXROWS; ++r) {
-      if (r < nrows) {
-        const float v = sc[r] * scale_log2e;
-        sp[r * npad + key] = v;
-        mx[r] = fmaxf(mx[r], v);
       }
     }
   }
@@ -465,38 +468,39 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(const T* __restrict__ q,
     for (int w = 0; w < 8; ++w) t += red[tid * 8 + w];
     res[tid] = t;
   }
-  // ---- phase 3: O[r][d] = sum_key p[r][key] * V^T[d][key]
-  {
-    const int d = tid & 63, part = tid >> 6;
-    const int per = ((npad / 8 + 3) / 4) * 8;                 // keys per quarter, multiple of 8
-    const int k0 = part * per, k1 = min(npad, k0 + per);
+  __syncthreads();
+  // ---- phase 3: O[r][d] = sum_key p[r][key] * V^T[d][key].  One warp per d row at a time, lane = 8-key chunk: every
+  // warp load is 512 contiguous bytes of the V^T row; per-row partials are reduced with shuffles.
+  const int b = bh / heads, hd = bh - b * heads;
+  for (int d = warp; d < 64; d += 8) {
     const T* vr = vb + static_cast<size_t>(d) * npad;
     float acc[AR_MAXROWS];
 #pragma unroll
     for (int r = 0; r < AR_MAXROWS; ++r) acc[r] = 0.f;
-    for (int key = k0; key < k1; key += 8) {
+    for (int key = lane * 8; key < npad; key += 256) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(vr + key));
-      const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), dd = T16<T>::unpack2(u.w);
-      const float vv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, dd.x, dd.y};
+      const float2 a = T16<T>::unpack2(u.x), bb = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), dd = T16<T>::unpack2(u.w);
+      const float vv[8] = {a.x, a.y, bb.x, bb.y, c.x, c.y, dd.x, dd.y};
 #pragma unroll
       for (int r = 0; r < AR_MAXROWS; ++r) {
         if (r < nrows) {
-          const float* pp = sp + r * npad + key;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[r] = fmaf(pp[e], vv[e], acc[r]);
+          const float4 p0 = *reinterpret_cast<const float4*>(sp + r * npad + key);
+          const float4 p1 = *reinterpret_cast<const float4*>(sp + r * npad + key + 4);
+          acc[r] = fmaf(p0.x, vv[0], acc[r]); acc[r] = fmaf(p0.y, vv[1], acc[r]); acc[r] = fmaf(p0.z, vv[2], acc[r]);
+          acc[r] = fmaf(p0.w, vv[3], acc[r]); acc[r] = fmaf(p1.x, vv[4], acc[r]); acc[r] = fmaf(p1.y, vv[5], acc[r]);
+          acc[r] = fmaf(p1.z, vv[6], acc[r]); acc[r] = fmaf(p1.w, vv[7], acc[r]);
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < AR_MAXROWS; ++r) so[(part * AR_MAXROWS + r) * 64 + d] = acc[r];
-  }
-  __syncthreads();
-  const int b = bh / heads, hd = bh - b * heads;
-  for (int i = tid; i < nrows * 64; i += 256) {
-    const int r = i >> 6, d = i & 63;
-    const float v = so[(0 * AR_MAXROWS + r) * 64 + d] + so[(1 * AR_MAXROWS + r) * 64 + d] +
-                    so[(2 * AR_MAXROWS + r) * 64 + d] + so[(3 * AR_MAXROWS + r) * 64 + d];
-    out[(static_cast<size_t>(b) * ntok + row_begin + r) * (heads * 64) + hd * 64 + d] = T16<T>::from_f(v / res[r]);
+    for (int r = 0; r < AR_MAXROWS; ++r) {
+      if (r < nrows) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        if (lane == 0)
+          out[(static_cast<size_t>(b) * ntok + row_begin + r) * (heads * 64) + hd * 64 + d] = T16<T>::from_f(acc[r] / res[r]);
+      }
+    }
   }
 }
 
