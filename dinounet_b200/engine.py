@@ -294,11 +294,11 @@ class ForwardEngine:
             plan.keep.append(qp)
             plan.add(f"b{i}.qkv", lib.b2u_qkv_rope, C.byref(qp))
             if self.attn_impl == "tc":
-                # the P patch-token rows fill whole 128-row tiles; the 5 cls/storage rows go to the few-row kernel
-                plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad,
-                         cfg.N_PREFIX, 64 ** -0.5, vt)
-                plan.add(f"b{i}.attnp", lib.b2u_attention_rows, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 0,
-                         cfg.N_PREFIX, 64 ** -0.5, vt)
+                # one launch over all ntok query rows.  (Splitting off the 5 cls/storage rows so that the 1024 patch rows fill
+                # whole tile pairs was measured: tcgen05 part 370 -> 326 us/layer, but the few-row kernel costs more than
+                # the 45 us it saves, so q_begin stays 0; b2u_attention_rows remains available.)
+                plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 0,
+                         64 ** -0.5, vt)
             else:
                 plan.add(f"b{i}.attn", lib.b2u_attention, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, 64 ** -0.5, vt)
             self._gemm(plan, f"b{i}.proj", O, T, D, D, w[f"b{i}.proj"], D, X, D, vt, out_fp32=True, bias=w[f"b{i}.projb"],

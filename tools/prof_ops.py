@@ -40,7 +40,7 @@ elif op == "attn_tc":
     vt = torch.zeros(32, 16, 64, 1032, device=dev, dtype=bf)
     vt[..., :1029] = rnd(32, 16, 64, 1029)
     o = torch.empty(32, 1029, 1024, device=dev, dtype=bf)
-    run = lambda: L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(o), 32, 16, 1029, 1032, 5, 0.125, L.BF16, stream()), "attn_tc") or L.check(lib.b2u_attention_rows(P(q), P(k), P(vt), P(o), 32, 16, 1029, 1032, 0, 5, 0.125, L.BF16, stream()), "rows")
+    run = lambda: L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(o), 32, 16, 1029, 1032, 0, 0.125, L.BF16, stream()), "attn_tc")
 elif op == "conv":   # decoder 512^2 conv 64 -> 32
     x = rnd(32 * 512 * 512, 64, dt=torch.float16)
     w = rnd(32, 9 * 64, dt=torch.float16, sc=0.05)
