@@ -266,30 +266,26 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
             tmem_ld32(t, va);
             tmem_ld32(t + 32, vb);
             tmem_ld_wait();
-            const float2 cp2 = make_float2(corr_prev, corr_prev);
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {       // absorb: O = O * corr_{j-1} + P_{j-1} V_{j-1}   (FFMA2)
-              const float2 r0 = ffma2(make_float2(o[c], o[c + 1]), cp2, make_float2(__uint_as_float(va[c]), __uint_as_float(va[c + 1])));
-              const float2 r1 = ffma2(make_float2(o[32 + c], o[33 + c]), cp2, make_float2(__uint_as_float(vb[c]), __uint_as_float(vb[c + 1])));
-              o[c] = r0.x; o[c + 1] = r0.y; o[32 + c] = r1.x; o[33 + c] = r1.y;
+            for (int c = 0; c < 32; ++c) {          // absorb: O = O * corr_{j-1} + P_{j-1} V_{j-1}
+              o[c] = fmaf(o[c], corr_prev, __uint_as_float(va[c]));
+              o[32 + c] = fmaf(o[32 + c], corr_prev, __uint_as_float(vb[c]));
             }
             tc_fence_before();
             mbar_arrive(&x_free[2 * g + ((j - 1) & 1)]);   // buffer (j-1)&1 may now receive S(j+1)
           }
           tmem_ld32(tS, va);
-          const float2 sc2 = make_float2(args.scale_log2e, args.scale_log2e), nm2 = make_float2(-m_new, -m_new);
-          float2 rs2 = make_float2(0.f, 0.f);
           auto emit = [&](const uint32_t (&v)[32], int pc) {
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-              const float2 t = ffma2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), sc2, nm2);   // FFMA2
-              float a = ex2(t.x), b = ex2(t.y);
+              float a = ex2(fmaf(__uint_as_float(v[c]), args.scale_log2e, -m_new));
+              float b = ex2(fmaf(__uint_as_float(v[c + 1]), args.scale_log2e, -m_new));
               if (tail) {
                 if (kbase + pc * 32 + c >= args.ntok) a = 0.f;
                 if (kbase + pc * 32 + c + 1 >= args.ntok) b = 0.f;
               }
-              rs2 = fadd2(rs2, make_float2(a, b));   // fp32 row sums of the un-rounded probabilities (as flash-attention)
+              rs += a + b;                          // fp32 row sum of the un-rounded probabilities (as flash-attention)
               pk[c >> 1] = TT::pack2(a, b);
             }
             // columns pc*32 .. +31 -> K-block pc>>1, 16-byte chunks (pc&1)*4 .. +3 of this row
@@ -311,7 +307,6 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
           emit(va, 2);
           tmem_ld_wait();
           emit(vb, 3);
-          rs = rs2.x + rs2.y;
         }
         tc_fence_before();                         // all reads of S_g(j) done: PV(j) may overwrite X[j&1][0:64)
         fence_proxy_async();                       // make the generic-proxy P writes visible to the MMA (async proxy)
