@@ -160,7 +160,8 @@ extern "C" int b2u_write_prefix(float* X, const float* prefix, int32_t B, int32_
 }
 
 // ------------------------------------------------------------------------------------------------ SPM stem conv0
-// Conv2d(3,64,k3,s2,p1) + folded BN + ReLU: thread = (output pixel, 8 channels); weights staged in smem as [27][64].
+// Conv2d(3,64,k3,s2,p1) + folded BN + ReLU.  thread = (4 consecutive output pixels of a row, 8 channels): the 9 input
+// columns each (ci, ky) needs are loaded once and every weight vector fetched from smem ([27][64]) is reused 4 times.
 template <typename T>
 __global__ void __launch_bounds__(256) stem_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
@@ -173,47 +174,64 @@ __global__ void __launch_bounds__(256) stem_conv0_kernel(const float* __restrict
   }
   if (threadIdx.x < 64) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
   __syncthreads();
-  const int So = S / 2;
+  const int So = S / 2, Q = So / 4;   // 4-pixel groups per output row
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  const long long total = static_cast<long long>(B) * So * So * 8;
+  const long long total = static_cast<long long>(B) * So * Q * 8;
   if (i >= total) return;
   const int cg = static_cast<int>(i & 7);
-  const long long pix = i >> 3;
-  const int b = static_cast<int>(pix / (So * So));
-  const int pr = static_cast<int>(pix - static_cast<long long>(b) * So * So);
-  const int oy = pr / So, ox = pr - oy * So;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long grp = i >> 3;
+  const int qx = static_cast<int>(grp % Q), oy = static_cast<int>((grp / Q) % So), b = static_cast<int>(grp / (static_cast<long long>(Q) * So));
+  const int ox0 = qx * 4;
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy + ky - 1;
       if (iy < 0 || iy >= S) continue;
+      const float* row = x + ((static_cast<long long>(b) * 3 + ci) * S + iy) * S;
+      float in[9];                                   // input columns 2*ox0-1 .. 2*ox0+7
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const int ix = 2 * ox0 - 1 + c;
+        in[c] = (ix >= 0 && ix < S) ? __ldg(row + ix) : 0.f;
+      }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox + kx - 1;
-        if (ix < 0 || ix >= S) continue;
-        const float xv = __ldg(x + ((static_cast<long long>(b) * 3 + ci) * S + iy) * S + ix);
-        const float* wp = sw + (ci * 9 + ky * 3 + kx) * 64 + cg * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + (ci * 9 + ky * 3 + kx) * 64 + cg * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + (ci * 9 + ky * 3 + kx) * 64 + cg * 8 + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wp[j], acc[j]);
+        for (int p = 0; p < 4; ++p) {
+          const float xv = in[2 * p + kx];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xv, wv[j], acc[p][j]);
+        }
       }
     }
-  float f[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float r16 = T16<T>::to_f(T16<T>::from_f(acc[j]));  // conv output is 16-bit under autocast
-    f[j] = fmaxf(r16 * ssc[cg * 8 + j] + ssh[cg * 8 + j], 0.f);
+  for (int p = 0; p < 4; ++p) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float r16 = T16<T>::to_f(T16<T>::from_f(acc[p][j]));  // conv output is 16-bit under autocast
+      f[j] = fmaxf(r16 * ssc[cg * 8 + j] + ssh[cg * 8 + j], 0.f);
+    }
+    Vec8<T> v;
+    v.from_float(f);
+    v.store(out + ((static_cast<long long>(b) * So + oy) * So + ox0 + p) * 64 + cg * 8);
   }
-  Vec8<T> v;
-  v.from_float(f);
-  v.store(out + pix * 64 + cg * 8);
 }
 
 extern "C" int b2u_stem_conv0(const float* x, const float* w, const float* scale, const float* shift, void* out,
                               int32_t B, int32_t S, int32_t dtype, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const long long total = static_cast<long long>(B) * (S / 2) * (S / 2) * 8;
+  if (S % 8) return set_error(-1, "b2u_stem_conv0: S %% 8 != 0");
+  const long long total = static_cast<long long>(B) * (S / 2) * (S / 8) * 8;
   B2U_DISPATCH_T(dtype, (stem_conv0_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(x, w, scale, shift, static_cast<T*>(out), B, S)));
   return check_launch("stem_conv0");
 }
@@ -260,18 +278,22 @@ extern "C" int b2u_maxpool3x3s2(const void* in, void* out, int32_t B, int32_t H,
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
-// w9 is [9][C] fp32 (tap-major) so a thread reads its 8 channels of each tap as two float4.
+// w9 is [9][C] fp32 (tap-major).  thread = (4 consecutive pixels of a plane row, 8 channels): the 9 x 8 weights live in
+// registers and the 3 x 6 input vectors are loaded once for the 4 outputs (3x fewer loads than one pixel per thread).
 template <typename T>
-__global__ void dwconv_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ w9,
-                              const float* __restrict__ bias, int B, int H, int W, int C8, int planes, int act) {
+__global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                     const float* __restrict__ w9, const float* __restrict__ bias, int B,
+                                                     int H, int W, int C8, int planes, int act) {
+  // 4-pixel groups per image: planes==3 -> (2H x 2W) + (H x W) + (H/2 x W/2) planes, every plane width is a multiple of 4
   const long long rows_per_img = planes == 3 ? (static_cast<long long>(H) * W * 21) / 4 : static_cast<long long>(H) * W;
+  const long long groups_per_img = rows_per_img / 4;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * rows_per_img * C8;
+  const long long total = static_cast<long long>(B) * groups_per_img * C8;
   if (i >= total) return;
   const int c8 = static_cast<int>(i % C8);
-  const long long row = i / C8;
-  const int b = static_cast<int>(row / rows_per_img);
-  long long t = row - static_cast<long long>(b) * rows_per_img;
+  const long long grp = i / C8;
+  const int b = static_cast<int>(grp / groups_per_img);
+  long long t = (grp - static_cast<long long>(b) * groups_per_img) * 4;   // first token of the group within the image
   int ph = H, pw = W;
   long long poff = 0;
   if (planes == 3) {
@@ -280,41 +302,55 @@ __global__ void dwconv_kernel(const T* __restrict__ in, T* __restrict__ out, con
     else if (t < n0 + n1) { poff = n0; t -= n0; }
     else { poff = n0 + n1; t -= n0 + n1; ph = H / 2; pw = W / 2; }
   }
-  const int y = static_cast<int>(t / pw), x = static_cast<int>(t - static_cast<long long>(y) * pw);
-  const T* base = in + (static_cast<long long>(b) * rows_per_img + poff) * C8 * 8 + c8 * 8;
+  const int y = static_cast<int>(t / pw), x0 = static_cast<int>(t - static_cast<long long>(y) * pw);
   const int C = C8 * 8;
-  float acc[8];
+  const T* base = in + (static_cast<long long>(b) * rows_per_img + poff) * C + c8 * 8;
+  float wr[9][8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9 + k * C + c8 * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w9 + k * C + c8 * 8) + 1);
+    wr[k][0] = w0.x; wr[k][1] = w0.y; wr[k][2] = w0.z; wr[k][3] = w0.w; wr[k][4] = w1.x; wr[k][5] = w1.y; wr[k][6] = w1.z; wr[k][7] = w1.w;
+  }
+  float acc[4][8];
   {
-    const float4 b0 = reinterpret_cast<const float4*>(bias + c8 * 8)[0], b1 = reinterpret_cast<const float4*>(bias + c8 * 8)[1];
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8) + 1);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      acc[p][0] = b0.x; acc[p][1] = b0.y; acc[p][2] = b0.z; acc[p][3] = b0.w; acc[p][4] = b1.x; acc[p][5] = b1.y; acc[p][6] = b1.z; acc[p][7] = b1.w;
+    }
   }
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = y + ky - 1;
     if (iy < 0 || iy >= ph) continue;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = x + kx - 1;
+    for (int c = 0; c < 6; ++c) {                      // input columns x0-1 .. x0+4
+      const int ix = x0 - 1 + c;
       if (ix < 0 || ix >= pw) continue;
       Vec8<T> v;
       v.load(base + (static_cast<long long>(iy) * pw + ix) * C);
       float f[8];
       v.to_float(f);
-      const float4 w0 = reinterpret_cast<const float4*>(w9 + (ky * 3 + kx) * C + c8 * 8)[0];
-      const float4 w1 = reinterpret_cast<const float4*>(w9 + (ky * 3 + kx) * C + c8 * 8)[1];
-      acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
-      acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-      acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
-      acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int kx = c - p;                          // output pixel x0+p sees this column as tap kx
+        if (kx < 0 || kx > 2) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(f[j], wr[ky * 3 + kx][j], acc[p][j]);
+      }
     }
   }
-  if (act == B2U_ACT_GELU) {
+  T* obase = out + ((static_cast<long long>(b) * rows_per_img + poff) + static_cast<long long>(y) * pw + x0) * C + c8 * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = gelu_erf(T16<T>::to_f(T16<T>::from_f(acc[j])));
+  for (int p = 0; p < 4; ++p) {
+    if (act == B2U_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = gelu_erf(T16<T>::to_f(T16<T>::from_f(acc[p][j])));
+    }
+    Vec8<T> o;
+    o.from_float(acc[p]);
+    o.store(obase + static_cast<long long>(p) * C);
   }
-  Vec8<T> o;
-  o.from_float(acc);
-  o.store(out + row * C + c8 * 8);
 }
 
 extern "C" int b2u_dwconv3x3(const void* in, void* out, const float* w, const float* bias, int32_t B, int32_t H,
@@ -322,8 +358,9 @@ extern "C" int b2u_dwconv3x3(const void* in, void* out, const float* w, const fl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (C % 8) return set_error(-1, "b2u_dwconv3x3: C %% 8 != 0");
   if (planes != 1 && planes != 3) return set_error(-1, "b2u_dwconv3x3: planes must be 1 or 3");
+  if ((planes == 3 && (W % 8 || H % 2)) || (planes == 1 && W % 4)) return set_error(-1, "b2u_dwconv3x3: plane widths must be multiples of 4");
   const long long rows = planes == 3 ? (static_cast<long long>(H) * W * 21) / 4 : static_cast<long long>(H) * W;
-  const long long total = static_cast<long long>(B) * rows * (C / 8);
+  const long long total = static_cast<long long>(B) * (rows / 4) * (C / 8);
   B2U_DISPATCH_T(dtype, (dwconv_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(in), static_cast<T*>(out), w, bias, B, H, W, C / 8, planes, act)));
   return check_launch("dwconv3x3");
 }

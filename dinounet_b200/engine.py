@@ -236,8 +236,8 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ plan
     def build_plan(self, B: int, S: int) -> Tuple[Plan, dict]:
-        if S % 32 or S < 64:
-            raise ValueError("input size must be a multiple of 32 (>= 64)")
+        if S % 32 or S < 128:
+            raise ValueError("input size must be a multiple of 32 (>= 128)")
         v, w, lib = self.v, self.w, self.lib
         vt, rt, tv, tr = self.vt, self.rt, self.tv, self.tr
         D, Hh = v.embed_dim, v.num_heads
