@@ -354,7 +354,9 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
   a.epi = p->epi;
   a.conv = p->conv;
   const bool v2 = get_option(0) != 1;
-  const int bn = pick_bn(p->N, v2);
+  if (e.act1 == B2U_ACT_SWIGLU && (!v2 || p->N % 64 || p->conv != B2U_CONV_NONE))
+    return set_error(-1, "b2u_gemm: SwiGLU epilogue needs the v2 kernel, N %% 64 == 0 and a plain GEMM");
+  const int bn = (e.act1 == B2U_ACT_SWIGLU && p->N <= 128) ? 128 : pick_bn(p->N, v2);
   a.n_tiles = (p->N + bn - 1) / bn;
   long long m_tiles;
   int rc;

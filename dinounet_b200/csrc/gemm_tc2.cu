@@ -32,7 +32,7 @@ template <int BN, int EPI = 0> struct Cfg2 {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 8 * 4096;        // 8 epilogue warps x (32 rows x 128 B)
   static constexpr int kBiasBytes = BN * 4;
-  static constexpr int kRope = EPI == 2 ? kRopeBytes : 0;
+  static constexpr int kRope = EPI == 2 ? kRopeBytes : 0;   // (EPI 3 reuses s_bias only)
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + kRope + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kHaloStages = BN <= 32 ? 3 : 2;
   static constexpr int kSmemHalo = kHaloStages * kHaloStageBytes + 9 * kBBytes + kStagingBytes + kBiasBytes + 1024 + 256;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void act_vec(float (&f)[NV]) {
   }
 }
 
-// EPI: 0 = generic 16-bit out, 1 = generic fp32 out, 2 = QKV(+RoPE, head split).  ACT1 / ACT2: compile-time activations
+// EPI: 0 = generic 16-bit out, 1 = generic fp32 out, 2 = QKV(+RoPE, head split), 3 = SwiGLU (silu(x1)*x2).  ACT1 / ACT2: compile-time activations
 // after the bias / after the affine (B2U_ACT_*), so the fully unrolled epilogue stays small enough for the I-cache.
 template <int BN, int EPI, int ACT1, int ACT2, typename T>
 __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
@@ -383,6 +383,59 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             if (dst_ok[i]) *reinterpret_cast<uint4*>(base + dst_off[i]) = val;
           }
         }
+      } else if constexpr (EPI == 3) {
+        // ---- SwiGLU (ffn_layers.py:73-77): the weight rows are packed in 32-row blocks [w1 block j | w2 block j], so the
+        // accumulator columns come in 64-column groups (x1[32] | x2[32]); out[:, 32j..32j+31] = silu(x1 + b1) * (x2 + b2)
+        // with the reference's 16-bit roundings (each Linear output, silu, the product).  Output is 16-bit [M, N/2].
+        epi_bar_sync();
+        for (int i = etid; i < BN; i += 256) s_bias[i] = (e.bias && n0 + i < args.N) ? __ldg(e.bias + n0 + i) : 0.f;
+        epi_bar_sync();
+        long long dst_row[4];
+        bool dst_ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {             // phase-2 rows: rr = i*8 + lane/4 (4 lanes x 16 B = one 64 B row segment)
+          long long m2;
+          dst_ok[i] = row_of(q4 * 32 + i * 8 + (lane >> 2), m2);
+          dst_row[i] = dst_ok[i] ? m2 : 0;
+        }
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll 1
+        for (int g = half * (BN / 128); g < (half + 1) * (BN / 128); ++g) {
+          uint32_t v0[32], v1r[32];
+          tmem_ld32(taddr + g * 64, v0);
+          tmem_ld32(taddr + g * 64 + 32, v1r);
+          tmem_ld_wait();
+          const int n = n0 + g * 64;
+          if (n >= args.N) continue;   // warp-uniform
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float h[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float a = TT::to_f(TT::from_f(__uint_as_float(v0[j + q]) + s_bias[g * 64 + j + q]));
+              const float b = TT::to_f(TT::from_f(__uint_as_float(v1r[j + q]) + s_bias[g * 64 + 32 + j + q]));
+              const float sg = TT::to_f(TT::from_f(a * rcp_approx(1.0f + __expf(-a))));   // silu(a), 16-bit like F.silu
+              h[q] = sg * b;
+            }
+            packed[j >> 1] = TT::pack2(h[0], h[1]);
+          }
+          // stage: row = lane, 64 B of output (4 x 16 B chunks) at chunk position c ^ ((row >> 1) & 3) within a 64 B slot
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(patch_u32 + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          __syncwarp();
+          const int ocol = (n >> 1) + (lane & 3) * 8 + e.col_off;      // hidden column = accumulator column / 2
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2);
+            const uint4 val = lds128(patch_u32 + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            if (dst_ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(e.out) + dst_row[i] * e.ldc + ocol) = val;
+          }
+        }
       } else {
         // ---- phase-2 row assignment: fp32 output -> 8 lanes per row (4 cols each), 4 rows per pass, 8 passes;
         //                              16-bit output -> 4 lanes per row (8 cols each), 8 rows per pass, 4 passes.
@@ -581,6 +634,12 @@ static int dispatch_epi(bool qkv, const GemmMaps& maps, const GemmArgs& args, cu
     else return set_error(-3, "gemm_tc2: QKV epilogue needs BLOCK_N >= 128");
   }
   const int a1 = args.epi.act1, a2 = args.epi.act2;
+  if (a1 == B2U_ACT_SWIGLU) {
+    if constexpr (BN >= 128) {
+      if (!args.epi.out_fp32 && a2 == 0) return launch_variant2<BN, 3, 0, 0, T>(maps, args, stream);
+    }
+    return set_error(-3, "gemm_tc2: SwiGLU epilogue needs BLOCK_N >= 128, a 16-bit output and no second activation");
+  }
   if (args.epi.out_fp32) {
     if (a1 == 0 && a2 == 0) return launch_variant2<BN, 1, 0, 0, T>(maps, args, stream);
   } else {

@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 F16, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_LRELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_LRELU, ACT_SWIGLU = 0, 1, 2, 3, 4
 CONV_NONE, CONV3X3_S1, CONV3X3_S2 = 0, 1, 2
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdinounet_b200.so")

@@ -23,7 +23,11 @@ extern "C" {
 typedef void* b2u_stream_t; /* cudaStream_t */
 
 enum { B2U_F16 = 0, B2U_BF16 = 1 };
-enum { B2U_ACT_NONE = 0, B2U_ACT_GELU = 1, B2U_ACT_RELU = 2, B2U_ACT_LRELU = 3 };
+enum { B2U_ACT_NONE = 0, B2U_ACT_GELU = 1, B2U_ACT_RELU = 2, B2U_ACT_LRELU = 3,
+       /* act1 = B2U_ACT_SWIGLU (SwiGLUFFN.forward, ffn_layers.py:73-77): Wp rows (and bias) are packed in 32-row blocks
+        * [w1 rows 32j..32j+31 | w2 rows 32j..32j+31], N = 2*hidden; out[:, j] = silu(x.w1_j + b1_j) * (x.w2_j + b2_j),
+        * 16-bit [M, N/2] (ldc/col_off in output columns). */
+       B2U_ACT_SWIGLU = 4 };
 enum { B2U_CONV_NONE = 0, B2U_CONV3X3_S1 = 1, B2U_CONV3X3_S2 = 2 };
 
 /* Epilogue applied to each fp32 accumulator element acc[m, n], in this order:

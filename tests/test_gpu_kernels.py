@@ -64,6 +64,27 @@ def test_gemm_epilogue_residual_scale_gelu_fp32out(gemm_impl):
     assert rel_err(out, ref) < 2 ** -6
 
 
+@pytest.mark.parametrize("dtype", [L.BF16, L.F16])
+@pytest.mark.parametrize("M,D,Hd", [(1029, 256, 512), (300, 128, 64), (2058, 512, 1024 + 64)])
+def test_gemm_swiglu_epilogue(dtype, M, D, Hd):
+    """SwiGLUFFN first half fused (ffn_layers.py:73-77): hidden = silu(x w1^T + b1) * (x w2^T + b2), with autocast roundings."""
+    td = TD[dtype]
+    x = _rand(M, D, dt=td)
+    w1, w2 = _rand(Hd, D, dt=td, scale=D ** -0.5, seed=1), _rand(Hd, D, dt=td, scale=D ** -0.5, seed=2)
+    b1, b2 = _rand(Hd, seed=3, scale=0.2), _rand(Hd, seed=4, scale=0.2)
+    # pack 32-row blocks [w1 block | w2 block]
+    Wp = torch.stack([w1.view(Hd // 32, 32, D), w2.view(Hd // 32, 32, D)], 1).reshape(2 * Hd, D).contiguous()
+    bp = torch.stack([b1.view(Hd // 32, 32), b2.view(Hd // 32, 32)], 1).reshape(2 * Hd).contiguous()
+    out = torch.full((M, Hd), float("nan"), device=DEV, dtype=td)
+    gemm(x, Wp, out, dtype, bias=bp, act1=L.ACT_SWIGLU, ldc=Hd)
+    torch.cuda.synchronize()
+    x1 = (x.float() @ w1.float().t() + b1).to(td)
+    x2 = (x.float() @ w2.float().t() + b2).to(td)
+    ref = (F.silu(x1.float()).to(td).float() * x2.float())
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -9), rel_err(out, ref)
+
+
 def test_gemm_row_remap_and_coloffset(gemm_impl):
     B, Pn, Nn, D, K = 3, 64, 69, 128, 64
     dtype, td = L.F16, torch.float16
