@@ -31,6 +31,22 @@ if op in ("fc1", "fc2", "proj"):
         A, W, bias = rnd(T, D), rnd(D, D, sc=D ** -0.5), rnd(D, dt=torch.float32)
         X, ls = rnd(T, D, dt=torch.float32), rnd(D, dt=torch.float32)
         run = lambda: gemm(A, W, X, L.BF16, out_fp32=True, bias=bias, scale=ls, residual=X, ldres=D)
+elif op == "qkv":
+    import ctypes as C
+    from oracle import dinounet_oracle as O
+    A = rnd(T, D)
+    W = rnd(3 * D, D, sc=D ** -0.5)
+    bias = rnd(3 * D, dt=torch.float32)
+    periods = 100.0 ** (2 * torch.arange(16, dtype=torch.float32) / 32)
+    sin, cos = [t.to(dev).contiguous() for t in O.rope_sincos(periods, 32, 32)]
+    q, k = (torch.empty(32, 16, 1029, 64, device=dev, dtype=bf) for _ in range(2))
+    vt = torch.zeros(32, 16, 64, 1032, device=dev, dtype=bf)
+    p = L.QkvParams()
+    p.B, p.ntok, p.D, p.heads, p.prefix = 32, 1029, D, 16, 5
+    p.A, p.lda, p.Wp, p.ldw, p.bias = P(A), D, P(W), D, P(bias)
+    p.rope_sin, p.rope_cos, p.q, p.k, p.v, p.dtype = P(sin), P(cos), P(q), P(k), P(vt), L.BF16
+    p.v_transposed, p.npad, p.rope_w = 1, 1032, 32
+    run = lambda: L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv")
 elif op == "attn":
     q, k, v = (rnd(32, 16, 1029, 64) for _ in range(3))
     o = torch.empty(32, 1029, 1024, device=dev, dtype=bf)
