@@ -253,9 +253,18 @@ def main():
             flops = v.depth * 2 * T * v.embed_dim * (3 * v.embed_dim + v.embed_dim + 2 * v.ffn_hidden)
             t_gemm = sum(fam.get(k, 0) for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2"))
             pk = peaks()
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if os.path.exists(tpath) and (a.model, B, S, a.vit_dtype) == ("dinounet_l", 32, 512, "bf16"):
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of
+                # the four ViT GEMM shapes at exactly this workload (tools/prof_ops.py), averaged over the family
+                traffic = json.load(open(tpath))["vit_gemm_family_avg_per_launch"]
+                traffic_src = "profiles/r01_traffic.json (ncu --set full, fc1/fc2/proj/qkv shapes)"
             ach = flops / (t_gemm * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel<256,EPI,ACT,%s> = persistent tcgen05 GEMM (ViT qkv/proj/fc1/fc2, %d launches/step)" % (a.vit_dtype, 4 * v.depth),
-                    "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                    "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": (T * v.embed_dim * 2 * 2 + T * v.ffn_hidden * 2 * 2 + T * 3 * v.embed_dim * 2 + 2 * T * v.embed_dim * 8
+                                                     + 2 * (4 * v.embed_dim * v.embed_dim + 2 * v.embed_dim * v.ffn_hidden)) / 4,
                     "peak_source": pk["src"] + " (bf16 sustained)", "share_of_step": t_gemm / sum(fam.values())}
             if a.ops_out:
                 os.makedirs(os.path.dirname(a.ops_out) or ".", exist_ok=True)
