@@ -30,12 +30,19 @@ struct AttnArgs {
   void* out;
 };
 
-constexpr int AT_STAGES = 4;
-constexpr int AT_QBYTES = 128 * 128;        // 128 rows x 64 x 2B
-constexpr int AT_PBYTES = 2 * 128 * 128;    // two K-blocks of [128 x 64]
-constexpr int AT_KBYTES = 128 * 128;
-constexpr int AT_VBYTES = 2 * 64 * 128;     // two K-blocks of [64 x 64]
-constexpr int AT_SMEM = 2 * AT_QBYTES + 2 * AT_PBYTES + AT_STAGES * (AT_KBYTES + AT_VBYTES) + 1024 + 256;
+// Per-head-dim configuration.  HD = 64 (ViT-S/B/L): two query-tile groups per CTA, 4-stage K/V ring.
+// HD = 128 (ViT-7B): one group (the fp32 O accumulator needs 128 registers per thread), 2-stage ring.
+template <int HD> struct AtCfg {
+  static constexpr int kGroups = HD == 64 ? 2 : 1;
+  static constexpr int kStages = HD == 64 ? 4 : 2;
+  static constexpr int kKB = HD / 64;                       // 64-wide K blocks of the head dim
+  static constexpr int kQBytes = 128 * HD * 2;              // kKB blocks of [128 rows x 64]
+  static constexpr int kPBytes = 2 * 128 * 128;             // two key blocks of [128 rows x 64 keys]
+  static constexpr int kKBytes = 128 * HD * 2;              // kKB blocks of [128 keys x 64]
+  static constexpr int kVBytes = 2 * HD * 128;              // two key blocks of [HD rows x 64 keys]
+  static constexpr int kThreads = 64 + kGroups * 128;
+  static constexpr int kSmem = kGroups * (kQBytes + kPBytes) + kStages * (kKBytes + kVBytes) + 1024 + 256;
+};
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -58,21 +65,23 @@ __device__ __forceinline__ float ex2(float x) {
   return r;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
+template <typename T, int HD>
+__global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
   using TT = T16<T>;
+  using CF = AtCfg<HD>;
+  constexpr int NG = CF::kGroups, NST = CF::kStages, KB = CF::kKB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                               // [2][16 KB]
-  uint8_t* sP = sQ + 2 * AT_QBYTES;                 // [2][32 KB]
-  uint8_t* sK = sP + 2 * AT_PBYTES;                 // [stages][16 KB]
-  uint8_t* sV = sK + AT_STAGES * AT_KBYTES;         // [stages][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_STAGES * AT_VBYTES);
+  uint8_t* sQ = smem;                               // [NG][kQBytes]
+  uint8_t* sP = sQ + NG * CF::kQBytes;              // [NG][32 KB]
+  uint8_t* sK = sP + NG * CF::kPBytes;              // [stages][kKBytes]
+  uint8_t* sV = sK + NST * CF::kKBytes;             // [stages][kVBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NST * CF::kVBytes);
   uint64_t* q_full = bars;                 // [2]
   uint64_t* q_free = q_full + 2;           // [2]
-  uint64_t* kv_full = q_free + 2;          // [stages]
-  uint64_t* kv_empty = kv_full + AT_STAGES;
-  uint64_t* s_full = kv_empty + AT_STAGES; // [2 groups][2 buffers]
+  uint64_t* kv_full = q_free + 2;          // [4]
+  uint64_t* kv_empty = kv_full + 4;
+  uint64_t* s_full = kv_empty + 4;         // [2 groups][2 buffers]
   uint64_t* x_free = s_full + 4;           // [2][2]
   uint64_t* p_full = x_free + 4;           // [2]
   uint64_t* o_full = p_full + 2;           // [2]
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       mbar_init(&x_free[2 * g], 128); mbar_init(&x_free[2 * g + 1], 128);
       mbar_init(&p_full[g], 128); mbar_init(&o_full[g], 1);
     }
-    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: X_g[b] at g*256 + b*128 (S_g(j) for j&1 == b, then O_g(j) in its first 64 columns)
+  // TMEM columns: X_g[b] at g*256 + b*128 (S_g(j) for j&1 == b, then O_g(j) in its first HD columns)
   const int J = args.nchunks;
 
   if (warp == 0) {
@@ -110,21 +119,23 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
         const int bh = static_cast<int>(item / args.npairs);
         const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
-        for (int g = 0; g < 2; ++g) {
-          const int q0 = args.q_begin + (pair * 2 + g) * 128;
+        for (int g = 0; g < NG; ++g) {
+          const int q0 = args.q_begin + (pair * NG + g) * 128;
           if (q0 >= args.ntok) continue;
           mbar_wait(&q_free[g], (qfree_cnt[g] & 1) ^ 1);
           ++qfree_cnt[g];
-          mbar_expect_tx(&q_full[g], AT_QBYTES);
-          tma_load_3d(sQ + g * AT_QBYTES, &maps.q, &q_full[g], 0, q0, bh);
+          mbar_expect_tx(&q_full[g], CF::kQBytes);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_3d(sQ + g * CF::kQBytes + kb * (128 * 128), &maps.q, &q_full[g], kb * 64, q0, bh);
         }
         for (int j = 0; j < J; ++j) {
           mbar_wait(&kv_empty[stage], kv_phase ^ 1);
-          mbar_expect_tx(&kv_full[stage], AT_KBYTES + AT_VBYTES);
-          tma_load_3d(sK + stage * AT_KBYTES, &maps.k, &kv_full[stage], 0, j * 128, bh);
-          tma_load_3d(sV + stage * AT_VBYTES, &maps.vt, &kv_full[stage], j * 128, 0, bh);
-          tma_load_3d(sV + stage * AT_VBYTES + 64 * 128, &maps.vt, &kv_full[stage], j * 128 + 64, 0, bh);
-          if (++stage == AT_STAGES) { stage = 0; kv_phase ^= 1; }
+          mbar_expect_tx(&kv_full[stage], CF::kKBytes + CF::kVBytes);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_3d(sK + stage * CF::kKBytes + kb * (128 * 128), &maps.k, &kv_full[stage], kb * 64, j * 128, bh);
+          tma_load_3d(sV + stage * CF::kVBytes, &maps.vt, &kv_full[stage], j * 128, 0, bh);
+          tma_load_3d(sV + stage * CF::kVBytes + HD * 128, &maps.vt, &kv_full[stage], j * 128 + 64, 0, bh);
+          if (++stage == NST) { stage = 0; kv_phase ^= 1; }
         }
       }
     }
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_f16(TT::kFmt, 128, 128);
-      constexpr uint32_t idesc_o = make_idesc_f16(TT::kFmt, 128, 64);
+      constexpr uint32_t idesc_o = make_idesc_f16(TT::kFmt, 128, HD);
       int stage = 0;
       uint32_t kv_phase = 0;
       uint32_t qfull_cnt[2] = {0, 0}, pfull_cnt[2] = {0, 0};
@@ -142,23 +153,27 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         mbar_wait(&x_free[2 * g + bfr], (xfree_cnt[g][bfr] & 1) ^ 1);   // softmax g has absorbed the previous occupant
         ++xfree_cnt[g][bfr];
         tc_fence_after();
-        const uint64_t da = make_desc_k128(smem_u32(sQ + g * AT_QBYTES));
-        const uint64_t db = make_desc_k128(smem_u32(sK + st * AT_KBYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tmem_base + g * 256 + bfr * 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_s, k != 0 ? 1u : 0u);
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t da = make_desc_k128(smem_u32(sQ + g * CF::kQBytes + kb * (128 * 128)));
+          const uint64_t db = make_desc_k128(smem_u32(sK + st * CF::kKBytes + kb * (128 * 128)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tmem_base + g * 256 + bfr * 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_s,
+                       (kb | k) != 0 ? 1u : 0u);
+        }
         tc_commit(&s_full[2 * g + bfr]);
       };
       auto next_stage = [&](int st, uint32_t ph, int& nst, uint32_t& nph) {
         nst = st + 1; nph = ph;
-        if (nst == AT_STAGES) { nst = 0; nph ^= 1; }
+        if (nst == NST) { nst = 0; nph ^= 1; }
       };
       for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
         const int bh = static_cast<int>(item / args.npairs);
         const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
-        const int nq = (args.q_begin + (pair * 2 + 1) * 128 < args.ntok) ? 2 : 1;
+        const int nq = (NG == 2 && args.q_begin + (pair * 2 + 1) * 128 < args.ntok) ? 2 : 1;
         for (int g = 0; g < nq; ++g) { mbar_wait(&q_full[g], qfull_cnt[g] & 1); ++qfull_cnt[g]; }
-        // `stage`/`kv_phase` track chunk j (whose V the PV MMA uses); S runs one chunk ahead.
+        // `stage`/`kv_phase` track chunk j (whose V the PV MMA uses); S runs one chunk ahead when the ring is deep enough.
         int st1; uint32_t ph1;
         next_stage(stage, kv_phase, st1, ph1);
         mbar_wait(&kv_full[stage], kv_phase);
@@ -179,8 +194,8 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
             const uint32_t tO = tmem_base + g * 256 + (j & 1) * 128;
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
-              const uint64_t da = make_desc_k128(smem_u32(sP + g * AT_PBYTES + kb * 128 * 128));
-              const uint64_t db = make_desc_k128(smem_u32(sV + stage * AT_VBYTES + kb * 64 * 128));
+              const uint64_t da = make_desc_k128(smem_u32(sP + g * CF::kPBytes + kb * 128 * 128));
+              const uint64_t db = make_desc_k128(smem_u32(sV + stage * CF::kVBytes + kb * HD * 128));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 tc_mma_f16(tO, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_o, (kb | k) != 0 ? 1u : 0u);
@@ -189,7 +204,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
           }
           tc_commit(&kv_empty[stage]);   // K_j / V_j are free once every MMA issued so far has retired
           if (j + 2 < J) {               // S(j+2) reuses buffer j&1 once O(j) has been absorbed by the softmax
-            mbar_wait(&kv_full[st2], ph2);
+            mbar_wait(&kv_full[st2], ph2);   // (2-stage ring: st2 == stage, refilled after the commit above)
             tc_fence_after();
             for (int g = 0; g < nq; ++g) issue_s(g, j + 2, st2);
           }
@@ -205,18 +220,28 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     const int q4 = warp & 3;                // TMEM lane quarter
     const int row = q4 * 32 + lane;
     const uint32_t tX = tmem_base + g * 256 + (static_cast<uint32_t>(q4 * 32) << 16);
-    const uint32_t sP_row = smem_u32(sP + g * AT_PBYTES) + row * 128;
-    const uint32_t sP_base = smem_u32(sP + g * AT_PBYTES);
+    const uint32_t sP_row = smem_u32(sP + g * CF::kPBytes) + row * 128;
+    const uint32_t sP_base = smem_u32(sP + g * CF::kPBytes);
     uint32_t sfull_cnt[2] = {0, 0}, ofull_cnt = 0;
     for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
       const int bh = static_cast<int>(item / args.npairs);
       const int pair = static_cast<int>(item - static_cast<long long>(bh) * args.npairs);
-      const int q0 = args.q_begin + (pair * 2 + g) * 128;
+      const int q0 = args.q_begin + (pair * NG + g) * 128;
       if (q0 >= args.ntok) continue;        // this group has no query tile in this item (warp-uniform)
       float m = -INFINITY, l = 0.f, corr_prev = 0.f;
-      float o[64];
+      float o[HD];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] = 0.f;
+      for (int i = 0; i < HD; ++i) o[i] = 0.f;
+      auto absorb = [&](uint32_t t) {       // O = O * corr_prev + (P V)(chunk) read from TMEM
+#pragma unroll
+        for (int h = 0; h < HD / 32; ++h) {
+          uint32_t v[32];
+          tmem_ld32(t + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[h * 32 + c] = fmaf(o[h * 32 + c], corr_prev, __uint_as_float(v[c]));
+        }
+      };
       for (int j = 0; j < J; ++j) {
         const uint32_t tS = tX + (j & 1) * 128;
         mbar_wait(&s_full[2 * g + (j & 1)], sfull_cnt[j & 1] & 1);
@@ -254,26 +279,18 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         const float m_new = fmaxf(m, mx * args.scale_log2e);   // chunk 0 always has valid keys -> finite
         const float corr = ex2(m - m_new);
         m = m_new;
+        if (j > 0) {                                // PV_{j-1} retired: P smem is free, O(j-1) sits in X[(j-1)&1][0:HD)
+          mbar_wait(&o_full[g], ofull_cnt & 1);
+          ++ofull_cnt;
+          tc_fence_after();
+          absorb(tX + ((j - 1) & 1) * 128);
+          tc_fence_before();
+          mbar_arrive(&x_free[2 * g + ((j - 1) & 1)]);   // buffer (j-1)&1 may now receive S(j+1)
+        }
         // ---- pass 2: P = exp2(s*scale - m) -> 16-bit -> swizzled smem (A operand of the PV MMA)
         float rs = 0.f;
         {
           uint32_t va[32], vb[32];
-          if (j > 0) {                              // PV_{j-1} retired: P smem is free, O(j-1) sits in X[(j-1)&1][0:64)
-            mbar_wait(&o_full[g], ofull_cnt & 1);
-            ++ofull_cnt;
-            tc_fence_after();
-            const uint32_t t = tX + ((j - 1) & 1) * 128;
-            tmem_ld32(t, va);
-            tmem_ld32(t + 32, vb);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {          // absorb: O = O * corr_{j-1} + P_{j-1} V_{j-1}
-              o[c] = fmaf(o[c], corr_prev, __uint_as_float(va[c]));
-              o[32 + c] = fmaf(o[32 + c], corr_prev, __uint_as_float(vb[c]));
-            }
-            tc_fence_before();
-            mbar_arrive(&x_free[2 * g + ((j - 1) & 1)]);   // buffer (j-1)&1 may now receive S(j+1)
-          }
           tmem_ld32(tS, va);
           auto emit = [&](const uint32_t (&v)[32], int pc) {
             uint32_t pk[16];
@@ -308,7 +325,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
           tmem_ld_wait();
           emit(vb, 3);
         }
-        tc_fence_before();                         // all reads of S_g(j) done: PV(j) may overwrite X[j&1][0:64)
+        tc_fence_before();                         // all reads of S_g(j) done: PV(j) may overwrite X[j&1][0:HD)
         fence_proxy_async();                       // make the generic-proxy P writes visible to the MMA (async proxy)
         mbar_arrive(&p_full[g]);
         l = l * corr + rs;
@@ -318,39 +335,34 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       mbar_wait(&o_full[g], ofull_cnt & 1);
       ++ofull_cnt;
       tc_fence_after();
-      {
-        const uint32_t t = tX + ((J - 1) & 1) * 128;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld32(t + h * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[h * 32 + c] = fmaf(o[h * 32 + c], corr_prev, __uint_as_float(v[c]));
-        }
-      }
+      absorb(tX + ((J - 1) & 1) * 128);
       tc_fence_before();
       mbar_arrive(&x_free[2 * g + ((J - 1) & 1)]);
-      // ---- normalise, stage this warp's 32 rows through (now free) P smem, coalesced store to [B, ntok, heads*64]
+      // ---- normalise, stage this warp's 32 rows through (now free) P smem (64 dims per 16 KB block), coalesced store
       const float inv = 1.f / l;
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        sts128a(sP_row + ((c ^ (row & 7)) << 4), TT::pack2(o[8 * c] * inv, o[8 * c + 1] * inv),
-                TT::pack2(o[8 * c + 2] * inv, o[8 * c + 3] * inv), TT::pack2(o[8 * c + 4] * inv, o[8 * c + 5] * inv),
-                TT::pack2(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
+      for (int hb = 0; hb < HD / 64; ++hb)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float* oo = o + hb * 64 + 8 * c;
+          sts128a(sP_row + hb * (128 * 128) + ((c ^ (row & 7)) << 4), TT::pack2(oo[0] * inv, oo[1] * inv),
+                  TT::pack2(oo[2] * inv, oo[3] * inv), TT::pack2(oo[4] * inv, oo[5] * inv), TT::pack2(oo[6] * inv, oo[7] * inv));
+        }
       __syncwarp();
       const int b = bh / args.heads, hd = bh - b * args.heads;
-      const int D = args.heads * 64;
+      const int D = args.heads * HD;
       T* outp = reinterpret_cast<T*>(args.out);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = q4 * 32 + i * 4 + (lane >> 3);
-        const uint4 val = lds128a(sP_base + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-        const int t = q0 + rr;
-        if (t < args.ntok)
-          *reinterpret_cast<uint4*>(outp + (static_cast<long long>(b) * args.ntok + t) * D + hd * 64 + (lane & 7) * 8) = val;
-      }
+      for (int hb = 0; hb < HD / 64; ++hb)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = q4 * 32 + i * 4 + (lane >> 3);
+          const uint4 val = lds128a(sP_base + hb * (128 * 128) + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+          const int t = q0 + rr;
+          if (t < args.ntok)
+            *reinterpret_cast<uint4*>(outp + (static_cast<long long>(b) * args.ntok + t) * D + hd * HD + hb * 64 + (lane & 7) * 8) = val;
+        }
       __syncwarp();
     }
   }
@@ -535,43 +547,59 @@ extern "C" int b2u_attention_rows(const void* q, const void* k, const void* vt, 
   return check_launch("attention_rows");
 }
 
-extern "C" int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,
-                                int32_t ntok, int32_t npad, int32_t q_begin, float scale, int32_t dtype,
-                                b2u_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+template <typename T, int HD>
+static int launch_attn_tc(const AttnMaps& maps, const AttnArgs& a, cudaStream_t stream) {
+  auto kern = attn_tc_kernel<T, HD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<HD>::kSmem);
+    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(attn_tc): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int sms = num_sms();
+  const int grid = static_cast<int>(a.items < sms ? a.items : sms);
+  kern<<<grid, AtCfg<HD>::kThreads, AtCfg<HD>::kSmem, stream>>>(maps, a);
+  return check_launch("attention_tc");
+}
+
+static int attention_tc_impl(const void* q, const void* k, const void* vt, void* out, int B, int heads, int ntok, int npad,
+                             int q_begin, int head_dim, float scale, int dtype, cudaStream_t stream) {
   if (!q || !k || !vt || !out) return set_error(-1, "b2u_attention_tc: null pointer");
   if (npad % 8 || npad < ntok) return set_error(-1, "b2u_attention_tc: npad must be a multiple of 8 and >= ntok");
+  if (head_dim != 64 && head_dim != 128) return set_error(-1, "b2u_attention_tc: head_dim must be 64 or 128");
+  if (q_begin < 0 || q_begin >= ntok) return set_error(-1, "b2u_attention_tc: bad q_begin");
   AttnMaps maps;
   AttnArgs a{};
   a.BH = B * heads;
   a.heads = heads;
   a.ntok = ntok;
-  if (q_begin < 0 || q_begin >= ntok) return set_error(-1, "b2u_attention_tc: bad q_begin");
   a.q_begin = q_begin;
   a.nchunks = (ntok + 127) / 128;
-  a.npairs = ((ntok - q_begin + 127) / 128 + 1) / 2;
+  const int groups = head_dim == 64 ? 2 : 1;
+  a.npairs = ((ntok - q_begin + 127) / 128 + groups - 1) / groups;
   a.items = static_cast<long long>(a.BH) * a.npairs;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.out = out;
   int rc;
-  const uint64_t BH = static_cast<uint64_t>(a.BH);
-  if ((rc = make_map_3d(&maps.q, q, dtype, 64, ntok, BH, 64, static_cast<uint64_t>(ntok) * 64, 64, 128))) return rc;
-  if ((rc = make_map_3d(&maps.k, k, dtype, 64, ntok, BH, 64, static_cast<uint64_t>(ntok) * 64, 64, 128))) return rc;
-  if ((rc = make_map_3d(&maps.vt, vt, dtype, npad, 64, BH, npad, static_cast<uint64_t>(npad) * 64, 64, 64))) return rc;
-  static bool configured[2] = {false, false};
-  const int di = dtype == B2U_BF16 ? 1 : 0;
-  if (!configured[di]) {
-    cudaError_t e = dtype == B2U_BF16
-                        ? cudaFuncSetAttribute(attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)
-                        : cudaFuncSetAttribute(attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(attn_tc): %s", cudaGetErrorString(e));
-    configured[di] = true;
-  }
-  const int sms = num_sms();
-  const int grid = static_cast<int>(a.items < sms ? a.items : sms);
-  if (dtype == B2U_BF16) attn_tc_kernel<__nv_bfloat16><<<grid, 320, AT_SMEM, stream>>>(maps, a);
-  else attn_tc_kernel<__half><<<grid, 320, AT_SMEM, stream>>>(maps, a);
-  return check_launch("attention_tc");
+  const uint64_t BH = static_cast<uint64_t>(a.BH), hd = static_cast<uint64_t>(head_dim);
+  if ((rc = make_map_3d(&maps.q, q, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
+  if ((rc = make_map_3d(&maps.k, k, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
+  if ((rc = make_map_3d(&maps.vt, vt, dtype, npad, hd, BH, npad, static_cast<uint64_t>(npad) * hd, 64, static_cast<uint32_t>(head_dim)))) return rc;
+  if (head_dim == 64)
+    return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 64>(maps, a, stream) : launch_attn_tc<__half, 64>(maps, a, stream);
+  return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 128>(maps, a, stream) : launch_attn_tc<__half, 128>(maps, a, stream);
+}
+
+extern "C" int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,
+                                int32_t ntok, int32_t npad, int32_t q_begin, float scale, int32_t dtype,
+                                b2u_stream_t stream_) {
+  return attention_tc_impl(q, k, vt, out, B, heads, ntok, npad, q_begin, 64, scale, dtype, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int b2u_attention_tc_hd(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,
+                                   int32_t ntok, int32_t npad, int32_t head_dim, float scale, int32_t dtype,
+                                   b2u_stream_t stream_) {
+  return attention_tc_impl(q, k, vt, out, B, heads, ntok, npad, 0, head_dim, scale, dtype, static_cast<cudaStream_t>(stream_));
 }
 
 }  // namespace b2u

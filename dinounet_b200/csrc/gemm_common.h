@@ -26,7 +26,7 @@ struct GemmArgs {
   int TW, TH, tiles_x, tiles_y;
   b2u_epilogue epi;
   // QKV epilogue
-  int ntok, D, heads, prefix;
+  int ntok, D, heads, prefix, head_dim;
   const float* rope_sin;
   const float* rope_cos;
   void* q;

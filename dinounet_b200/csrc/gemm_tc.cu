@@ -423,7 +423,9 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
 extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!p || !p->A || !p->Wp || !p->q || !p->k || !p->v) return set_error(-1, "b2u_qkv_rope: null pointer");
-  if (p->D != p->heads * 64) return set_error(-1, "b2u_qkv_rope: head_dim must be 64");
+  const int head_dim = p->heads > 0 ? p->D / p->heads : 0;
+  if (p->D != p->heads * head_dim || (head_dim != 64 && head_dim != 128))
+    return set_error(-1, "b2u_qkv_rope: head_dim must be 64 or 128");
   GemmMaps maps;
   GemmArgs a{};
   a.M = p->B * p->ntok;
@@ -434,7 +436,8 @@ extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   a.n_tiles = (a.N + bn - 1) / bn;
   a.conv = 0;
   a.epi.bias = p->bias;
-  a.ntok = p->ntok; a.D = p->D; a.heads = p->heads; a.prefix = p->prefix;
+  a.ntok = p->ntok; a.D = p->D; a.heads = p->heads; a.prefix = p->prefix; a.head_dim = head_dim;
+  if (head_dim == 128 && !v2) return set_error(-1, "b2u_qkv_rope: head_dim 128 needs the v2 GEMM kernel");
   a.rope_sin = p->rope_sin; a.rope_cos = p->rope_cos;
   a.q = p->q; a.k = p->k; a.v = p->v;
   a.npad = p->v_transposed ? p->npad : 0;

@@ -22,7 +22,7 @@ constexpr int kHaloW = 130;                           // 128 output pixels + 1 h
 constexpr int kHaloBytes = 3 * kHaloW * 128;           // one TMA box: 3 rows x 130 px x 64 ch x 2 B
 constexpr int kHaloStageBytes = 49 * 1024;             // box rounded up to the 1024 B swizzle period
 
-constexpr int kRopeBytes = 128 * 16 * 2 * 4;   // (rope_h + rope_w <= 128) rows x 16 angles x {sin, cos} fp32
+constexpr int kRopeBytes = 128 * 32 * 2 * 4;   // (rope_h + rope_w <= 128) rows x <=32 angles x {sin, cos} fp32
 
 template <int BN, int EPI = 0> struct Cfg2 {
   // the QKV variant trades one pipeline stage for the in-smem rope tables
@@ -132,15 +132,16 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
   if constexpr (EPI == 2) {
     if (args.rope_w > 0) {
-      // rows 0..h-1: angles that depend on the patch row (table columns 0..15 of patch (py, 0));
-      // rows h..h+w-1: angles that depend on the patch column (table columns 16..31 of patch (0, px))
-      const int n = (args.rope_h + args.rope_w) * 32;
+      // rows 0..h-1: the hq angles that depend on the patch row (table columns 0..hq-1 of patch (py, 0));
+      // rows h..h+w-1: the hq angles that depend on the patch column (table columns hq..2hq-1 of patch (0, px))
+      const int HDm = args.head_dim, hq = HDm >> 2;
+      const int n = (args.rope_h + args.rope_w) * 2 * hq;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int r = i >> 5, c = i & 31;
-        const bool is_cos = c >= 16;
-        const int a = c & 15;
-        const long long src = r < args.rope_h ? static_cast<long long>(r) * args.rope_w * 64 + a
-                                              : static_cast<long long>(r - args.rope_h) * 64 + 16 + a;
+        const int r = i / (2 * hq), c = i - r * 2 * hq;
+        const bool is_cos = c >= hq;
+        const int a = c - (is_cos ? hq : 0);
+        const long long src = r < args.rope_h ? static_cast<long long>(r) * args.rope_w * HDm + a
+                                              : static_cast<long long>(r - args.rope_h) * HDm + hq + a;
         s_rope[i] = is_cos ? __ldg(args.rope_cos + src) : __ldg(args.rope_sin + src);
       }
     }
@@ -292,15 +293,17 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         epi_bar_sync();
         for (int i = etid; i < BN; i += 256) s_bias[i] = (e.bias && n0 + i < args.N) ? __ldg(e.bias + n0 + i) : 0.f;
         epi_bar_sync();
+        const int HDm = args.head_dim;                 // 64 or 128
+        const int hq = HDm >> 2;                       // angles per axis (rope_position_encoding.py: D_head / 4)
         // phase-1 owner row
         long long m1;
         const bool v1 = row_of(q4 * 32 + lane, m1);
         const int b1 = static_cast<int>(m1 / args.ntok);
         const int t1 = static_cast<int>(m1 - static_cast<long long>(b1) * args.ntok);
         const bool rot = v1 && t1 >= args.prefix;
-        const float* sinr = args.rope_sin + static_cast<long long>(rot ? t1 - args.prefix : 0) * 64;
-        const float* cosr = args.rope_cos + static_cast<long long>(rot ? t1 - args.prefix : 0) * 64;
-        // phase-2 rows of this lane: rr = i*4 + lane/8  (8 lanes x 16 B = one 128 B head row)
+        const float* sinr = args.rope_sin + static_cast<long long>(rot ? t1 - args.prefix : 0) * HDm;
+        const float* cosr = args.rope_cos + static_cast<long long>(rot ? t1 - args.prefix : 0) * HDm;
+        // phase-2 rows of this lane: rr = i*4 + lane/8  (8 lanes x 16 B = the unit's two 64 B segments of a row)
         long long dst_off[8];
         bool dst_ok[8];
 #pragma unroll
@@ -309,46 +312,58 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           dst_ok[i] = row_of(q4 * 32 + i * 4 + (lane >> 3), m2);
           const int b2 = static_cast<int>(m2 / args.ntok);
           const int t2 = static_cast<int>(m2 - static_cast<long long>(b2) * args.ntok);
-          dst_off[i] = (static_cast<long long>(b2) * args.heads * args.ntok + t2) * 64;
+          dst_off[i] = (static_cast<long long>(b2) * args.heads * args.ntok + t2) * HDm;
         }
         mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
+        // A "unit" = 64 accumulator columns = the 32 low + 32 matching high rope columns of one head:
+        //   head_dim 64 : unit u = head u of the tile, lo = [0,32), hi = [32,64)
+        //   head_dim 128: unit u = (head u/2, pass p = u&1), lo = [32p, 32p+32), hi = [64+32p, 64+32p+32)
 #pragma unroll 1
-        for (int g = half * (BN / 128); g < (half + 1) * (BN / 128); ++g) {
+        for (int u = half * (BN / 128); u < (half + 1) * (BN / 128); ++u) {
+          const int hcol = HDm == 64 ? u * 64 : (u >> 1) * 128;          // first accumulator column of the head
+          const int pss = HDm == 64 ? 0 : (u & 1);
+          const int lo_off = pss * 32, hi_off = (HDm >> 1) + pss * 32;    // element offsets inside the head
           uint32_t v0[32], v1r[32];
-          tmem_ld32(taddr + g * 64, v0);
-          tmem_ld32(taddr + g * 64 + 32, v1r);
+          tmem_ld32(taddr + hcol + lo_off, v0);
+          tmem_ld32(taddr + hcol + hi_off, v1r);
           tmem_ld_wait();
-          const int n = n0 + g * 64;
+          const int n = n0 + hcol;
           if (n >= args.N) continue;   // warp-uniform
           const int which = n / args.D;
-          const int head = (n - which * args.D) >> 6;
+          const int head = (n - which * args.D) / HDm;
           float x[64];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            x[j] = TT::to_f(TT::from_f(__uint_as_float(v0[j]) + s_bias[g * 64 + j]));
-            x[32 + j] = TT::to_f(TT::from_f(__uint_as_float(v1r[j]) + s_bias[g * 64 + 32 + j]));
+            x[j] = TT::to_f(TT::from_f(__uint_as_float(v0[j]) + s_bias[hcol + lo_off + j]));
+            x[32 + j] = TT::to_f(TT::from_f(__uint_as_float(v1r[j]) + s_bias[hcol + hi_off + j]));
           }
           if (which == 2 && args.npad > 0) {
-            // V^T [B, heads, 64, npad]: lane = token, loop over d -> each store instruction writes 32 consecutive keys
+            // V^T [B, heads, head_dim, npad]: lane = token, loop over d -> each store instruction writes 32 consecutive keys
             if (v1) {
-              T* dst = reinterpret_cast<T*>(args.v) + (static_cast<long long>(b1) * args.heads + head) * 64 * args.npad + t1;
+              T* dst = reinterpret_cast<T*>(args.v) + (static_cast<long long>(b1) * args.heads + head) * HDm * args.npad + t1;
 #pragma unroll
-              for (int j = 0; j < 64; ++j) dst[static_cast<long long>(j) * args.npad] = TT::from_f(x[j]);
+              for (int j = 0; j < 32; ++j) {
+                dst[static_cast<long long>(lo_off + j) * args.npad] = TT::from_f(x[j]);
+                dst[static_cast<long long>(hi_off + j) * args.npad] = TT::from_f(x[32 + j]);
+              }
             }
             continue;   // warp-uniform
           }
           uint32_t packed[32];
           if (which < 2 && rot && args.rope_w > 0) {
-            // separable tables from smem: angle j (<16) from the row table, (16..31) from the column table; cos/sin[j+32] == [j]
+            // separable tables from smem ([h + w] rows of (sin[hq] | cos[hq])): angle A < hq comes from the patch row's
+            // table, A >= hq from the patch column's; cos/sin[A + head_dim/2] == cos/sin[A]
             const int pidx = t1 - args.prefix;
             const int py = pidx / args.rope_w, px = pidx - py * args.rope_w;
-            const uint32_t ry = smem_u32(s_rope) + py * 128, rx = smem_u32(s_rope) + (args.rope_h + px) * 128;
+            const uint32_t rstride = hq * 8;           // bytes per table row
+            const uint32_t ry = smem_u32(s_rope) + py * rstride, rx = smem_u32(s_rope) + (args.rope_h + px) * rstride;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const uint32_t rbase_ = (j < 16 ? ry : rx) + (j & 15) * 4;
-              const float4 sn = lds128f(rbase_), cs = lds128f(rbase_ + 64);
+              const int A = lo_off + j;                // angle index in [0, head_dim/2)
+              const uint32_t rbase_ = (A < hq ? ry : rx) + (A & (hq - 1)) * 4;
+              const float4 sn = lds128f(rbase_), cs = lds128f(rbase_ + hq * 4);
               packed[j / 2] = TT::pack2(x[j] * cs.x - x[j + 32] * sn.x, x[j + 1] * cs.y - x[j + 33] * sn.y);
               packed[j / 2 + 1] = TT::pack2(x[j + 2] * cs.z - x[j + 34] * sn.z, x[j + 3] * cs.w - x[j + 35] * sn.w);
               packed[16 + j / 2] = TT::pack2(x[j + 32] * cs.x + x[j] * sn.x, x[j + 33] * cs.y + x[j + 1] * sn.y);
@@ -357,8 +372,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           } else if (which < 2 && rot) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 c_lo = *reinterpret_cast<const float4*>(cosr + j), s_lo = *reinterpret_cast<const float4*>(sinr + j);
-              const float4 c_hi = *reinterpret_cast<const float4*>(cosr + 32 + j), s_hi = *reinterpret_cast<const float4*>(sinr + 32 + j);
+              const float4 c_lo = *reinterpret_cast<const float4*>(cosr + lo_off + j), s_lo = *reinterpret_cast<const float4*>(sinr + lo_off + j);
+              const float4 c_hi = *reinterpret_cast<const float4*>(cosr + hi_off + j), s_hi = *reinterpret_cast<const float4*>(sinr + hi_off + j);
               packed[j / 2] = TT::pack2(x[j] * c_lo.x - x[j + 32] * s_lo.x, x[j + 1] * c_lo.y - x[j + 33] * s_lo.y);
               packed[j / 2 + 1] = TT::pack2(x[j + 2] * c_lo.z - x[j + 34] * s_lo.z, x[j + 3] * c_lo.w - x[j + 35] * s_lo.w);
               packed[16 + j / 2] = TT::pack2(x[j + 32] * c_hi.x + x[j] * s_hi.x, x[j + 33] * c_hi.y + x[j + 1] * s_hi.y);
@@ -368,14 +383,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 64; j += 2) packed[j / 2] = TT::pack2(x[j], x[j + 1]);
           }
-          // stage: row = lane, 8 x 16 B chunks, chunk position c ^ (row & 7)
+          // stage: row = lane, 8 x 16 B chunks (4 of the lo segment, 4 of the hi segment), chunk position c ^ (row & 7)
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             sts128(patch_u32 + lane * 128 + ((c ^ (lane & 7)) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
           __syncwarp();
           T* base = reinterpret_cast<T*>(which == 0 ? args.q : (which == 1 ? args.k : args.v)) +
-                    static_cast<long long>(head) * args.ntok * 64 + (lane & 7) * 8;
+                    static_cast<long long>(head) * args.ntok * HDm + ((lane & 4) ? hi_off : lo_off) + (lane & 3) * 8;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + (lane >> 3);

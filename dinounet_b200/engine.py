@@ -60,9 +60,11 @@ class ForwardEngine:
         if variant not in cfg.VARIANTS:
             raise ValueError(f"Unknown model: {variant}")
         self.v = cfg.VARIANTS[variant]
-        if self.v.ffn_layer != "mlp" or self.v.embed_dim // self.v.num_heads != 64:
-            raise NotImplementedError(
-                f"{variant}: SwiGLU FFN / head_dim 128 kernels are not built yet (round-1 scope: dinounet_s/b/l)")
+        self.hd = self.v.embed_dim // self.v.num_heads
+        if self.hd not in (64, 128) or self.v.ffn_layer not in ("mlp", "swiglu64"):
+            raise NotImplementedError(f"{variant}: kernels exist for head_dim 64/128 and mlp / swiglu64 FFNs")
+        if self.hd == 128 and attn_impl != "tc":
+            raise NotImplementedError("head_dim 128 needs the tcgen05 attention kernel (attn_impl='tc')")
         if tuple(features) != (32, 64, 128, 256):
             raise NotImplementedError("kernels are built for the planner's features_per_stage=(32,64,128,256)")
         self.lib = L.load()
@@ -126,8 +128,16 @@ class ForwardEngine:
             w[f"b{i}.proj"], w[f"b{i}.projb"] = self._lin(P[p + "attn.proj.weight"], tv), f32(P[p + "attn.proj.bias"])
             w[f"b{i}.ls1"], w[f"b{i}.ls2"] = f32(P[p + "ls1.gamma"]), f32(P[p + "ls2.gamma"])
             w[f"b{i}.n2w"], w[f"b{i}.n2b"] = f32(P[p + "norm2.weight"]), f32(P[p + "norm2.bias"])
-            w[f"b{i}.fc1"], w[f"b{i}.fc1b"] = self._lin(P[p + "mlp.fc1.weight"], tv), f32(P[p + "mlp.fc1.bias"])
-            w[f"b{i}.fc2"], w[f"b{i}.fc2b"] = self._lin(P[p + "mlp.fc2.weight"], tv), f32(P[p + "mlp.fc2.bias"])
+            if v.ffn_layer == "mlp":
+                w[f"b{i}.fc1"], w[f"b{i}.fc1b"] = self._lin(P[p + "mlp.fc1.weight"], tv), f32(P[p + "mlp.fc1.bias"])
+                w[f"b{i}.fc2"], w[f"b{i}.fc2b"] = self._lin(P[p + "mlp.fc2.weight"], tv), f32(P[p + "mlp.fc2.bias"])
+            else:   # SwiGLU (ffn_layers.py:73-77): w1|w2 interleaved in 32-row blocks for the fused silu(x1)*x2 epilogue
+                hid = v.ffn_hidden
+                w1, w2 = P[p + "mlp.w1.weight"].float(), P[p + "mlp.w2.weight"].float()
+                w[f"b{i}.fc1"] = self._dev(torch.stack([w1.view(hid // 32, 32, D), w2.view(hid // 32, 32, D)], 1).reshape(2 * hid, D), tv)
+                w[f"b{i}.fc1b"] = f32(torch.stack([P[p + "mlp.w1.bias"].float().view(hid // 32, 32),
+                                                   P[p + "mlp.w2.bias"].float().view(hid // 32, 32)], 1).reshape(2 * hid))
+                w[f"b{i}.fc2"], w[f"b{i}.fc2b"] = self._lin(P[p + "mlp.w3.weight"], tv), f32(P[p + "mlp.w3.bias"])
         w["norm.w"], w["norm.b"] = f32(P[Bk + "norm.weight"]), f32(P[Bk + "norm.bias"])
         # ---- SPM
         S = A + "spm."
@@ -203,7 +213,7 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ plan helpers
     def _rope_tables(self, h: int, wd: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """rope_position_encoding.py:57-106 (eval, 'separate' normalisation, fp32) -> sin, cos [h*w, 64]."""
+        """rope_position_encoding.py:57-106 (eval, 'separate' normalisation, fp32) -> sin, cos [h*w, head_dim]."""
         periods = self.w["periods"]
         ch = torch.arange(0.5, h, dtype=torch.float32) / h
         cw = torch.arange(0.5, wd, dtype=torch.float32) / wd
@@ -264,11 +274,12 @@ class ForwardEngine:
         X = buf("X", (T, D), torch.float32)
         Y = buf("Y", (T, D), tv)
         npad = (N + 7) // 8 * 8
-        Q, K_ = buf("Q", (B, Hh, N, 64), tv), buf("K", (B, Hh, N, 64), tv)
+        hd = self.hd
+        Q, K_ = buf("Q", (B, Hh, N, hd), tv), buf("K", (B, Hh, N, hd), tv)
         if self.attn_impl == "tc":   # V^T with zeroed padding columns (never written by the QKV epilogue)
-            V = bufs["V"] = torch.zeros((B, Hh, 64, npad), dtype=tv, device=dev)
+            V = bufs["V"] = torch.zeros((B, Hh, hd, npad), dtype=tv, device=dev)
         else:
-            V = buf("V", (B, Hh, N, 64), tv)
+            V = buf("V", (B, Hh, N, hd), tv)
         O = buf("O", (T, D), tv)
         Hid = buf("Hid", (T, v.ffn_hidden), tv)
         taps = [buf(f"tap{k}", (B * P, D), torch.float32) for k in range(4)]
@@ -297,16 +308,24 @@ class ForwardEngine:
                 # one launch over all ntok query rows.  (Splitting off the 5 cls/storage rows so that the 1024 patch rows fill
                 # whole tile pairs was measured: tcgen05 part 370 -> 326 us/layer, but the few-row kernel costs more than
                 # the 45 us it saves, so q_begin stays 0; b2u_attention_rows remains available.)
-                plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 0,
-                         64 ** -0.5, vt)
+                if hd == 64:
+                    plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 0,
+                             hd ** -0.5, vt)
+                else:
+                    plan.add(f"b{i}.attn", lib.b2u_attention_tc_hd, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, hd,
+                             hd ** -0.5, vt)
             else:
                 plan.add(f"b{i}.attn", lib.b2u_attention, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, 64 ** -0.5, vt)
             self._gemm(plan, f"b{i}.proj", O, T, D, D, w[f"b{i}.proj"], D, X, D, vt, out_fp32=True, bias=w[f"b{i}.projb"],
                        scale=w[f"b{i}.ls1"], residual=X, ldres=D)
             plan.add(f"b{i}.ln2", lib.b2u_layernorm, _ptr(X), _ptr(Y), _ptr(w[f"b{i}.n2w"]), _ptr(w[f"b{i}.n2b"]), T, D,
                      cfg.LN_EPS_VIT, 0, 0, 0, 0, vt)
-            self._gemm(plan, f"b{i}.fc1", Y, T, D, D, w[f"b{i}.fc1"], v.ffn_hidden, Hid, v.ffn_hidden, vt,
-                       bias=w[f"b{i}.fc1b"], act1=L.ACT_GELU)
+            if v.ffn_layer == "mlp":
+                self._gemm(plan, f"b{i}.fc1", Y, T, D, D, w[f"b{i}.fc1"], v.ffn_hidden, Hid, v.ffn_hidden, vt,
+                           bias=w[f"b{i}.fc1b"], act1=L.ACT_GELU)
+            else:
+                self._gemm(plan, f"b{i}.fc1", Y, T, D, D, w[f"b{i}.fc1"], 2 * v.ffn_hidden, Hid, v.ffn_hidden, vt,
+                           bias=w[f"b{i}.fc1b"], act1=L.ACT_SWIGLU)
             self._gemm(plan, f"b{i}.fc2", Hid, T, v.ffn_hidden, v.ffn_hidden, w[f"b{i}.fc2"], D, X, D, vt, out_fp32=True,
                        bias=w[f"b{i}.fc2b"], scale=w[f"b{i}.ls2"], residual=X, ldres=D)
             if i in v.interaction_indexes:

@@ -60,6 +60,7 @@ SIGNATURES = {
     "b2u_qkv_rope": [C.POINTER(QkvParams), vp],
     "b2u_attention": [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
     "b2u_attention_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp],
+    "b2u_attention_tc_hd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp],
     "b2u_attention_rows": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp],
     "b2u_layernorm": [vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp],
     "b2u_cast_rows": [vp, vp, i32, i32, i32, i32, i32, i32, vp],

@@ -81,7 +81,8 @@ int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream);
 
 /* QKV projection with masked bias + RoPE + head split fused in the epilogue (attention.py:30-40,66-92):
  *   qkv = A[M=B*ntok, D] * Wp[3D, D]^T + bias (already multiplied by bias_mask); rounded to dtype; q,k rows with
- *   token index >= prefix rotated with sin/cos[(tok - prefix), 64] (fp32); written as q,k,v [B, heads, ntok, 64]. */
+ *   token index >= prefix rotated with sin/cos[(tok - prefix), hd] (fp32); written as q,k,v [B, heads, ntok, hd],
+ *   hd = D / heads = 64 (ViT-S/B/L) or 128 (ViT-7B). */
 typedef struct b2u_qkv_params {
   int32_t B, ntok, D, heads, prefix;
   const void* A;
@@ -115,6 +116,10 @@ int b2u_attention(const void* q, const void* k, const void* v, void* out, int32_
  * number of cls/storage tokens the ViT's 1024 patch rows fill whole tiles and b2u_attention_rows does the prefix. */
 int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads, int32_t ntok,
                      int32_t npad, int32_t q_begin, float scale, int32_t dtype, b2u_stream_t stream);
+
+/* Same kernel for head_dim 64 or 128 (ViT-7B: q,k [B, heads, ntok, 128], vt [B, heads, 128, npad]); all query rows. */
+int b2u_attention_tc_hd(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads, int32_t ntok,
+                        int32_t npad, int32_t head_dim, float scale, int32_t dtype, b2u_stream_t stream);
 
 /* Few-row attention (same layouts as b2u_attention_tc): query rows [row_begin, row_begin + nrows), one warp per row,
  * fp32 softmax.  Meant for the handful of prefix-token rows. */

@@ -58,6 +58,9 @@ VARIANTS: Dict[str, VariantCfg] = {
     "dinounet_l": VariantCfg("dinounet_l", 1024, 24, 16, "mlp", 4096, True, (4, 11, 17, 23)),
     # swiglu64, ffn_ratio 3 -> int(4096*3*2/3) aligned to 64 = 8192 (ffn_layers.py:67-68)
     "dinounet_7b": VariantCfg("dinounet_7b", 4096, 40, 32, "swiglu", 8192, False, (9, 19, 29, 39), True),
+    # TEST-ONLY miniature of the 7B recipe (SwiGLU-64 with ffn_ratio 3, head_dim 128, no qkv bias, untied local cls norm):
+    # exercises exactly the code paths that differ from s/b/l at a size the CPU oracle and the goldens can afford.
+    "dinounet_7b_tiny": VariantCfg("dinounet_7b_tiny", 1024, 4, 8, "swiglu", 2048, False, (0, 1, 2, 3), True),
 }
 
 FEATURES = (32, 64, 128, 256)      # plans features_per_stage

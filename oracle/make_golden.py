@@ -22,6 +22,7 @@ CASES = [
     ("dinounet_s", 1, 512, 0, 1),
     ("dinounet_b", 1, 256, 0, 0),
     ("dinounet_l", 1, 256, 0, 0),
+    ("dinounet_7b_tiny", 1, 256, 0, 0),
 ]
 NSAMP = 2048
 

@@ -169,9 +169,30 @@ PLANS_ARCH = {
 }
 
 
+def _register_tiny_7b(ref):
+    """Adds the test-only `dinounet_7b_tiny` recipe (dinov3_vit7b16's kwargs, hub/backbones.py:452-494, at small size) to
+    the reference's own registries so the REAL reference code builds it."""
+    if "dinounet_7b_tiny" in ref.DINOv3_MODEL_FACTORIES:
+        return
+    from dinounet.dinov3.hub.backbones import _make_dinov3_vit
+
+    def factory(*, pretrained=False, **kw):
+        return _make_dinov3_vit(img_size=224, patch_size=16, in_chans=3, pos_embed_rope_base=100,
+                                pos_embed_rope_normalize_coords="separate", pos_embed_rope_rescale_coords=2,
+                                pos_embed_rope_dtype="fp32", embed_dim=1024, depth=4, num_heads=8, ffn_ratio=3,
+                                qkv_bias=False, drop_path_rate=0.4, layerscale_init=1.0e-05, norm_layer="layernormbf16",
+                                ffn_layer="swiglu64", ffn_bias=True, proj_bias=True, n_storage_tokens=4, mask_k_bias=True,
+                                untie_global_and_local_cls_norm=True, pretrained=False, compact_arch_name="vit7b")
+
+    ref.DINOv3_MODEL_FACTORIES["dinounet_7b_tiny"] = factory
+    ref.DINOv3_INTERACTION_INDEXES["dinounet_7b_tiny"] = [0, 1, 2, 3]
+    ref.DINOv3_MODEL_INFO["dinounet_7b_tiny"] = {"embed_dim": 1024, "depth": 4, "num_heads": 8, "params": "test"}
+
+
 def build_reference_model(model_name: str, num_classes: int = 2, state_dict=None):
     """Build the REAL reference DinoUNet (random-init, no download) in eval mode on CPU."""
     ref = load_reference_module()
+    _register_tiny_7b(ref)
 
     def _load_no_download(name, pretrained_path=None):
         return ref.DINOv3_MODEL_FACTORIES[name](pretrained=False)

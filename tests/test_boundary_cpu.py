@@ -104,7 +104,9 @@ def test_no_cpu_fallback(built):
         net.train()(torch.zeros(1, 3, 64, 64))
 
 
-def test_engine_rejects_unbuilt_variants(built):
+def test_engine_rejects_unsupported_kernel_choices(built):
     from dinounet_b200.engine import ForwardEngine
-    with pytest.raises(NotImplementedError):
-        ForwardEngine("dinounet_7b", {}, 2, torch.device("cpu"))
+    with pytest.raises(NotImplementedError):   # head_dim 128 exists only in the tcgen05 attention kernel
+        ForwardEngine("dinounet_7b", {}, 2, torch.device("cpu"), attn_impl="mma")
+    with pytest.raises(ValueError):
+        ForwardEngine("dinounet_xl", {}, 2, torch.device("cpu"))

@@ -248,6 +248,51 @@ def test_attention_tcgen05(dtype, B, Hh, N):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("dtype", [L.BF16, L.F16])
+@pytest.mark.parametrize("B,Hh,N", [(1, 2, 1029), (2, 3, 261), (1, 1, 128)])
+def test_attention_tcgen05_head_dim_128(dtype, B, Hh, N):
+    td = TD[dtype]
+    lib = L.load()
+    q, k, v = (_rand(B, Hh, N, 128, dt=td, seed=s) for s in range(3))
+    npad = (N + 7) // 8 * 8
+    vt = torch.zeros(B, Hh, 128, npad, device=DEV, dtype=td)
+    vt[..., :N] = v.transpose(2, 3)
+    out = torch.full((B, N, Hh * 128), float("nan"), device=DEV, dtype=td)
+    L.check(lib.b2u_attention_tc_hd(P(q), P(k), P(vt), P(out), B, Hh, N, npad, 128, 128 ** -0.5, dtype, stream()), "attn128")
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, Hh * 128)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -8), rel_err(out, ref)
+
+
+def test_qkv_rope_head_dim_128():
+    """QKV epilogue for the 7B head size: rope pairs (j, j+64), 32 angles per axis, V^T with 128 rows per head."""
+    dtype, td = L.BF16, torch.bfloat16
+    B, h, D, Hh = 2, 8, 512, 4
+    N = h * h + 5
+    npad = (N + 7) // 8 * 8
+    lib = L.load()
+    Y = _rand(B * N, D, dt=td)
+    Wq = _rand(3 * D, D, dt=td, scale=D ** -0.5, seed=1)
+    periods = 100.0 ** (2 * torch.arange(32, dtype=torch.float32) / 64)
+    sin, cos = [t.to(DEV).contiguous() for t in O.rope_sincos(periods, h, h)]
+    qkv = (Y.float() @ Wq.float().t()).to(td)
+    qr, kr, vr = [t.transpose(1, 2) for t in torch.unbind(qkv.reshape(B, N, 3, Hh, 128), 2)]
+    qr, kr = O._rope(qr, sin, cos), O._rope(kr, sin, cos)
+    for rope_w in (0, h):
+        q, k = (torch.full((B, Hh, N, 128), float("nan"), device=DEV, dtype=td) for _ in range(2))
+        vt = torch.zeros(B, Hh, 128, npad, device=DEV, dtype=td)
+        p = L.QkvParams()
+        p.B, p.ntok, p.D, p.heads, p.prefix = B, N, D, Hh, 5
+        p.A, p.lda, p.Wp, p.ldw, p.bias = P(Y), D, P(Wq), D, None
+        p.rope_sin, p.rope_cos, p.q, p.k, p.v, p.dtype = P(sin), P(cos), P(q), P(k), P(vt), dtype
+        p.v_transposed, p.npad, p.rope_w = 1, npad, rope_w
+        L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv128")
+        torch.cuda.synchronize()
+        assert rel_err(q, qr) < 2 ** -6 and rel_err(k, kr) < 2 ** -6, (rope_w, rel_err(q, qr), rel_err(k, kr))
+        assert rel_err(vt[..., :N].transpose(2, 3), vr) < 2 ** -6 and vt[..., N:].abs().max() == 0
+
+
 def test_qkv_vt_store_matches_transpose():
     dtype, td = L.BF16, torch.bfloat16
     B, h, D, Hh = 2, 8, 384, 6

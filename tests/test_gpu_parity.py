@@ -165,3 +165,24 @@ def test_streamed_predictor_matches_direct_forward():
     assert len(outs) == 5 and all(torch.equal(a, b) for a, b in zip(outs, direct))
     labs = [y.clone() for y in StreamedPredictor(net, want_labels=True).run(xs)]
     assert all(torch.equal(l.long(), d.argmax(1)) for l, d in zip(labs, direct))
+
+
+def test_7b_recipe_forward_matches_reference_golden(golden_dir):
+    """SwiGLU FFN + head_dim 128 + no qkv bias (the dinounet_7b recipe, hub/backbones.py:452-494) on a miniature
+    (`dinounet_7b_tiny`, registered test-only) against the golden produced by the REAL reference code."""
+    import dataclasses
+    from dinounet_b200 import config as cfgmod
+    name = "dinounet_7b_tiny"
+    cfgmod.VARIANTS[name] = cfgmod.VariantConfig(name, 1024, 4, 8, "swiglu64", 2048, False, (0, 1, 2, 3), True, 0.4)
+    try:
+        sd = O.make_state_dict(name, 2, seed=0)
+        x = O.make_input(1, 256, 0)
+        net = _net(name, sd)
+        with torch.no_grad():
+            y = net(x.cuda())
+        golden = torch.from_numpy(np.load(os.path.join(golden_dir, f"{name}_b1_s256_w0_x0.npz"))["logits"])
+        sd_cuda = {k: v.cuda() for k, v in sd.items()}
+        regime = O.forward(sd_cuda, name, x.cuda(), autocast_like_reference=True)
+        _compare(y, golden, regime, "7b-recipe tiny B1 S256 vs golden(reference)")
+    finally:
+        cfgmod.VARIANTS.pop(name, None)

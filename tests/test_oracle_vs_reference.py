@@ -9,7 +9,7 @@ from oracle.ref_loader import build_reference_model, reference_available
 pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
 
 
-@pytest.mark.parametrize("model,size", [("dinounet_s", 128), ("dinounet_b", 64)])
+@pytest.mark.parametrize("model,size", [("dinounet_s", 128), ("dinounet_b", 64), ("dinounet_7b_tiny", 64)])
 def test_bit_identical_to_reference(model, size):
     sd = O.make_state_dict(model, 2, seed=3)
     net = build_reference_model(model, 2)
