@@ -26,7 +26,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--model", default="dinounet_l", choices=["dinounet_s", "dinounet_b", "dinounet_l", "dinounet_7b"])
     ap.add_argument("--batch", type=int, default=32, help="patches per GPU per step")
     ap.add_argument("--size", type=int, default=512)
@@ -134,10 +134,41 @@ def run_reference(a):
     }))
 
 
+def run_reference_cuda(a):
+    """the same oracle port run by PyTorch eager on the B200 in the reference's GPU precision
+    regime (outer fp16 autocast, inner bf16 ViT, fp32 MSDA) — what a user gets from the reference code on this GPU
+    (cuBLAS/cuDNN/SDPA library kernels).  Informational third arm; not part of the driver contract."""
+    import torch
+    from oracle import dinounet_oracle as O
+    dev = torch.device("cuda", 0)
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(a.model, 2, seed=0).items()}
+    x = O.make_input(a.batch, a.size, 0).to(dev)
+    with torch.no_grad():
+        for _ in range(max(1, a.warmup)):
+            O.forward(sd, a.model, x, autocast_like_reference=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            O.forward(sd, a.model, x, autocast_like_reference=True)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    print(json.dumps({
+        "impl": "reference-cuda", "metric": "2D patches/sec (512x512) forward", "value": a.batch / ms * 1e3,
+        "unit": "patches/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "dtype": "fp16/bf16 autocast", "data": "synthetic",
+        "config": {"workload": f"{a.model} forward, {a.size}x{a.size}x3, batch {a.batch}, torch eager (library kernels), "
+                               "inputs resident in HBM"},
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    if a.impl == "reference-cuda":
+        return run_reference_cuda(a)
     import torch
     import torch.distributed as dist
     os.environ.setdefault("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "1")

@@ -277,5 +277,89 @@ extern "C" int b2u_msda_forward_f32(const float* value, const int64_t* spatial_s
                                                                             attw, out, B, S, Lq, heads, dh, levels, points);
   return check_launch("msda_forward_f32");
 }
+// Backward of the op above == the reference pybind op `ms_deform_attn_backward` (the one native kernel the reference's
+// training step executes, ms_deform_attn.py:58-66).  One warp per (b, q, head); lanes stride the channels, so the
+// per-sample scalars (grad of the location / attention weight) are warp-shuffle reductions and the scatter into
+// grad_value is a coalesced row of `red.global.add.f32` per bilinear corner (value maps are L2-resident: 32x32xD).
+__global__ void msda_bwd_f32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                                    const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                                    const float* __restrict__ attw, const float* __restrict__ gout,
+                                    float* __restrict__ gvalue, float* __restrict__ gloc, float* __restrict__ gattw,
+                                    int B, int S, int Lq, int M, int D, int L, int P) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(B) * Lq * M;
+  if (warp >= total) return;
+  const int m = static_cast<int>(warp % M);
+  const long long bq = warp / M;
+  const int b = static_cast<int>(bq / Lq);
+  const long long wbase = warp * L * P;
+  const float* go = gout + (bq * M + m) * D;
+  const long long rs = static_cast<long long>(M) * D;  // stride between spatial positions of one head
+  for (int l = 0; l < L; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const long long lbase = ((static_cast<long long>(b) * S + lsi[l]) * M + m) * D;
+    const float* vl = value + lbase;
+    float* gvl = gvalue + lbase;
+    for (int p = 0; p < P; ++p) {
+      const long long wi = wbase + l * P + p;
+      const float lx = loc[wi * 2], ly = loc[wi * 2 + 1], aw = attw[wi];
+      const float px = lx * W - 0.5f, py = ly * H - 0.5f;
+      float g_aw = 0.f, g_x = 0.f, g_y = 0.f;
+      if (py > -1 && px > -1 && py < H && px < W) {
+        const float fx = floorf(px), fy = floorf(py);
+        const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+        const float ax = px - fx, ay = py - fy;
+        const bool t = y0 >= 0, bt = y0 + 1 < H, lf = x0 >= 0, rt = x0 + 1 < W;
+        const long long o00 = static_cast<long long>(y0 * W + x0) * rs, o01 = o00 + rs,
+                        o10 = o00 + static_cast<long long>(W) * rs, o11 = o10 + rs;
+        const float w00 = (1.f - ay) * (1.f - ax), w01 = (1.f - ay) * ax, w10 = ay * (1.f - ax), w11 = ay * ax;
+        for (int c = lane; c < D; c += 32) {
+          const float g = go[c];
+          const float v00 = (t && lf) ? vl[o00 + c] : 0.f, v01 = (t && rt) ? vl[o01 + c] : 0.f;
+          const float v10 = (bt && lf) ? vl[o10 + c] : 0.f, v11 = (bt && rt) ? vl[o11 + c] : 0.f;
+          g_aw += g * (w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11);
+          g_x += g * ((1.f - ay) * (v01 - v00) + ay * (v11 - v10));
+          g_y += g * ((1.f - ax) * (v10 - v00) + ax * (v11 - v01));
+          const float ga = g * aw;
+          if (t && lf) atomicAdd(gvl + o00 + c, ga * w00);
+          if (t && rt) atomicAdd(gvl + o01 + c, ga * w01);
+          if (bt && lf) atomicAdd(gvl + o10 + c, ga * w10);
+          if (bt && rt) atomicAdd(gvl + o11 + c, ga * w11);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          g_aw += __shfl_xor_sync(0xffffffffu, g_aw, o);
+          g_x += __shfl_xor_sync(0xffffffffu, g_x, o);
+          g_y += __shfl_xor_sync(0xffffffffu, g_y, o);
+        }
+      }
+      if (lane == 0) {
+        gattw[wi] = g_aw;
+        gloc[wi * 2] = g_x * aw * W;
+        gloc[wi * 2 + 1] = g_y * aw * H;
+      }
+    }
+  }
+}
+
+extern "C" int b2u_msda_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                     const float* loc, const float* attw, const float* grad_out, float* grad_value,
+                                     float* grad_loc, float* grad_attw, int32_t B, int32_t S, int32_t Lq, int32_t heads,
+                                     int32_t dh, int32_t levels, int32_t points, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!value || !spatial_shapes || !level_start_index || !loc || !attw || !grad_out || !grad_value || !grad_loc ||
+      !grad_attw)
+    return set_error(-1, "b2u_msda_backward_f32: null pointer");
+  if (B <= 0 || S <= 0 || Lq <= 0 || heads <= 0 || dh <= 0 || levels <= 0 || points <= 0)
+    return set_error(-1, "b2u_msda_backward_f32: non-positive dimension");
+  cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * static_cast<size_t>(B) * S * heads * dh, stream);
+  if (e != cudaSuccess) return set_error(-2, "b2u_msda_backward_f32: memset: %s", cudaGetErrorString(e));
+  const long long warps = static_cast<long long>(B) * Lq * heads;
+  msda_bwd_f32_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+      value, spatial_shapes, level_start_index, loc, attw, grad_out, grad_value, grad_loc, grad_attw, B, S, Lq, heads,
+      dh, levels, points);
+  return check_launch("msda_backward_f32");
+}
 
 }  // namespace b2u

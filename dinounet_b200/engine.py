@@ -521,6 +521,12 @@ class ForwardEngine:
             raise ValueError("expected [B, 3, S, S]")
         plan, bufs = self.get_plan(B, S)
         bufs["x"].copy_(x, non_blocking=True)
+        return self.run_resident(B, S, use_graph)
+
+    def run_resident(self, B: int, S: int, use_graph: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Runs the (B, S) plan on whatever `get_plan(B, S)[1]["x"]` holds (a producer kernel, e.g. the sliding-window
+        tile gather, wrote the batch there on the current stream)."""
+        plan, bufs = self.get_plan(B, S)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if use_graph:
             key = (B, S)

@@ -71,6 +71,10 @@ SIGNATURES = {
     "b2u_dwconv3x3": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_msda_forward": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_msda_forward_f32": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "b2u_sw_gather_tiles": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "b2u_sw_accumulate": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "b2u_sw_finalize": [vp, vp, i32, i64, vp, vp],
+    "b2u_msda_backward_f32": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_tail_fuse": [vp, i32, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_in_stats_work_floats": [i32, i32, i32],
     "b2u_in_stats": [vp, i64, vp, vp, i32, i32, i32, i32, vp],

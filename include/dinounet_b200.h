@@ -178,6 +178,32 @@ int b2u_msda_forward_f32(const float* value, const int64_t* spatial_shapes, cons
                          const float* loc, const float* attw, float* out, int32_t B, int32_t S, int32_t Lq,
                          int32_t heads, int32_t dh, int32_t levels, int32_t points, b2u_stream_t stream);
 
+/* Drop-in for the reference pybind op `ms_deform_attn_backward` (ops/src/vision.cpp:19, ms_deform_attn.h:48-67; the one
+ * native kernel the reference's training step runs, ms_deform_attn.py:58-66).  Same inputs as the forward plus
+ * grad_out fp32 [B, Lq, heads*dh]; writes grad_value [B, S, heads, dh] (zeroed here, then accumulated),
+ * grad_loc [B, Lq, heads, levels, points, 2] and grad_attw [B, Lq, heads, levels, points], all fp32, caller-owned.
+ * grad_value is accumulated with fp32 atomics (as in the reference kernel): summation order is not fixed. */
+int b2u_msda_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const float* loc, const float* attw, const float* grad_out, float* grad_value,
+                          float* grad_loc, float* grad_attw, int32_t B, int32_t S, int32_t Lq, int32_t heads,
+                          int32_t dh, int32_t levels, int32_t points, b2u_stream_t stream);
+
+/* ---- Sliding-window prediction (inference/predict_from_raw_data.py:537-621, sliding_window_prediction.py:11-56).
+ * tile_desc: DEVICE int32 [n_entries][4] = (slice d, y0, x0, flip bits: 1 = rows / tensor dim 2, 2 = cols / dim 3).
+ * b2u_sw_gather_tiles: volume fp32 [Cin, D, H, W] -> batch fp32 [n_entries, 3, th, tw]; crops, mirrors and applies the
+ *   1/2/>3 -> 3 channel rule of DINOv3EncoderAdapter.forward (dinounet_training.py:491-497).
+ * b2u_sw_accumulate: one tile whose mirror variants are logits[first .. first+nvar) (fp32 [n, C, th, tw], variant 0
+ *   unflipped, nvar in {1,2,4}): un-mirror, mean over variants, * gaussian (fp16 [th, tw], NULL = 1), accumulate into
+ *   acc fp16 [C, D, H, W] and npred fp16 [D, H, W] with the reference's fp16 rounding sequence (:545-551, :598-599).
+ *   Launches for overlapping tiles must be stream-ordered.
+ * b2u_sw_finalize: acc /= npred (:601); *inf_flag |= 1 if any result is inf (:603-606 raises). */
+int b2u_sw_gather_tiles(const float* volume, float* batch, const int32_t* tile_desc, int32_t n_entries, int32_t Cin,
+                        int32_t D, int32_t H, int32_t W, int32_t th, int32_t tw, b2u_stream_t stream);
+int b2u_sw_accumulate(const float* logits, const int32_t* tile_desc, int32_t first, int32_t nvar, const void* gaussian,
+                      void* acc, void* npred, int32_t C, int32_t D, int32_t H, int32_t W, int32_t th, int32_t tw,
+                      b2u_stream_t stream);
+int b2u_sw_finalize(void* acc, const void* npred, int32_t C, int64_t plane, int32_t* inf_flag, b2u_stream_t stream);
+
 /* Adapter tail (dinov3_adapter.py:467-482): out[b,y,x,:] = BN_eval( base[b,y,x,:] + bilinear(tap[b,:,:,:] -> HxW) ).
  * base: fp32 token stream slice or 16-bit image (base_fp32), tap fp32 [B, Ht*Wt, D] (token-major), align_corners=False. */
 int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_batch_stride, const float* tap, void* out,

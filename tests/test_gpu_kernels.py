@@ -436,6 +436,53 @@ def test_msda_f32_dropin_reference_fixture():
     assert (out - ref).abs().max() < 1e-6
 
 
+def _msda_case(N_, M_, D_, Lq_, shapes_list, P_, seed):
+    shapes = torch.as_tensor(shapes_list, dtype=torch.long, device=DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S_ = int(shapes.prod(1).sum())
+    L_ = len(shapes_list)
+    g = torch.Generator().manual_seed(seed)
+    value = (torch.rand(N_, S_, M_, D_, generator=g) * 0.01).to(DEV)
+    loc = (torch.rand(N_, Lq_, M_, L_, P_, 2, generator=g) * 1.3 - 0.15).to(DEV)   # some samples leave the map
+    aw = torch.rand(N_, Lq_, M_, L_, P_, generator=g).to(DEV) + 1e-5
+    aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).contiguous()
+    gout = torch.randn(N_, Lq_, M_ * D_, generator=g).to(DEV)
+    return value, shapes, lsi, loc, aw, gout
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_msda_backward_dropin_reference_fixture(channels):
+    """ops/test.py:89-121 (`check_gradient_numerical`, its first four channel counts) restated: the op's gradients
+    against autograd through the grid_sample formulation, evaluated in fp64 on the CPU."""
+    from dinounet_b200 import ops
+    value, shapes, lsi, loc, aw, gout = _msda_case(1, 2, channels, 2, [(6, 4), (3, 2)], 2, 3)
+    gv, gl, ga = ops.ms_deform_attn_backward(value, shapes, lsi, loc, aw, gout, 2)
+    v64, l64, a64 = (t.double().cpu().requires_grad_(True) for t in (value, loc, aw))
+    O.msda_core(v64, [(6, 4), (3, 2)], l64, a64).backward(gout.double().cpu())
+    for got, want in ((gv, v64.grad), (gl, l64.grad), (ga, a64.grad)):
+        assert got.shape == want.shape
+        assert rel_err(got.cpu().double(), want) < 1e-5, rel_err(got.cpu().double(), want)
+
+
+def test_msda_backward_engine_shape_and_autograd_function():
+    """dinounet_l's extractor shape (16 heads x 32, one 32x32 level, 4 points, Lq=5376) through the autograd face."""
+    from dinounet_b200 import ops
+    value, shapes, lsi, loc, aw, gout = _msda_case(2, 16, 32, 5376, [(32, 32)], 4, 11)
+    v, l, a = (t.clone().requires_grad_(True) for t in (value, loc, aw))
+    out = ops.MSDeformAttnFunction.apply(v, shapes, lsi, l, a, 64)
+    out.backward(gout)
+    v2, l2, a2 = (t.clone().requires_grad_(True) for t in (value, loc, aw))
+    ref = O.msda_core(v2, [(32, 32)], l2, a2)
+    ref.backward(gout)
+    assert rel_err(out, ref) < 1e-5
+    for got, want in ((v.grad, v2.grad), (l.grad, l2.grad), (a.grad, a2.grad)):
+        assert rel_err(got, want) < 2e-5, rel_err(got, want)
+    with pytest.raises(RuntimeError):
+        ops.ms_deform_attn_backward(value.cpu(), shapes, lsi, loc, aw, gout, 64)
+    with pytest.raises(RuntimeError):
+        ops.ms_deform_attn_forward(value.transpose(1, 2), shapes, lsi, loc, aw, 64)
+
+
 def test_instancenorm_film_se_seg():
     lib = L.load()
     B, rows, Cc = 2, 4096, 32

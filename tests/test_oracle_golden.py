@@ -13,7 +13,7 @@ from oracle import dinounet_oracle as O
 
 def _cases(golden_dir):
     out = []
-    for f in sorted(glob.glob(os.path.join(golden_dir, "*.npz"))):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "dinounet_*.npz"))):
         m, b, s, w, x = os.path.basename(f)[:-4].rsplit("_", 4)
         out.append((f, m, int(b[1:]), int(s[1:]), int(w[1:]), int(x[1:])))
     return out
