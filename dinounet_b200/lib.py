@@ -122,6 +122,6 @@ def launch_count() -> int:
     return int(load().b2u_launch_count())
 
 
-def check(rc: int, what: str):
+def check(rc: int, what: str = "native call"):
     if rc != 0:
         raise NativeLibraryError(f"{what} failed (rc={rc}): {last_error()}")

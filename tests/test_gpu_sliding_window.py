@@ -88,9 +88,13 @@ def test_kernels_gather_and_accumulate_against_torch():
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
     npred.clamp_(min=0.5)
     rn.clamp_(min=0.5)
+    a2, n2 = acc.clone(), npred.clone()
     L.check(lib.b2u_sw_finalize(acc.data_ptr(), npred.data_ptr(), C, D * H * W, flag.data_ptr(), st))
     racc /= rn
-    assert torch.equal(acc, racc) and int(flag.item()) == int(torch.isinf(racc).any())
+    assert torch.equal(acc, racc) and int(flag.item()) == 0 and not torch.isinf(racc).any()
+    a2[1, 1, 7, 9], n2[1, 7, 9] = 60000.0, 0.5          # 120000 is not representable in fp16
+    L.check(lib.b2u_sw_finalize(a2.data_ptr(), n2.data_ptr(), C, D * H * W, flag.data_ptr(), st))
+    assert int(flag.item()) == 1 and torch.isinf(a2[1, 1, 7, 9])
 
 
 @pytest.mark.parametrize("shape,patch,step,gaussian,mirror,tile_batch", [
@@ -120,5 +124,10 @@ def test_predictor_512_tiles_and_inf_error():
     assert torch.equal(got, want)
     with pytest.raises(AssertionError):
         p.predict_sliding_window_return_logits(x[0])
+    # fp16 accumulator overflow -> the reference's RuntimeError (predict_from_raw_data.py:603-606)
+    sd = O.make_state_dict("dinounet_s", 2, seed=0)
+    sd["decoder.seg_layers.2.weight"] = sd["decoder.seg_layers.2.weight"] * 1e5
+    net.load_state_dict(sd, strict=True)
+    net.repack()
     with pytest.raises(RuntimeError, match="Encountered inf"):
-        p.predict_sliding_window_return_logits(x * float("inf"))
+        p.predict_sliding_window_return_logits(x[:, :, :512, :512])
