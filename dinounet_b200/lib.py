@@ -74,6 +74,9 @@ SIGNATURES = {
     "b2u_sw_gather_tiles": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_sw_accumulate": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "b2u_sw_finalize": [vp, vp, i32, i64, vp, vp],
+    "b2u_dice_ce_work_doubles": [i32, i32, i64],
+    "b2u_dice_ce_forward": [vp, vp, i32, vp, vp, vp, vp, i32, i32, i64, f32, f32, i32, i32, f32, vp],
+    "b2u_dice_ce_backward": [vp, vp, i32, vp, vp, i32, i32, i64, f32, f32, i32, i32, f32, f32, vp],
     "b2u_msda_backward_f32": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_tail_fuse": [vp, i32, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "b2u_in_stats_work_floats": [i32, i32, i32],
@@ -89,7 +92,8 @@ SIGNATURES = {
     "b2u_version": [],
     "b2u_launch_count": [],
 }
-_RESTYPES = {"b2u_last_error": C.c_char_p, "b2u_launch_count": C.c_int64, "b2u_in_stats_work_floats": C.c_int64}
+_RESTYPES = {"b2u_last_error": C.c_char_p, "b2u_launch_count": C.c_int64, "b2u_in_stats_work_floats": C.c_int64,
+             "b2u_dice_ce_work_doubles": C.c_int64}
 
 _lib: Optional[C.CDLL] = None
 

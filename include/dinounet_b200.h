@@ -204,6 +204,26 @@ int b2u_sw_accumulate(const float* logits, const int32_t* tile_desc, int32_t fir
                       b2u_stream_t stream);
 int b2u_sw_finalize(void* acc, const void* npred, int32_t C, int64_t plane, int32_t* inf_flag, b2u_stream_t stream);
 
+/* ---- Dice + cross-entropy loss and online-validation statistics on the logits of the forward path
+ * (training/loss/compound_losses.py:31-56 `DC_and_CE_loss`, dice.py:72-119 `MemoryEfficientSoftDiceLoss`,
+ * robust_ce_loss.py:12-16, built at nnUNetTrainer.py:363-365; consumer nnUNetTrainer.py:961-1005 `validation_step`).
+ * logits fp32 [B, C, plane] (plane = H*W); target [B, plane] labels, target_kind 0 = uint8, 1 = int32, 2 = int64,
+ * 3 = float32 (nnU-Net hands float label maps).  work: caller-owned, b2u_dice_ce_work_doubles(B, C, plane) doubles.
+ * forward: out3[0] = weight_ce*CE + weight_dice*dice, out3[1] = CE (mean over all pixels), out3[2] = dice term
+ *   (-mean_c (2*sum(p*y)+smooth)/max(sum(y)+sum(p)+smooth, 1e-8); over the batch if batch_dice, background class skipped
+ *   unless do_bg);  tp_fp_fn (optional) int64 [3][C] = hard tp / fp / fn of argmax(logits) vs target, summed over the
+ *   batch (get_tp_fp_fn_tn with axes (0,2,3), nnUNetTrainer.py:971-991);  *bad_label is set to 1 if a label is outside
+ *   [0, C) (torch raises a device assert there).  Deterministic (fixed reduction order, fp64 partials).
+ * backward: grad_logits fp32 [B, C, plane] = grad_scale * dLoss/dlogits, from the sums the forward left in `work`.
+ * ignore_label / region (BCE) training are not covered. */
+int64_t b2u_dice_ce_work_doubles(int32_t B, int32_t C, int64_t plane);
+int b2u_dice_ce_forward(const float* logits, const void* target, int32_t target_kind, double* work, float* out3,
+                        int64_t* tp_fp_fn, int32_t* bad_label, int32_t B, int32_t C, int64_t plane, float weight_ce,
+                        float weight_dice, int32_t batch_dice, int32_t do_bg, float smooth, b2u_stream_t stream);
+int b2u_dice_ce_backward(const float* logits, const void* target, int32_t target_kind, const double* work,
+                         float* grad_logits, int32_t B, int32_t C, int64_t plane, float weight_ce, float weight_dice,
+                         int32_t batch_dice, int32_t do_bg, float smooth, float grad_scale, b2u_stream_t stream);
+
 /* Adapter tail (dinov3_adapter.py:467-482): out[b,y,x,:] = BN_eval( base[b,y,x,:] + bilinear(tap[b,:,:,:] -> HxW) ).
  * base: fp32 token stream slice or 16-bit image (base_fp32), tap fp32 [B, Ht*Wt, D] (token-major), align_corners=False. */
 int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_batch_stride, const float* tap, void* out,
