@@ -35,6 +35,7 @@ struct GemmArgs {
   int npad;  // > 0: V is written transposed as V^T [B, heads, 64, npad]
   int rope_h, rope_w;  // > 0: separable rope tables staged in smem
   int halo_stages;  // conv == 3 (halo-reuse 3x3 mode)
+  int pair;         // 1: CTA-pair (tcgen05 cta_group::2) kernel, W map box holds BLOCK_N / 2 rows
 };
 
 int num_sms();

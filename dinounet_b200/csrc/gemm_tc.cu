@@ -364,8 +364,10 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
     a.M = p->M;
     a.num_kb = (p->K + BK - 1) / BK;
     m_tiles = (static_cast<long long>(p->M) + BM - 1) / BM;
+    // CTA pairs (cta_group::2) for the 256-wide tiles of plain GEMMs (option 3 = 1 disables, for A/B runs)
+    a.pair = (v2 && bn == 256 && m_tiles >= 2 && get_option(3) != 1) ? 1 : 0;
     if ((rc = make_map_2d(&maps.a[0], p->A, p->M, p->K, p->lda, BM, p->dtype))) return rc;
-    if ((rc = make_map_2d(&maps.b, p->Wp, p->N, p->K, p->ldw, bn, p->dtype))) return rc;
+    if ((rc = make_map_2d(&maps.b, p->Wp, p->N, p->K, p->ldw, a.pair ? bn / 2 : bn, p->dtype))) return rc;
   } else {
     const int stride = p->conv == B2U_CONV3X3_S2 ? 2 : 1;
     if (p->C % 8) return set_error(-1, "b2u_gemm(conv): C must be a multiple of 8");
@@ -449,9 +451,10 @@ extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   }
   if (a.npad && (a.npad % 8 || a.npad < p->ntok)) return set_error(-1, "b2u_qkv_rope: bad npad");
   int rc;
-  if ((rc = make_map_2d(&maps.a[0], p->A, a.M, p->D, p->lda, BM, p->dtype))) return rc;
-  if ((rc = make_map_2d(&maps.b, p->Wp, a.N, p->D, p->ldw, bn, p->dtype))) return rc;
   a.m_tiles = static_cast<int>((static_cast<long long>(a.M) + BM - 1) / BM);
+  a.pair = (v2 && bn == 256 && a.m_tiles >= 2 && get_option(3) != 1) ? 1 : 0;
+  if ((rc = make_map_2d(&maps.a[0], p->A, a.M, p->D, p->lda, BM, p->dtype))) return rc;
+  if ((rc = make_map_2d(&maps.b, p->Wp, a.N, p->D, p->ldw, a.pair ? bn / 2 : bn, p->dtype))) return rc;
   if (a.npad && !v2) return set_error(-1, "b2u_qkv_rope: V^T output needs the v2 GEMM kernel");
   return run_gemm(true, bn, p->dtype, maps, a, stream);
 }

@@ -24,11 +24,15 @@ constexpr int kHaloStageBytes = 49 * 1024;             // box rounded up to the 
 
 constexpr int kRopeBytes = 128 * 32 * 2 * 4;   // (rope_h + rope_w <= 128) rows x <=32 angles x {sin, cos} fp32
 
-template <int BN, int EPI = 0> struct Cfg2 {
-  // the QKV variant trades one pipeline stage for the in-smem rope tables
-  static constexpr int kStages = (BN == 256) ? (EPI == 2 ? 3 : 4) : (BN == 128 ? (EPI == 2 ? 5 : 6) : 8);
+// PAIR: two CTAs of a cluster form one tcgen05 cta_group::2 unit: a 256 x BN output tile, each CTA stages its own 128
+// rows of A and HALF of the W tile (BN/2 rows), so a stage is A 16 KB + W 16 KB (BN 256) instead of 16 + 32 KB: 1.5x less
+// L2 -> SM traffic per flop and a 1.5x deeper TMA ring in the same shared memory.
+template <int BN, int EPI = 0, bool PAIR = false> struct Cfg2 {
+  // the QKV variant trades pipeline stages for the in-smem rope tables
+  static constexpr int kStages = PAIR ? ((BN == 256) ? (EPI == 2 ? 5 : 6) : 8)
+                                      : ((BN == 256) ? (EPI == 2 ? 3 : 4) : (BN == 128 ? (EPI == 2 ? 5 : 6) : 8));
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 8 * 4096;        // 8 epilogue warps x (32 rows x 128 B)
   static constexpr int kBiasBytes = BN * 4;
@@ -95,9 +99,9 @@ __device__ __forceinline__ void act_vec(float (&f)[NV]) {
 
 // EPI: 0 = generic 16-bit out, 1 = generic fp32 out, 2 = QKV(+RoPE, head split), 3 = SwiGLU (silu(x1)*x2).  ACT1 / ACT2: compile-time activations
 // after the bias / after the affine (B2U_ACT_*), so the fully unrolled epilogue stays small enough for the I-cache.
-template <int BN, int EPI, int ACT1, int ACT2, typename T>
+template <int BN, int EPI, int ACT1, int ACT2, typename T, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
-  using C = Cfg2<BN, EPI>;
+  using C = Cfg2<BN, EPI, PAIR>;
   using TT = T16<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -119,17 +123,26 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long total_tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
+  // PAIR: the cluster (CTA pair) is the scheduling unit; tile = (pair of m-tiles, n-tile); this CTA owns m-tile 2*mp + rank
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit_id = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_cnt = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const long long total_tiles = PAIR ? static_cast<long long>((args.m_tiles + 1) / 2) * args.n_tiles
+                                     : static_cast<long long>(args.m_tiles) * args.n_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < 8; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(w_bar, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 16 : 8); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / multicast commit
+  if (warp == 1) {
+    if constexpr (PAIR) { tmem_alloc2(tmem_slot, C::kTmemCols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, C::kTmemCols); tmem_relinquish(); }
+  }
   if constexpr (EPI == 2) {
     if (args.rope_w > 0) {
       // rows 0..h-1: the hq angles that depend on the patch row (table columns 0..hq-1 of patch (py, 0));
@@ -160,9 +173,23 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         mbar_expect_tx(w_bar, 9 * C::kBBytes);
         for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_wtaps + tap * C::kBBytes, &maps.b, w_bar, tap * BK, 0);
       }
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t full0 = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0u;   // the leader CTA's full barriers
+      for (long long tile = unit_id; tile < total_tiles; tile += unit_cnt) {
         const int nt = static_cast<int>(tile % args.n_tiles);
-        const int mt = static_cast<int>(tile / args.n_tiles);
+        const int mt = PAIR ? 2 * static_cast<int>(tile / args.n_tiles) + static_cast<int>(cta_rank)
+                            : static_cast<int>(tile / args.n_tiles);
+        if constexpr (PAIR) {
+          // both CTAs post their bytes on the LEADER's full barrier; only the leader arms it (for both halves)
+          for (int kb = 0; kb < args.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * C::kStageBytes;
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            tma_load_2d_pair(sA, &maps.a[0], full0 + stage * 8, kb * BK, mt * BM);
+            tma_load_2d_pair(sA + C::kABytes, &maps.b, full0 + stage * 8, kb * BK, nt * BN + static_cast<int>(cta_rank) * (BN / 2));
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         int img = 0, y0 = 0, x0 = 0;
         if (args.conv) {
           const int per_img = args.tiles_x * args.tiles_y;
@@ -205,16 +232,32 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(TT::kFmt, BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(TT::kFmt, PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (long long tile = unit_id; tile < total_tiles; tile += unit_cnt, ++it) {
         const int buf = it & 1;
         mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
+        if constexpr (PAIR) {
+          for (int kb = 0; kb < args.num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sA = smem_u32(smem + stage * C::kStageBytes);
+            const uint64_t da = make_desc_k128(sA);
+            const uint64_t db = make_desc_k128(sA + C::kABytes);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_f16_pair(tacc, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_pair(&empty_bar[stage], 3);      // frees the stage in BOTH CTAs
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          tc_commit_pair(&tfull_bar[buf], 3);          // both CTAs' epilogues drain their 128 rows
+          continue;
+        }
         if (halo) {
           if (it == 0) { mbar_wait(w_bar, 0); }
           mbar_wait(&full_bar[stage], phase);
@@ -263,10 +306,12 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     const b2u_epilogue& e = args.epi;
     const int etid = threadIdx.x - 64;               // 0..127 among epilogue threads
     int it = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const uint32_t tempty0 = PAIR ? mapa_u32(smem_u32(tempty_bar), 0) : 0u;   // the leader CTA's "accumulator drained" barriers
+    for (long long tile = unit_id; tile < total_tiles; tile += unit_cnt, ++it) {
       const int buf = it & 1;
       const int nt = static_cast<int>(tile % args.n_tiles);
-      const int mt = static_cast<int>(tile / args.n_tiles);
+      const int mt = PAIR ? 2 * static_cast<int>(tile / args.n_tiles) + static_cast<int>(cta_rank)
+                          : static_cast<int>(tile / args.n_tiles);
       const int n0 = nt * BN;
       int img = 0, y0 = 0, x0 = 0;
       if (args.conv) {
@@ -611,20 +656,58 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       // this warp is done reading accumulator buffer `buf`
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(tempty0 + buf * 8);
+        else mbar_arrive(&tempty_bar[buf]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // nobody leaves while the peer can still touch its smem / barriers / TMEM
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 template <int BN, int EPI, int ACT1, int ACT2, typename T>
+static int launch_pair2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  auto kern = gemm_tc2_kernel<BN, EPI, ACT1, ACT2, T, true>;
+  static bool configured = false;
+  constexpr int kSmem = Cfg2<BN, EPI, true>::kSmem;
+  static_assert(kSmem <= 227 * 1024, "pair variant exceeds the shared memory of an SM");
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(gemm_tc2 pair): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long tiles = static_cast<long long>((args.m_tiles + 1) / 2) * args.n_tiles;
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * static_cast<unsigned>(tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, args);
+  if (e != cudaSuccess) return set_error(-2, "gemm_tc2 pair launch: %s", cudaGetErrorString(e));
+  return check_launch("gemm_tc2_pair");
+}
+
+template <int BN, int EPI, int ACT1, int ACT2, typename T>
 static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
+  if constexpr (BN == 256) {
+    if (args.pair) return launch_pair2<BN, EPI, ACT1, ACT2, T>(maps, args, stream);
+  }
   auto kern = gemm_tc2_kernel<BN, EPI, ACT1, ACT2, T>;
   static bool configured = false;
   constexpr int kMaxSmem = (BN <= 64 && Cfg2<BN, EPI>::kSmemHalo > Cfg2<BN, EPI>::kSmem) ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem;

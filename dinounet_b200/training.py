@@ -8,9 +8,11 @@ works unchanged; otherwise they derive from `object` (the hook itself is a stati
 """
 from typing import List, Tuple, Union
 
+import torch
 from torch import nn
 
 from . import config as cfg
+from .loss import DC_and_CE_loss, validation_statistics
 from .network_architecture import DinoUNet
 
 try:  # the reference package (needs batchgenerators etc.); optional
@@ -51,6 +53,29 @@ class DinoUNetTrainer(_Base):
                                     num_classes=num_output_channels,
                                     dinov3_pretrained_path=DinoUNetTrainer._dinov3_pretrained_path,
                                     dinov3_model_name=DinoUNetTrainer._dinov3_model_name)
+
+
+    # ---- forward-only callers of the path that the trainer owns (nnUNetTrainer.py:355-365, :945-1005)
+    def _build_loss(self):
+        """Label-map training: Dice (batch_dice from the plans, smooth 1e-5, no background) + CE, weights 1:1 — the
+        fused B200 loss.  No deep-supervision wrapper (the trainer derives from nnUNetTrainerNoDeepSupervision)."""
+        if self.label_manager.has_regions:
+            raise NotImplementedError("region-based (sigmoid/BCE) training is not covered by the fused B200 loss")
+        return DC_and_CE_loss({"batch_dice": self.configuration_manager.batch_dice, "smooth": 1e-5, "do_bg": False,
+                               "ddp": self.is_ddp}, {}, weight_ce=1, weight_dice=1,
+                              ignore_label=self.label_manager.ignore_label)
+
+    def validation_step(self, batch: dict) -> dict:
+        """One online-validation batch: B200 forward, then loss + hard tp/fp/fn in one fused pass over the logits."""
+        data = batch["data"].to(self.device, non_blocking=True)
+        target = batch["target"]
+        if isinstance(target, list):
+            target = target[0]
+        target = target.to(self.device, non_blocking=True)
+        with torch.no_grad():
+            output = self.network(data)
+        del data
+        return validation_statistics(self.loss, output, target)
 
 
 class DinoUNetTrainer_s(DinoUNetTrainer):

@@ -267,7 +267,9 @@ int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream);
 /* key 1 (B2U_OPT_MSDA_IMPL): 0 = shared-memory value-slab gather (default), 1 = first-generation warp-per-query kernel. */
 /* key 2 (B2U_OPT_CONV_HALO): 0 = 3x3 convs with <= 64 in/out channels and >= 128-px rows use the halo-reuse mode
  * (default), 1 = always the per-tap TMA walk. */
-enum { B2U_OPT_GEMM_IMPL = 0, B2U_OPT_MSDA_IMPL = 1, B2U_OPT_CONV_HALO = 2 };
+/* key 3 (B2U_OPT_GEMM_PAIR): 0 = plain GEMMs with 256-wide tiles run on CTA pairs (tcgen05 cta_group::2, 256 x 256
+ * tile per pair, each CTA stages half of the weight tile) (default), 1 = one CTA per tile. */
+enum { B2U_OPT_GEMM_IMPL = 0, B2U_OPT_MSDA_IMPL = 1, B2U_OPT_CONV_HALO = 2, B2U_OPT_GEMM_PAIR = 3 };
 int b2u_set_option(int32_t key, int32_t value);
 
 const char* b2u_last_error(void);

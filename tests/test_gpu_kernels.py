@@ -44,6 +44,34 @@ def test_gemm_plain(gemm_impl, dtype, M, N, K):
     assert rel_err(out, ref) < tol, rel_err(out, ref)
 
 
+@pytest.mark.parametrize("dtype", [L.BF16, L.F16])
+@pytest.mark.parametrize("M,N,K", [(2058, 1024, 256), (257, 512, 128), (768, 256, 64), (128, 256, 64), (8232, 4096, 1024),
+                                   (5000, 768, 320)])
+def test_gemm_cta_pair_equals_single_cta_bitwise(dtype, M, N, K):
+    """256-wide tiles run on CTA pairs (tcgen05 cta_group::2; B2U_OPT_GEMM_PAIR=0): same products, same K order -> the
+    result must equal the one-CTA-per-tile kernel bit for bit (odd m-tile counts, M/N/K tails, M < 256 -> no pairing)."""
+    lib = L.load()
+    td = TD[dtype]
+    A, W = _rand(M, K, dt=td), _rand(N, K, dt=td, scale=K ** -0.5, seed=1)
+    bias = _rand(N, seed=2)
+    res = _rand(M, N, seed=3)
+    outs = {}
+    for pair_off in (0, 1):
+        lib.b2u_set_option(3, pair_off)
+        try:
+            o16 = torch.full((M, N), float("nan"), device=DEV, dtype=td)
+            gemm(A, W, o16, dtype, bias=bias, act1=L.ACT_GELU)
+            o32 = res.clone()
+            gemm(A, W, o32, dtype, out_fp32=True, bias=bias, scale=bias, residual=o32, ldres=N)
+            torch.cuda.synchronize()
+        finally:
+            lib.b2u_set_option(3, 0)
+        outs[pair_off] = (o16, o32)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = F.gelu((A.float() @ W.float().t() + bias).to(td).float())
+    assert rel_err(outs[0][0], ref) < (2 ** -6 if dtype == L.BF16 else 2 ** -9)
+
+
 def test_gemm_epilogue_residual_scale_gelu_fp32out(gemm_impl):
     M, N, K = 1029 * 2, 384, 1536
     dtype, td = L.BF16, torch.bfloat16

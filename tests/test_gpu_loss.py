@@ -66,3 +66,31 @@ def test_validation_statistics_match_reference_step():
     bad[0, 0, 0, 0] = 3
     with pytest.raises(RuntimeError):
         validation_statistics(mod, z, bad)
+
+
+def test_trainer_validation_step_on_the_b200_forward():
+    """`DinoUNetTrainer.validation_step` (forward + fused statistics) against the oracle applied to the same logits."""
+    import os
+    from types import SimpleNamespace
+    import dinounet_b200
+    from dinounet_b200 import config
+    from oracle import dinounet_oracle as O
+    os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
+    net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, "dinounet_s")
+    net.load_state_dict(O.make_state_dict("dinounet_s", 2, seed=0), strict=True)
+    net = net.to(DEV).eval()
+    tr = dinounet_b200.DinoUNetTrainer_s.__new__(dinounet_b200.DinoUNetTrainer_s)
+    tr.device, tr.network, tr.is_ddp = DEV, net, False
+    tr.label_manager = SimpleNamespace(has_regions=False, ignore_label=None, has_ignore_label=False)
+    tr.configuration_manager = SimpleNamespace(batch_dice=True)
+    tr.loss = tr._build_loss()
+    g = torch.Generator().manual_seed(5)
+    batch = {"data": torch.randn(2, 3, 256, 256, generator=g), "target": torch.randint(0, 2, (2, 1, 256, 256), generator=g).float()}
+    out = tr.validation_step(batch)
+    with torch.no_grad():
+        logits = net(batch["data"].to(DEV))
+    want, _, _ = LO.dc_and_ce_loss(logits.double(), batch["target"].to(DEV))
+    tp, fp, fn = LO.validation_hard_counts(logits, batch["target"].to(DEV))
+    assert abs(float(out["loss"]) - float(want)) < 2e-6 * max(1.0, abs(float(want)))
+    assert np.array_equal(out["tp_hard"], tp.cpu().numpy()[1:]) and np.array_equal(out["fn_hard"], fn.cpu().numpy()[1:])
+    assert np.array_equal(out["fp_hard"], fp.cpu().numpy()[1:])
