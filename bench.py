@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--gemm-impl", default="v2", choices=["v1", "v2"])
     ap.add_argument("--attn-impl", default="tc", choices=["tc", "mma"])
+    ap.add_argument("--gemm-pair", default="on", choices=["on", "off"], help="CTA-pair (cta_group::2) GEMM tiles (A/B switch)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="patches in the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--ops-out", default="", help="write the per-kernel timing breakdown (JSON) here")
     return ap.parse_args()
@@ -188,6 +189,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib.load().b2u_set_option(0, 1 if a.gemm_impl == "v1" else 0)
+    lib.load().b2u_set_option(3, 1 if a.gemm_pair == "off" else 0)
 
     B, S, K, W = a.batch, a.size, a.steps, max(3, a.warmup)
     sd = O.make_state_dict(a.model, 2, seed=0)

@@ -70,16 +70,26 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): branch-free, 2 MUFU + ~10 FMA (erff() is ~2x that)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): branch-free, 2 MUFU + 11 FMA-pipe instructions.  Constants
+// are folded (z = |x|/sqrt2 never materialises) and exp goes straight to ex2.approx.ftz: __expf() wraps it in a
+// compare / pre-scale / square sequence for arguments below -126 that costs 3 more instructions per element, and an
+// underflow to zero is exactly what erf -> 1 wants here.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float er = 1.0f - p * t * __expf(-ax * ax);   // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(er, x));
+  const float e = ex2_approx((x * x) * (-0.5f * 1.4426950408889634f));   // exp(-x^2/2)
+  const float er = fmaf(-(p * t), e, 1.0f);                                // erf(|x|/sqrt2)
+  const float h = 0.5f * x;
+  return fmaf(h, copysignf(er, x), h);
 }
 
 template <int ACT, int NV>
@@ -343,8 +353,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         // phase-1 owner row
         long long m1;
         const bool v1 = row_of(q4 * 32 + lane, m1);
-        const int b1 = static_cast<int>(m1 / args.ntok);
-        const int t1 = static_cast<int>(m1 - static_cast<long long>(b1) * args.ntok);
+        const unsigned ntok_u = static_cast<unsigned>(args.ntok);   // token rows fit 32 bits (host-checked): 32-bit divides
+        const int b1 = static_cast<int>(static_cast<unsigned>(m1) / ntok_u);
+        const int t1 = static_cast<int>(static_cast<unsigned>(m1) - static_cast<unsigned>(b1) * ntok_u);
         const bool rot = v1 && t1 >= args.prefix;
         const float* sinr = args.rope_sin + static_cast<long long>(rot ? t1 - args.prefix : 0) * HDm;
         const float* cosr = args.rope_cos + static_cast<long long>(rot ? t1 - args.prefix : 0) * HDm;
@@ -355,8 +366,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         for (int i = 0; i < 8; ++i) {
           long long m2;
           dst_ok[i] = row_of(q4 * 32 + i * 4 + (lane >> 3), m2);
-          const int b2 = static_cast<int>(m2 / args.ntok);
-          const int t2 = static_cast<int>(m2 - static_cast<long long>(b2) * args.ntok);
+          const int b2 = static_cast<int>(static_cast<unsigned>(m2) / ntok_u);
+          const int t2 = static_cast<int>(static_cast<unsigned>(m2) - static_cast<unsigned>(b2) * ntok_u);
           dst_off[i] = (static_cast<long long>(b2) * args.heads * args.ntok + t2) * HDm;
         }
         mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
@@ -380,9 +391,13 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           const int head = (n - which * args.D) / HDm;
           float x[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x[j] = TT::to_f(TT::from_f(__uint_as_float(v0[j]) + s_bias[hcol + lo_off + j]));
-            x[32 + j] = TT::to_f(TT::from_f(__uint_as_float(v1r[j]) + s_bias[hcol + hi_off + j]));
+          for (int j = 0; j < 32; j += 2) {   // Linear output rounded to 16 bits (packed converts: F2FP, not the slow F2F)
+            const float2 lo = TT::unpack2(TT::pack2(__uint_as_float(v0[j]) + s_bias[hcol + lo_off + j],
+                                                    __uint_as_float(v0[j + 1]) + s_bias[hcol + lo_off + j + 1]));
+            const float2 hi = TT::unpack2(TT::pack2(__uint_as_float(v1r[j]) + s_bias[hcol + hi_off + j],
+                                                    __uint_as_float(v1r[j + 1]) + s_bias[hcol + hi_off + j + 1]));
+            x[j] = lo.x; x[j + 1] = lo.y;
+            x[32 + j] = hi.x; x[33 + j] = hi.y;
           }
           if (which == 2 && args.npad > 0) {
             // V^T [B, heads, head_dim, npad]: lane = token, loop over d -> each store instruction writes 32 consecutive keys
@@ -477,7 +492,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             for (int q = 0; q < 2; ++q) {
               const float a = TT::to_f(TT::from_f(__uint_as_float(v0[j + q]) + s_bias[g * 64 + j + q]));
               const float b = TT::to_f(TT::from_f(__uint_as_float(v1r[j + q]) + s_bias[g * 64 + 32 + j + q]));
-              const float sg = TT::to_f(TT::from_f(a * rcp_approx(1.0f + __expf(-a))));   // silu(a), 16-bit like F.silu
+              const float sg = TT::to_f(TT::from_f(a * rcp_approx(1.0f + ex2_approx(a * -1.4426950408889634f))));   // silu(a), 16-bit like F.silu
               h[q] = sg * b;
             }
             packed[j >> 1] = TT::pack2(h[0], h[1]);
@@ -580,6 +595,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           }
           // per-column parameters of this lane (constant over the rows): loaded before the TMEM wait
           constexpr int NV = o32 ? 4 : 8;
+          const bool affine = e.scale != nullptr || e.shift != nullptr;   // warp-uniform
           float bi[NV], sc[NV], sh[NV];
 #pragma unroll
           for (int j = 0; j < NV; ++j) { bi[j] = 0.f; sc[j] = 1.f; sh[j] = 0.f; }
@@ -607,11 +623,17 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
               float f[4] = {a4.x + bi[0], a4.y + bi[1], a4.z + bi[2], a4.w + bi[3]};
               if (e.round16) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) f[j] = TT::to_f(TT::from_f(f[j]));
+                for (int j = 0; j < 4; j += 2) {
+                  const float2 t = TT::unpack2(TT::pack2(f[j], f[j + 1]));
+                  f[j] = t.x;
+                  f[j + 1] = t.y;
+                }
               }
               act_vec<ACT1, 4>(f);
+              if (affine) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+                for (int j = 0; j < 4; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+              }
               act_vec<ACT2, 4>(f);
               if (e.residual) { f[0] += res[i].x; f[1] += res[i].y; f[2] += res[i].z; f[3] += res[i].w; }
               if (e.add16) {
@@ -630,13 +652,19 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
               const float4 a4 = lds128f(patch_u32 + rr * 128 + ((g0 ^ (rr & 7)) << 4));
               const float4 b4 = lds128f(patch_u32 + rr * 128 + (((g0 + 1) ^ (rr & 7)) << 4));
               float f[8] = {a4.x + bi[0], a4.y + bi[1], a4.z + bi[2], a4.w + bi[3], b4.x + bi[4], b4.y + bi[5], b4.z + bi[6], b4.w + bi[7]};
-              if (e.round16) {
+              if (e.round16) {   // packed convert: one F2FP per two values
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = TT::to_f(TT::from_f(f[j]));
+                for (int j = 0; j < 8; j += 2) {
+                  const float2 t = TT::unpack2(TT::pack2(f[j], f[j + 1]));
+                  f[j] = t.x;
+                  f[j + 1] = t.y;
+                }
               }
               act_vec<ACT1, 8>(f);
+              if (affine) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+              }
               act_vec<ACT2, 8>(f);
               if (e.residual) {
                 f[0] += res[2 * i].x; f[1] += res[2 * i].y; f[2] += res[2 * i].z; f[3] += res[2 * i].w;
