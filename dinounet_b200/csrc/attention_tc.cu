@@ -12,6 +12,8 @@
 // Every MMA operand is K-major SW128 (the layout the GEMM kernel already uses): V is consumed as V^T [B,H,64,npad]
 // (written transposed by the QKV epilogue), so no MN-major descriptors are needed.  TMEM: 2 groups x 2 buffers x 128 = 512 cols.
 // Replaces F.scaled_dot_product_attention at dinounet/dinov3/layers/attention.py:116.
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/dinounet_b200.h"
 #include "host_util.h"
@@ -287,9 +289,13 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
           tc_fence_before();
           mbar_arrive(&x_free[2 * g + ((j - 1) & 1)]);   // buffer (j-1)&1 may now receive S(j+1)
         }
-        // ---- pass 2: P = exp2(s*scale - m) -> 16-bit -> swizzled smem (A operand of the PV MMA)
+        // ---- pass 2: P = exp2(s*scale - m) -> 16-bit -> swizzled smem (A operand of the PV MMA).
+        // Two compiled bodies: only the last key chunk has columns >= ntok to zero; left as a runtime test inside the
+        // element loop the compiler if-converts it into an index add + compare + select PER ELEMENT of every chunk
+        // (30 % of the kernel's instructions).
         float rs = 0.f;
-        {
+        auto pass2 = [&](auto tail_c) {
+          constexpr bool kTail = decltype(tail_c)::value;
           uint32_t va[32], vb[32];
           tmem_ld32(tS, va);
           auto emit = [&](const uint32_t (&v)[32], int pc) {
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
             for (int c = 0; c < 32; c += 2) {
               float a = ex2(fmaf(__uint_as_float(v[c]), args.scale_log2e, -m_new));
               float b = ex2(fmaf(__uint_as_float(v[c + 1]), args.scale_log2e, -m_new));
-              if (tail) {
+              if constexpr (kTail) {
                 if (kbase + pc * 32 + c >= args.ntok) a = 0.f;
                 if (kbase + pc * 32 + c + 1 >= args.ntok) b = 0.f;
               }
@@ -324,7 +330,9 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
           emit(va, 2);
           tmem_ld_wait();
           emit(vb, 3);
-        }
+        };
+        if (tail) pass2(std::true_type{});
+        else pass2(std::false_type{});
         tc_fence_before();                         // all reads of S_g(j) done: PV(j) may overwrite X[j&1][0:HD)
         fence_proxy_async();                       // make the generic-proxy P writes visible to the MMA (async proxy)
         mbar_arrive(&p_full[g]);

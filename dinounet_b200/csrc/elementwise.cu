@@ -697,7 +697,9 @@ extern "C" int b2u_se_apply(const void* t, const void* sc, int64_t ldsc, const f
 }
 
 // ------------------------------------------------------------------------------------------------ seg head
-// thread per pixel: InstanceNorm + LeakyReLU on C (<= 64) channels, 1x1 conv to ncls (<= 8), NCHW fp32 logits, argmax.
+// thread per pixel: InstanceNorm + LeakyReLU on C channels (kept in registers), 1x1 conv to ncls (<= 128) classes in
+// groups of 8 accumulators, NCHW fp32 logits, argmax (first maximum, like torch.argmax).
+constexpr int kSegMaxClasses = 128;
 template <typename T, int C>
 __global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, const float* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -705,7 +707,7 @@ __global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, 
                                                        float* __restrict__ logits, uint8_t* __restrict__ labels,
                                                        int rows, int ncls) {
   __shared__ float s_a[C], s_b[C];       // per-image affine: y = x*a + b
-  __shared__ float s_w[8 * C], s_bias[8];
+  __shared__ float s_w[kSegMaxClasses * C], s_bias[kSegMaxClasses];
   const int b = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += 256) {
     const float mean = sums[(static_cast<long long>(b) * C + c) * 2] / rows;
@@ -715,14 +717,12 @@ __global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, 
     s_b[c] = beta[c] - mean * a;
   }
   for (int i = threadIdx.x; i < ncls * C; i += 256) s_w[i] = w[i];
-  if (threadIdx.x < ncls) s_bias[threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < ncls; i += 256) s_bias[i] = bias[i];
   __syncthreads();
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= rows) return;
   const T* xp = x + (static_cast<long long>(b) * rows + p) * C;
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = k < ncls ? s_bias[k] : -INFINITY;
+  float t[C];
 #pragma unroll
   for (int g = 0; g < C / 8; ++g) {
     Vec8<T> v;
@@ -731,21 +731,29 @@ __global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, 
     v.to_float(f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = f[j] * s_a[g * 8 + j] + s_b[g * 8 + j];
-      t = t > 0.f ? t : 0.01f * t;
-      t = T16<T>::to_f(T16<T>::from_f(t));  // the normalised activation is a 16-bit tensor in the reference regime
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (k < ncls) acc[k] = fmaf(t, s_w[k * C + g * 8 + j], acc[k]);
+      float u = f[j] * s_a[g * 8 + j] + s_b[g * 8 + j];
+      u = u > 0.f ? u : 0.01f * u;
+      t[g * 8 + j] = T16<T>::to_f(T16<T>::from_f(u));  // the normalised activation is a 16-bit tensor in the reference regime
     }
   }
   int best = 0;
-  float bv = acc[0];
+  float bv = -INFINITY;
+  for (int k0 = 0; k0 < ncls; k0 += 8) {   // warp-uniform trip count
+    float acc[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (k < ncls) {
-      logits[(static_cast<long long>(b) * ncls + k) * rows + p] = acc[k];
-      if (acc[k] > bv) { bv = acc[k]; best = k; }
+    for (int k = 0; k < 8; ++k) acc[k] = k0 + k < ncls ? s_bias[k0 + k] : -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k0 + k < ncls) acc[k] = fmaf(t[c], s_w[(k0 + k) * C + c], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k0 + k < ncls) {
+        logits[(static_cast<long long>(b) * ncls + k0 + k) * rows + p] = acc[k];
+        if (acc[k] > bv) { bv = acc[k]; best = k0 + k; }
+      }
     }
   }
   if (labels) labels[static_cast<long long>(b) * rows + p] = static_cast<uint8_t>(best);
@@ -756,7 +764,7 @@ extern "C" int b2u_seg_head(const void* x, const float* sums, const float* gamma
                             int32_t C, int32_t ncls, int32_t dtype, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (C != 32) return set_error(-1, "b2u_seg_head: C must be 32 (plans features_per_stage[0])");
-  if (ncls < 1 || ncls > 8) return set_error(-1, "b2u_seg_head: 1 <= ncls <= 8");
+  if (ncls < 1 || ncls > kSegMaxClasses) return set_error(-1, "b2u_seg_head: 1 <= ncls <= %d", kSegMaxClasses);
   dim3 grid((rows + 255) / 256, B);
   B2U_DISPATCH_T(dtype, (seg_head_kernel<T, 32><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
   return check_launch("seg_head");

@@ -205,16 +205,42 @@ extern "C" int64_t b2u_dice_ce_work_doubles(int32_t B, int32_t C, int64_t plane)
   return static_cast<int64_t>(B) * stats_blocks(plane) * (C * kStat + 1) + static_cast<int64_t>(B) * (C * kStat + 1);
 }
 
+// one instantiation per class count: every per-class sum lives in a named register (large counts spill, which is fine
+// for a pass that is run once per step)
 #define B2U_LOSS_SWITCH(C, BODY)                                                               \
   switch (C) {                                                                                 \
-    case 2: { constexpr int CC = 2; BODY } break;                                              \
-    case 3: { constexpr int CC = 3; BODY } break;                                              \
-    case 4: { constexpr int CC = 4; BODY } break;                                              \
-    case 5: { constexpr int CC = 5; BODY } break;                                              \
-    case 6: { constexpr int CC = 6; BODY } break;                                              \
-    case 8: { constexpr int CC = 8; BODY } break;                                              \
-    case 16: { constexpr int CC = 16; BODY } break;                                            \
-    default: return set_error(-1, "dice_ce: %d classes not in {2,3,4,5,6,8,16}", C);           \
+    case 2: { constexpr int CC = 2; BODY } break;                                        \
+    case 3: { constexpr int CC = 3; BODY } break;                                        \
+    case 4: { constexpr int CC = 4; BODY } break;                                        \
+    case 5: { constexpr int CC = 5; BODY } break;                                        \
+    case 6: { constexpr int CC = 6; BODY } break;                                        \
+    case 7: { constexpr int CC = 7; BODY } break;                                        \
+    case 8: { constexpr int CC = 8; BODY } break;                                        \
+    case 9: { constexpr int CC = 9; BODY } break;                                        \
+    case 10: { constexpr int CC = 10; BODY } break;                                        \
+    case 11: { constexpr int CC = 11; BODY } break;                                        \
+    case 12: { constexpr int CC = 12; BODY } break;                                        \
+    case 13: { constexpr int CC = 13; BODY } break;                                        \
+    case 14: { constexpr int CC = 14; BODY } break;                                        \
+    case 15: { constexpr int CC = 15; BODY } break;                                        \
+    case 16: { constexpr int CC = 16; BODY } break;                                        \
+    case 17: { constexpr int CC = 17; BODY } break;                                        \
+    case 18: { constexpr int CC = 18; BODY } break;                                        \
+    case 19: { constexpr int CC = 19; BODY } break;                                        \
+    case 20: { constexpr int CC = 20; BODY } break;                                        \
+    case 21: { constexpr int CC = 21; BODY } break;                                        \
+    case 22: { constexpr int CC = 22; BODY } break;                                        \
+    case 23: { constexpr int CC = 23; BODY } break;                                        \
+    case 24: { constexpr int CC = 24; BODY } break;                                        \
+    case 25: { constexpr int CC = 25; BODY } break;                                        \
+    case 26: { constexpr int CC = 26; BODY } break;                                        \
+    case 27: { constexpr int CC = 27; BODY } break;                                        \
+    case 28: { constexpr int CC = 28; BODY } break;                                        \
+    case 29: { constexpr int CC = 29; BODY } break;                                        \
+    case 30: { constexpr int CC = 30; BODY } break;                                        \
+    case 31: { constexpr int CC = 31; BODY } break;                                        \
+    case 32: { constexpr int CC = 32; BODY } break;                                        \
+    default: return set_error(-1, "dice_ce: %d classes not in [2, 32]", C);                    \
   }
 
 extern "C" int b2u_dice_ce_forward(const float* logits, const void* target, int32_t target_kind, double* work,

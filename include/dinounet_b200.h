@@ -215,7 +215,7 @@ int b2u_sw_finalize(void* acc, const void* npred, int32_t C, int64_t plane, int3
  *   batch (get_tp_fp_fn_tn with axes (0,2,3), nnUNetTrainer.py:971-991);  *bad_label is set to 1 if a label is outside
  *   [0, C) (torch raises a device assert there).  Deterministic (fixed reduction order, fp64 partials).
  * backward: grad_logits fp32 [B, C, plane] = grad_scale * dLoss/dlogits, from the sums the forward left in `work`.
- * ignore_label / region (BCE) training are not covered. */
+ * 2 <= C <= 32.  ignore_label / region (BCE) training are not covered. */
 int64_t b2u_dice_ce_work_doubles(int32_t B, int32_t C, int64_t plane);
 int b2u_dice_ce_forward(const float* logits, const void* target, int32_t target_kind, double* work, float* out3,
                         int64_t* tp_fp_fn, int32_t* bad_label, int32_t B, int32_t C, int64_t plane, float weight_ce,

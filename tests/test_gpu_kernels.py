@@ -464,6 +464,31 @@ def test_msda_f32_dropin_reference_fixture():
     assert (out - ref).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("ncls", [1, 3, 8, 9, 20, 117, 128])
+def test_seg_head_many_classes(ncls):
+    """1x1 seg conv + argmax for any class count up to 128 (multi-organ label sets), first-maximum argmax."""
+    lib = L.load()
+    B, rows, Cc = 2, 4096, 32
+    x = (_rand(B * rows, Cc, dt=torch.float16, seed=ncls) * 2 + 0.5)
+    sums = torch.empty((B, Cc, 2), device=DEV)
+    work = torch.zeros(int(lib.b2u_in_stats_work_floats(B, rows, Cc)), device=DEV)
+    L.check(lib.b2u_in_stats(P(x), Cc, P(sums), P(work), B, rows, Cc, L.F16, stream()), "stats")
+    g, b = _rand(Cc, seed=1), _rand(Cc, seed=2)
+    w, wb = _rand(ncls, Cc, seed=3), _rand(ncls, seed=4)
+    logits = torch.full((B, ncls, rows), float("nan"), device=DEV)
+    labels = torch.empty(B, rows, device=DEV, dtype=torch.uint8)
+    L.check(lib.b2u_seg_head(P(x), P(sums), P(g), P(b), 1e-5, P(w), P(wb), P(logits), P(labels), B, rows, Cc, ncls, L.F16,
+                             stream()), "seg")
+    torch.cuda.synchronize()
+    xin = x.float().view(B, rows, Cc).transpose(1, 2).reshape(B, Cc, 64, 64)
+    act = F.leaky_relu(F.instance_norm(xin, None, None, g, b, True, 0.1, 1e-5), 0.01).half().float()
+    ref = F.conv2d(act, w.view(ncls, Cc, 1, 1), wb).flatten(2)
+    assert rel_err(logits, ref) < 3e-3
+    assert (labels.long() == logits.argmax(1)).all()
+    assert lib.b2u_seg_head(P(x), P(sums), P(g), P(b), 1e-5, P(w), P(wb), P(logits), P(labels), B, rows, Cc, 129, L.F16,
+                            stream()) != 0
+
+
 def _msda_case(N_, M_, D_, Lq_, shapes_list, P_, seed):
     shapes = torch.as_tensor(shapes_list, dtype=torch.long, device=DEV)
     lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))

@@ -17,7 +17,8 @@ def _case(B, C, H, W, seed, scale=3.0):
     return (torch.randn(B, C, H, W, generator=g) * scale).to(DEV), torch.randint(0, C, (B, 1, H, W), generator=g).to(DEV)
 
 
-@pytest.mark.parametrize("B,C,H,W", [(2, 2, 512, 512), (3, 4, 96, 200), (1, 3, 33, 17), (4, 16, 64, 64), (2, 5, 128, 128)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 2, 512, 512), (3, 4, 96, 200), (1, 3, 33, 17), (4, 16, 64, 64), (2, 5, 128, 128), (2, 7, 64, 96),
+                                     (1, 21, 128, 128), (2, 32, 64, 64)])
 @pytest.mark.parametrize("batch_dice", [True, False])
 def test_loss_and_gradient_match_oracle(B, C, H, W, batch_dice):
     z, t = _case(B, C, H, W, B * 100 + C)

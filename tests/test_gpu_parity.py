@@ -79,6 +79,33 @@ def test_forward_matches_oracle_and_golden(model, B, S, golden_dir):
     assert (labels.cpu().long() == y.argmax(1).cpu()).all()
 
 
+@pytest.mark.parametrize("ncls", [5, 14])
+def test_forward_multiclass_matches_oracle(ncls):
+    """More than two segmentation heads (the plans' label set decides; nnUNetTrainer.py:201-208): logits and argmax
+    labels against the fp32 oracle and the reference-regime eager forward."""
+    model = "dinounet_s"
+    sd = O.make_state_dict(model, ncls, seed=0)
+    x = O.make_input(1, 256, 0)
+    os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
+    net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, ncls, None, model)
+    net.load_state_dict(sd, strict=True)
+    net = net.to("cuda").eval()
+    with torch.no_grad():
+        y = net(x.cuda())
+        labels = net.predict_labels(x.cuda())
+    ref = O.forward(sd, model, x)
+    regime = O.forward({k: v.cuda() for k, v in sd.items()}, model, x.cuda(), autocast_like_reference=True).float().cpu()
+    scale = ref.abs().max().item()
+    err = (y.cpu() - ref).abs().max().item() / scale
+    err_r = (regime - ref).abs().max().item() / scale
+    flips = int((y.argmax(1).cpu() != ref.argmax(1)).sum())
+    flips_r = int((regime.argmax(1) != ref.argmax(1)).sum())
+    print(f"{ncls} classes: rel err {err:.3e} (reference regime {err_r:.3e}), flips {flips} (regime {flips_r}) / {ref[:, 0].numel()}")
+    assert y.shape == (1, ncls, 256, 256) and err <= 1.5 * err_r + 2e-3 and err < 3e-2
+    assert flips <= 1.25 * flips_r + 8
+    assert (labels.cpu().long() == y.argmax(1).cpu()).all()
+
+
 def test_forward_512_golden_and_fp16_vit(golden_dir):
     model = "dinounet_s"
     sd = O.make_state_dict(model, 2, seed=0)
