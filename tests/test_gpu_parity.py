@@ -101,8 +101,13 @@ def test_forward_multiclass_matches_oracle(ncls):
     flips = int((y.argmax(1).cpu() != ref.argmax(1)).sum())
     flips_r = int((regime.argmax(1) != ref.argmax(1)).sum())
     print(f"{ncls} classes: rel err {err:.3e} (reference regime {err_r:.3e}), flips {flips} (regime {flips_r}) / {ref[:, 0].numel()}")
-    assert y.shape == (1, ncls, 256, 256) and err <= 1.5 * err_r + 2e-3 and err < 3e-2
-    assert flips <= 1.25 * flips_r + 8
+    assert y.shape == (1, ncls, 256, 256) and torch.isfinite(y).all() and err < 3e-2
+    if torch.isfinite(regime).all():       # the reference's own fp16 regime overflows on some synthetic weight sets
+        assert err <= 1.5 * err_r + 2e-3 and flips <= 1.25 * flips_r + 8
+    else:
+        margin = ref.topk(2, dim=1).values
+        safe = (margin[:, 0] - margin[:, 1]) > 4 * err * scale
+        assert not ((y.argmax(1).cpu() != ref.argmax(1)) & safe).any()
     assert (labels.cpu().long() == y.argmax(1).cpu()).all()
 
 
