@@ -7,6 +7,8 @@
 //   the streaming read of the offset/logit rows and the write of the sampled rows.
 // b2u_msda_forward_f32 — signature-compatible (in meaning) with the reference pybind op `ms_deform_attn_forward`
 //   (ops/src/vision.cpp:18, ms_deform_attn_cuda.cu:25-85, ms_deform_im2col_cuda.cuh:242-304): fp32, multi-level.
+#include <algorithm>
+
 #include "common.cuh"
 #include "../../include/dinounet_b200.h"
 #include "host_util.h"
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ va
   const int Lq = (HW * 21) / 4;
   const int b = blockIdx.z, hg = blockIdx.y;
   constexpr int ROW = HPC * DH;                           // elements per position in the slab
+  constexpr bool SWZ = (HPC == 1 && DH == 32);
   // ---- stage the slab: value[b, pos, hg*HPC .. +HPC, :] -> slab[pos][:]  (ROW*2 bytes contiguous per position)
   {
     constexpr int V16 = ROW * 2 / 16;                     // 16-byte vectors per position
@@ -98,7 +101,11 @@ __global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ va
     const int src_stride = heads * DH * 2 / 16;           // vectors between consecutive positions
     for (int i = threadIdx.x; i < HW * V16; i += 256) {
       const int pos = i / V16, v = i - pos * V16;
-      dst[i] = __ldg(src + static_cast<long long>(pos) * src_stride + v);
+      // SWZ (one head of 32 channels = 4 x 16 B per position): chunk c of position pos lives at c ^ ((pos >> 1) & 3), so
+      // the 8 lanes of a quarter-warp that sample 8 neighbouring positions (neighbouring queries do) hit 8 distinct
+      // 16-byte bank groups instead of 2
+      const int vs = SWZ ? (v ^ ((pos >> 1) & 3)) : v;
+      dst[pos * V16 + vs] = __ldg(src + static_cast<long long>(pos) * src_stride + v);
     }
   }
   __syncthreads();
@@ -139,11 +146,13 @@ __global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ va
         const int yy = y0 + (c >> 1), xx = x0 + (c & 1);
         if (yy < 0 || yy >= Hv || xx < 0 || xx >= Wv) continue;
         const float wt = aw * cw[c];
-        const T* src = hb + (yy * Wv + xx) * ROW;
+        const int pos = yy * Wv + xx;
+        const T* src = hb + pos * ROW;
+        const int sw = SWZ ? ((pos >> 1) & 3) : 0;
         if constexpr (DH % 8 == 0) {
 #pragma unroll
           for (int j = 0; j < DH; j += 8) {
-            const uint4 u = *reinterpret_cast<const uint4*>(src + j);
+            const uint4 u = *reinterpret_cast<const uint4*>(src + (SWZ ? (((j >> 3) ^ sw) << 3) : j));
             const float2 a0 = T16<T>::unpack2(u.x), a1 = T16<T>::unpack2(u.y), a2 = T16<T>::unpack2(u.z), a3 = T16<T>::unpack2(u.w);
             acc[j] = fmaf(wt, a0.x, acc[j]); acc[j + 1] = fmaf(wt, a0.y, acc[j + 1]);
             acc[j + 2] = fmaf(wt, a1.x, acc[j + 2]); acc[j + 3] = fmaf(wt, a1.y, acc[j + 3]);
@@ -187,8 +196,9 @@ static int launch_msda_smem(const void* value, const float* offaw, void* out, in
     configured = smem;
   }
   const int groups = heads / HPC;
-  // enough CTAs for ~2 waves of 148 SMs; each re-stages its slab from L2
-  int qsplit = (2 * num_sms() + B * groups - 1) / (B * groups);
+  // enough CTAs for ~2 waves of 148 SMs (x the CTAs that fit an SM); each re-stages its slab from L2
+  const int per_sm = static_cast<int>(std::max<size_t>(1, (200 * 1024) / std::max<size_t>(smem, 1)));
+  int qsplit = ((per_sm > 1 ? 6 : 2) * per_sm * num_sms() + B * groups - 1) / (B * groups);
   if (qsplit < 1) qsplit = 1;
   dim3 grid(qsplit, groups, B);
   kern<<<grid, 256, smem, stream>>>(static_cast<const T*>(value), offaw, static_cast<T*>(out), Hv, Wv, heads, qsplit);
@@ -201,12 +211,14 @@ extern "C" int b2u_msda_forward(const void* value, const float* offaw, void* out
   if (heads != 16 || points != 4) return set_error(-1, "b2u_msda_forward: built for 16 heads x 4 points (dinounet_training.py:758-759)");
   if ((Hv & 1) || (Wv & 1)) return set_error(-1, "b2u_msda_forward: value map must have even size");
   // shared-memory slab path (default): per CTA HPC heads x Hv*Wv positions x dh channels must fit in 200 KB
-  if (get_option(1) == 0) {
+  if (get_option(1) != 1) {
     const size_t per_head = static_cast<size_t>(Hv) * Wv * dh * 2;
 #define B2U_MSDA_SMEM(DH_, HPC_)                                                                                          \
     if (dh == DH_ && per_head * HPC_ <= 200 * 1024)                                                                        \
       return dtype == B2U_BF16 ? launch_msda_smem<__nv_bfloat16, DH_, HPC_>(value, offaw, out, B, Hv, Wv, heads, stream) \
                                : launch_msda_smem<__half, DH_, HPC_>(value, offaw, out, B, Hv, Wv, heads, stream);
+    // dh 32: one head per CTA (64 KB slab, 3 CTAs per SM, swizzled rows); option 1 == 2 keeps the two-heads-per-CTA layout
+    if (get_option(1) != 2) { B2U_MSDA_SMEM(32, 1) }
     B2U_MSDA_SMEM(12, 8) B2U_MSDA_SMEM(24, 4) B2U_MSDA_SMEM(32, 2) B2U_MSDA_SMEM(12, 2) B2U_MSDA_SMEM(24, 1) B2U_MSDA_SMEM(32, 1)
 #undef B2U_MSDA_SMEM
   }

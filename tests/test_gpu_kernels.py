@@ -418,7 +418,7 @@ def test_dwconv_three_planes_gelu():
     assert rel_err(out, ref) < 2e-3
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("dh", [12, 24, 32])
 def test_msda_forward_matches_reference_sampling(dh, impl):
     """the op the reference itself pins in ops/test.py: CUDA sampling == grid_sample formulation."""
@@ -429,7 +429,7 @@ def test_msda_forward_matches_reference_sampling(dh, impl):
     value = _rand(B, HW, heads, dh, dt=torch.float16)
     offaw = torch.cat([_rand(B * Lq, 128, scale=3.0, seed=1), _rand(B * Lq, 64, seed=2)], 1).contiguous()
     out = torch.full((B * Lq, heads * dh), float("nan"), device=DEV, dtype=torch.float16)
-    lib.b2u_set_option(1, impl)     # 0 = shared-memory slab kernel, 1 = warp-per-query kernel
+    lib.b2u_set_option(1, impl)     # 0 = shared-memory slab kernel (dh 32: one swizzled head per CTA), 1 = warp-per-query kernel, 2 = slab kernel without the one-head layout
     try:
         L.check(lib.b2u_msda_forward(P(value), P(offaw), P(out), B, Hv, Hv, heads, dh, pts, L.F16, stream()), "msda")
         torch.cuda.synchronize()

@@ -63,6 +63,13 @@ elif op == "conv":   # decoder 512^2 conv 64 -> 32
     bias = rnd(32, dt=torch.float32)
     out = torch.empty(32 * 512 * 512, 32, device=dev, dtype=torch.float16)
     run = lambda: gemm(x, w, out, L.F16, M=0, K=9 * 64, lda=64, bias=bias, conv=L.CONV3X3_S1, img=(32, 512, 512, 64))
+elif op == "msda":
+    Bm, Hv, heads, dh = 32, 32, 16, 32
+    Lq = Hv * Hv * 21 // 4
+    value = rnd(Bm, Hv * Hv, heads, dh, dt=torch.float16)
+    offaw = torch.cat([rnd(Bm * Lq, heads * 8, dt=torch.float32, sc=2.0), rnd(Bm * Lq, heads * 4, dt=torch.float32)], 1).contiguous()
+    out = torch.empty(Bm * Lq, heads * dh, device=dev, dtype=torch.float16)
+    run = lambda: L.check(lib.b2u_msda_forward(P(value), P(offaw), P(out), Bm, Hv, Hv, heads, dh, 4, L.F16, stream()), "msda")
 else:
     raise SystemExit("unknown op")
 
