@@ -32,6 +32,7 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--vit-dtype", default="bf16")
     ap.add_argument("--rest-dtype", default="fp16")
+    ap.add_argument("--query-dtype", default="16", choices=["16", "fp32"], help="adapter query stream storage")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--gemm-impl", default="v2", choices=["v1", "v2"])
     ap.add_argument("--attn-impl", default="tc", choices=["tc", "mma"])
@@ -195,7 +196,7 @@ def main():
     sd = O.make_state_dict(a.model, 2, seed=0)
     net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, a.model)
     net.load_state_dict(sd, strict=True)
-    net.vit_dtype, net.rest_dtype, net.attn_impl = a.vit_dtype, a.rest_dtype, a.attn_impl
+    net.vit_dtype, net.rest_dtype, net.attn_impl, net.query_dtype = a.vit_dtype, a.rest_dtype, a.attn_impl, a.query_dtype
     net = net.to(dev).eval()
     del sd
     eng = net._get_engine(dev)

@@ -35,34 +35,55 @@ static inline int blocks_for(long long n, int per_block) { return static_cast<in
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // one warp per row; three passes over the (L1-resident) row: mean, centred variance, normalise.
-template <typename T, bool OUT32>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, void* __restrict__ out,
+// IN16: the input stream is 16-bit (the adapter's query stream in "c16" mode) instead of fp32.
+template <typename T, bool IN16> struct LnIn;
+template <typename T> struct LnIn<T, false> {
+  static constexpr int kV = 4;   // elements per vector load
+  __device__ static __forceinline__ void load(const void* base, long long row, int D, int i, float (&f)[4]) {
+    const float4 v = reinterpret_cast<const float4*>(static_cast<const float*>(base) + row * D)[i];
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+};
+template <typename T> struct LnIn<T, true> {
+  static constexpr int kV = 4;
+  __device__ static __forceinline__ void load(const void* base, long long row, int D, int i, float (&f)[4]) {
+    const uint2 u = reinterpret_cast<const uint2*>(static_cast<const T*>(base) + row * D)[i];
+    const float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+};
+
+template <typename T, bool OUT32, bool IN16>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ in, void* __restrict__ out,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int rows, int D, float eps, int rows_in, int rows_out,
                                                         int row_off) {
+  using In = LnIn<T, IN16>;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
   long long ir = r;
   if (rows_out > 0) ir = static_cast<long long>(r / rows_out) * rows_in + row_off + (r % rows_out);
-  const float4* x = reinterpret_cast<const float4*>(in + ir * D);
   const int nv = D >> 2;
   float s = 0.f;
-  for (int i = lane; i < nv; i += 32) { const float4 v = x[i]; s += (v.x + v.y) + (v.z + v.w); }
+  for (int i = lane; i < nv; i += 32) { float v[4]; In::load(in, ir, D, i, v); s += (v[0] + v[1]) + (v[2] + v[3]); }
   const float mean = warp_sum(s) / D;
   float q = 0.f;
   for (int i = lane; i < nv; i += 32) {
-    const float4 v = x[i];
-    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    float v[4];
+    In::load(in, ir, D, i, v);
+    const float a = v[0] - mean, b = v[1] - mean, c = v[2] - mean, d = v[3] - mean;
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) / D + eps);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   for (int i = lane; i < nv; i += 32) {
-    const float4 v = x[i], g = g4[i], b = b4[i];
-    const float y0 = (v.x - mean) * rstd * g.x + b.x, y1 = (v.y - mean) * rstd * g.y + b.y;
-    const float y2 = (v.z - mean) * rstd * g.z + b.z, y3 = (v.w - mean) * rstd * g.w + b.w;
+    float v[4];
+    In::load(in, ir, D, i, v);
+    const float4 g = g4[i], b = b4[i];
+    const float y0 = (v[0] - mean) * rstd * g.x + b.x, y1 = (v[1] - mean) * rstd * g.y + b.y;
+    const float y2 = (v[2] - mean) * rstd * g.z + b.z, y3 = (v[3] - mean) * rstd * g.w + b.w;
     if (OUT32) {
       reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<long long>(r) * D)[i] = make_float4(y0, y1, y2, y3);
     } else {
@@ -72,17 +93,35 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
-extern "C" int b2u_layernorm(const float* in, void* out, const float* gamma, const float* beta, int32_t rows, int32_t D,
-                             float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32,
-                             int32_t dtype, b2u_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int layernorm_impl(const void* in, bool in16, void* out, const float* gamma, const float* beta, int32_t rows,
+                          int32_t D, float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32,
+                          int32_t dtype, cudaStream_t stream) {
   if (D % 4) return set_error(-1, "b2u_layernorm: D %% 4 != 0");
   const int grid = blocks_for(rows, 8);
   B2U_DISPATCH_T(dtype, {
-    if (out_fp32) layernorm_kernel<T, true><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
-    else layernorm_kernel<T, false><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+    if (in16) {
+      if (out_fp32) layernorm_kernel<T, true, true><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+      else layernorm_kernel<T, false, true><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+    } else {
+      if (out_fp32) layernorm_kernel<T, true, false><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+      else layernorm_kernel<T, false, false><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+    }
   });
   return check_launch("layernorm");
+}
+
+extern "C" int b2u_layernorm(const float* in, void* out, const float* gamma, const float* beta, int32_t rows, int32_t D,
+                             float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32,
+                             int32_t dtype, b2u_stream_t stream_) {
+  return layernorm_impl(in, false, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off, out_fp32, dtype,
+                        static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int b2u_layernorm16(const void* in, void* out, const float* gamma, const float* beta, int32_t rows, int32_t D,
+                               float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32,
+                               int32_t dtype, b2u_stream_t stream_) {
+  return layernorm_impl(in, true, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off, out_fp32, dtype,
+                        static_cast<cudaStream_t>(stream_));
 }
 
 // ------------------------------------------------------------------------------------------------ cast rows
@@ -111,6 +150,28 @@ extern "C" int b2u_cast_rows(const float* in, void* out, int32_t rows, int32_t D
   B2U_DISPATCH_T(dtype, (cast_rows_kernel<T><<<blocks_for(total8, 256), 256, 0, stream>>>(
                              in, static_cast<T*>(out), total8, D / 8, rows_in, rows_out, row_off)));
   return check_launch("cast_rows");
+}
+
+// 16-bit row gather (same row selection as b2u_cast_rows): 16 bytes per thread
+__global__ void copy_rows16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total8, int D8,
+                                   int rows_in, int rows_out, int row_off) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const long long r = i / D8;
+  const int c8 = static_cast<int>(i - r * D8);
+  long long ir = r;
+  if (rows_out > 0) ir = (r / rows_out) * rows_in + row_off + (r % rows_out);
+  out[i] = in[ir * D8 + c8];
+}
+
+extern "C" int b2u_copy_rows16(const void* in, void* out, int32_t rows, int32_t D, int32_t rows_in, int32_t rows_out,
+                               int32_t row_off, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (D % 8) return set_error(-1, "b2u_copy_rows16: D %% 8 != 0");
+  const long long total8 = static_cast<long long>(rows) * (D / 8);
+  copy_rows16_kernel<<<blocks_for(total8, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out),
+                                                                 total8, D / 8, rows_in, rows_out, row_off);
+  return check_launch("copy_rows16");
 }
 
 // ------------------------------------------------------------------------------------------------ patchify

@@ -56,7 +56,7 @@ class Plan:
 class ForwardEngine:
     def __init__(self, variant: str, params: Dict[str, torch.Tensor], num_classes: int, device: torch.device,
                  vit_dtype: str = "bf16", rest_dtype: str = "fp16", features=(32, 64, 128, 256),
-                 attn_impl: str = "tc"):
+                 attn_impl: str = "tc", query_dtype: str = "16"):
         if variant not in cfg.VARIANTS:
             raise ValueError(f"Unknown model: {variant}")
         self.v = cfg.VARIANTS[variant]
@@ -74,6 +74,12 @@ class ForwardEngine:
         self.tv, self.tr = _TORCH16[self.vt], _TORCH16[self.rt]
         self.features = tuple(features)
         self.attn_impl = attn_impl   # "tc" = tcgen05/TMEM kernel (default), "mma" = first-generation mma.sync kernel
+        # The adapter's query stream c [B, 5376, D] (dinov3_adapter.py:210-231).  "16": stored in rest_dtype, every
+        # residual update rounded to 16 bits - what the reference's autocast regime does (there in bf16: conv outputs and
+        # `query + attn` are 16-bit tensors); "fp32": kept in fp32 (2x the HBM traffic of the 12 stream passes per step).
+        if query_dtype not in ("16", "fp32"):
+            raise ValueError("query_dtype must be '16' or 'fp32'")
+        self.c16 = query_dtype == "16"
         self.w: Dict[str, torch.Tensor] = {}
         self._plans: Dict[Tuple[int, int], Tuple[Plan, dict]] = {}
         self._graphs: Dict[Tuple[int, int], object] = {}
@@ -342,7 +348,9 @@ class ForwardEngine:
         c3s = buf("c3s", (B * S16 * S16, 256), tr)
         c4s = buf("c4s", (B * S32 * S32, 256), tr)
         c1 = buf("c1", (B * S4 * S4, D), tr)
-        Cst = buf("Cst", (B * Lq, D), torch.float32)
+        c16 = self.c16
+        Cst = buf("Cst", (B * Lq, D), tr if c16 else torch.float32)
+        ln_c = lib.b2u_layernorm16 if c16 else lib.b2u_layernorm
         plan.add("stem0", lib.b2u_stem_conv0, _ptr(x), _ptr(w["stem0.w"]), _ptr(w["stem0.sc"]), _ptr(w["stem0.sh"]),
                  _ptr(sA), B, S, rt)
 
@@ -360,7 +368,7 @@ class ForwardEngine:
         self._gemm(plan, "spm.fc1", pool, B * S4 * S4, 64, 64, w["spmfc1.w"], D, c1, D, rt, bias=w["spmfc1.b"])
         le = w["level_embed"]
         for i, (src, kk, nl, off) in enumerate(((c2s, 128, n2, 0), (c3s, 256, n3, n2), (c4s, 256, n4, n2 + n3))):
-            self._gemm(plan, f"spm.fc{i + 2}", src, B * nl, kk, kk, w[f"spmfc{i + 2}.w"], D, Cst, D, rt, out_fp32=True,
+            self._gemm(plan, f"spm.fc{i + 2}", src, B * nl, kk, kk, w[f"spmfc{i + 2}.w"], D, Cst, D, rt, out_fp32=not c16,
                        rows=(nl, Lq, off), bias=w[f"spmfc{i + 2}.b"], shift=le[i])
 
         # ================= interaction blocks (dinov3_adapter.py:140-231) =================
@@ -374,7 +382,7 @@ class ForwardEngine:
         dh = (D // 2) // cfg.DEFORM_HEADS
         for e, k in enumerate((0, 1, 2, 3, 3, 3)):
             pre = f"e{e}."
-            plan.add(pre + "qnorm", lib.b2u_layernorm, _ptr(Cst), _ptr(QN), _ptr(w[pre + "query_norm.w"]),
+            plan.add(pre + "qnorm", ln_c, _ptr(Cst), _ptr(QN), _ptr(w[pre + "query_norm.w"]),
                      _ptr(w[pre + "query_norm.b"]), B * Lq, D, cfg.LN_EPS_ADAPTER, 0, 0, 0, 0, rt)
             plan.add(pre + "fnorm", lib.b2u_layernorm, _ptr(taps[k]), _ptr(FN), _ptr(w[pre + "feat_norm.w"]),
                      _ptr(w[pre + "feat_norm.b"]), B * P, D, cfg.LN_EPS_ADAPTER, 0, 0, 0, 0, rt)
@@ -383,28 +391,40 @@ class ForwardEngine:
                        bias=w[pre + "offawb"])
             plan.add(pre + "msda", lib.b2u_msda_forward, _ptr(VAL), _ptr(OFFAW), _ptr(SAMP), B, h, h, cfg.DEFORM_HEADS, dh,
                      cfg.DEFORM_POINTS, rt)
-            self._gemm(plan, pre + "outproj", SAMP, B * Lq, D // 2, D // 2, w[pre + "out"], D, Cst, D, rt, out_fp32=True,
-                       bias=w[pre + "outb"], residual=Cst, ldres=D)
-            plan.add(pre + "ffnnorm", lib.b2u_layernorm, _ptr(Cst), _ptr(QN), _ptr(w[pre + "ffn_norm.w"]),
+            if c16:
+                self._gemm(plan, pre + "outproj", SAMP, B * Lq, D // 2, D // 2, w[pre + "out"], D, Cst, D, rt,
+                           bias=w[pre + "outb"], add16=Cst, ldadd=D)
+            else:
+                self._gemm(plan, pre + "outproj", SAMP, B * Lq, D // 2, D // 2, w[pre + "out"], D, Cst, D, rt, out_fp32=True,
+                           bias=w[pre + "outb"], residual=Cst, ldres=D)
+            plan.add(pre + "ffnnorm", ln_c, _ptr(Cst), _ptr(QN), _ptr(w[pre + "ffn_norm.w"]),
                      _ptr(w[pre + "ffn_norm.b"]), B * Lq, D, cfg.LN_EPS_ADAPTER, 0, 0, 0, 0, rt)
             self._gemm(plan, pre + "ffn1", QN, B * Lq, D, D, w[pre + "f1"], D // 4, F1, D // 4, rt, bias=w[pre + "f1b"])
             plan.add(pre + "dwconv", lib.b2u_dwconv3x3, _ptr(F1), _ptr(F2), _ptr(w[pre + "dw"]), _ptr(w[pre + "dwb"]), B,
                      S16, S16, D // 4, 3, L.ACT_GELU, rt)
-            self._gemm(plan, pre + "ffn2", F2, B * Lq, D // 4, D // 4, w[pre + "f2"], D, Cst, D, rt, out_fp32=True,
-                       bias=w[pre + "f2b"], residual=Cst, ldres=D)
+            if c16:
+                self._gemm(plan, pre + "ffn2", F2, B * Lq, D // 4, D // 4, w[pre + "f2"], D, Cst, D, rt,
+                           bias=w[pre + "f2b"], add16=Cst, ldadd=D)
+            else:
+                self._gemm(plan, pre + "ffn2", F2, B * Lq, D // 4, D // 4, w[pre + "f2"], D, Cst, D, rt, out_fp32=True,
+                           bias=w[pre + "f2b"], residual=Cst, ldres=D)
 
         # ================= adapter tail (dinov3_adapter.py:460-482) =================
         C16 = buf("C16", (B * n2, D), tr)
         UP = buf("UP", (B * S4 * S4, D), tr)
         fs = [buf("f1", (B * S4 * S4, D), tr), buf("f2", (B * n2, D), tr), buf("f3", (B * n3, D), tr),
               buf("f4", (B * n4, D), tr)]
-        plan.add("cast_c2", lib.b2u_cast_rows, _ptr(Cst), _ptr(C16), B * n2, D, Lq, n2, 0, rt)
+        if c16:
+            plan.add("cast_c2", lib.b2u_copy_rows16, _ptr(Cst), _ptr(C16), B * n2, D, Lq, n2, 0)
+        else:
+            plan.add("cast_c2", lib.b2u_cast_rows, _ptr(Cst), _ptr(C16), B * n2, D, Lq, n2, 0, rt)
         self._gemm(plan, "up", C16, B * n2, D, D, w["up.w"], 4 * D, UP, D, rt, ps=(D, S8, S8), bias=w["up.b"], add16=c1,
                    ldadd=D)
         plan.add("tail1", lib.b2u_tail_fuse, _ptr(UP), 0, S4 * S4 * D, _ptr(taps[0]), _ptr(fs[0]), _ptr(w["bn1.sc"]),
                  _ptr(w["bn1.sh"]), B, S4, S4, h, h, D, rt)
         for i, (off, res) in enumerate(((0, S8), (n2, S16), (n2 + n3, S32))):
-            plan.add(f"tail{i + 2}", lib.b2u_tail_fuse, Cst.data_ptr() + off * D * 4, 1, Lq * D, _ptr(taps[i + 1]),
+            plan.add(f"tail{i + 2}", lib.b2u_tail_fuse, Cst.data_ptr() + off * D * (2 if c16 else 4), 0 if c16 else 1, Lq * D,
+                     _ptr(taps[i + 1]),
                      _ptr(fs[i + 1]), _ptr(w[f"bn{i + 2}.sc"]), _ptr(w[f"bn{i + 2}.sh"]), B, res, res, h, h, D, rt)
 
         # ================= FAPM + ups (dinounet_training.py:419-441, 255-264, 499-510) =================

@@ -64,6 +64,8 @@ SIGNATURES = {
     "b2u_attention_rows": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp],
     "b2u_layernorm": [vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp],
     "b2u_cast_rows": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "b2u_copy_rows16": [vp, vp, i32, i32, i32, i32, i32, vp],
+    "b2u_layernorm16": [vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32, i32, vp],
     "b2u_patchify": [vp, vp, i32, i32, i32, vp],
     "b2u_write_prefix": [vp, vp, i32, i32, i32, i32, vp],
     "b2u_stem_conv0": [vp, vp, vp, vp, vp, i32, i32, i32, vp],

@@ -132,10 +132,17 @@ int b2u_attention_rows(const void* q, const void* k, const void* vt, void* out, 
 int b2u_layernorm(const float* in, void* out, const float* gamma, const float* beta, int32_t rows, int32_t D,
                   float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32, int32_t dtype,
                   b2u_stream_t stream);
+/* Same, for a 16-bit input stream `in` (element type = dtype). */
+int b2u_layernorm16(const void* in, void* out, const float* gamma, const float* beta, int32_t rows, int32_t D,
+                  float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32, int32_t dtype,
+                  b2u_stream_t stream);
 
 /* fp32 -> 16-bit cast of a [rows, D] matrix with the same row selection as b2u_layernorm. */
 int b2u_cast_rows(const float* in, void* out, int32_t rows, int32_t D, int32_t rows_in, int32_t rows_out,
                   int32_t row_off, int32_t dtype, b2u_stream_t stream);
+/* 16-bit -> 16-bit row gather with the same row selection (no conversion). */
+int b2u_copy_rows16(const void* in, void* out, int32_t rows, int32_t D, int32_t rows_in, int32_t rows_out,
+                    int32_t row_off, b2u_stream_t stream);
 
 /* Patch-embed operand: x fp32 NCHW [B,3,S,S] -> [B*(S/16)^2, 768] 16-bit with k = c*256 + ky*16 + kx
  * (non-overlapping patches: a permutation + cast, no duplication)  (patch_embed.py:64-76). */

@@ -24,11 +24,11 @@ from oracle import dinounet_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _net(model, sd, vit="bf16", rest="fp16"):
+def _net(model, sd, vit="bf16", rest="fp16", query="16"):
     os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
     net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, model)
     net.load_state_dict(sd, strict=True)
-    net.vit_dtype, net.rest_dtype = vit, rest
+    net.vit_dtype, net.rest_dtype, net.query_dtype = vit, rest, query
     return net.to("cuda").eval()
 
 
@@ -109,6 +109,21 @@ def test_forward_multiclass_matches_oracle(ncls):
         safe = (margin[:, 0] - margin[:, 1]) > 4 * err * scale
         assert not ((y.argmax(1).cpu() != ref.argmax(1)) & safe).any()
     assert (labels.cpu().long() == y.argmax(1).cpu()).all()
+
+
+def test_query_stream_fp32_vs_16bit(golden_dir):
+    """The adapter's query stream in fp32 vs rest_dtype (default): both inside the tolerance; prints both errors."""
+    model, B, S = "dinounet_l", 1, 256
+    sd = O.make_state_dict(model, 2, seed=0)
+    x = O.make_input(B, S, 0)
+    golden = torch.from_numpy(np.load(os.path.join(golden_dir, f"{model}_b{B}_s{S}_w0_x0.npz"))["logits"])
+    errs = {}
+    for q in ("16", "fp32"):
+        net = _net(model, sd, query=q)
+        with torch.no_grad():
+            y = net(x.cuda())
+        errs[q] = _compare(y, golden, None, f"{model} query stream {q}")
+    assert errs["16"] <= errs["fp32"] * 1.5 + 2e-3
 
 
 def test_forward_512_golden_and_fp16_vit(golden_dir):
