@@ -34,16 +34,17 @@ struct AttnArgs {
 
 // Per-head-dim configuration.  HD = 64 (ViT-S/B/L): two query-tile groups per CTA, 4-stage K/V ring.
 // HD = 128 (ViT-7B): one group (the fp32 O accumulator needs 128 registers per thread), 2-stage ring.
-template <int HD> struct AtCfg {
+template <int HD, int SPLIT = 1> struct AtCfg {
   static constexpr int kGroups = HD == 64 ? 2 : 1;
-  static constexpr int kStages = HD == 64 ? 4 : 2;
+  static constexpr int kStages = HD == 64 ? (SPLIT > 1 ? 3 : 4) : 2;   // SPLIT > 1 pays for its exchange slots with a stage
   static constexpr int kKB = HD / 64;                       // 64-wide K blocks of the head dim
   static constexpr int kQBytes = 128 * HD * 2;              // kKB blocks of [128 rows x 64]
   static constexpr int kPBytes = 2 * 128 * 128;             // two key blocks of [128 rows x 64 keys]
   static constexpr int kKBytes = 128 * HD * 2;              // kKB blocks of [128 keys x 64]
   static constexpr int kVBytes = 2 * HD * 128;              // two key blocks of [HD rows x 64 keys]
-  static constexpr int kThreads = 64 + kGroups * 128;
-  static constexpr int kSmem = kGroups * (kQBytes + kPBytes) + kStages * (kKBytes + kVBytes) + 1024 + 256;
+  static constexpr int kThreads = 64 + kGroups * 128 * SPLIT;
+  static constexpr int kXchgBytes = SPLIT > 1 ? 2 * 128 * 4 * 4 : 0;   // [2 groups][128 rows][4] fp32 exchange slots
+  static constexpr int kSmem = kGroups * (kQBytes + kPBytes) + kStages * (kKBytes + kVBytes) + 1024 + 256 + kXchgBytes;
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -67,10 +68,10 @@ __device__ __forceinline__ float ex2(float x) {
   return r;
 }
 
-template <typename T, int HD>
-__global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
+template <typename T, int HD, int SPLIT>
+__global__ void __launch_bounds__(AtCfg<HD, SPLIT>::kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
   using TT = T16<T>;
-  using CF = AtCfg<HD>;
+  using CF = AtCfg<HD, SPLIT>;
   constexpr int NG = CF::kGroups, NST = CF::kStages, KB = CF::kKB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
   uint64_t* p_full = x_free + 4;           // [2]
   uint64_t* o_full = p_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* xchg = reinterpret_cast<float*>(bars + 32);   // 256 B of barriers, then the exchange slots
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
     for (int g = 0; g < 2; ++g) {
       mbar_init(&q_full[g], 1); mbar_init(&q_free[g], 1);
       mbar_init(&s_full[2 * g], 1); mbar_init(&s_full[2 * g + 1], 1);
-      mbar_init(&x_free[2 * g], 128); mbar_init(&x_free[2 * g + 1], 128);
-      mbar_init(&p_full[g], 128); mbar_init(&o_full[g], 1);
+      mbar_init(&x_free[2 * g], 128 * SPLIT); mbar_init(&x_free[2 * g + 1], 128 * SPLIT);
+      mbar_init(&p_full[g], 128 * SPLIT); mbar_init(&o_full[g], 1);
     }
     for (int s = 0; s < 4; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     fence_mbar_init();
@@ -218,12 +220,24 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
     }
   } else {
     // ===================== softmax / output warps =====================
-    const int g = (warp - 2) >> 2;          // query tile of the pair
+    // SPLIT warps share each (query tile, TMEM lane quarter): warp `part` owns key columns [part*128/SPLIT, ...) of
+    // every score tile and head dims [part*HD/SPLIT, ...) of O.  More resident warps per scheduler hide the TMEM-load /
+    // MUFU / dependency latencies this loop is bound by (2 warps per scheduler stalled on "wait" + "long scoreboard"
+    // 70 % of the time); the price is one 64-thread named barrier per key tile to combine the row maxima.
+    const int sw = warp - 2;
+    const int g = (sw >> 2) / SPLIT;        // query tile of the pair
+    const int part = (sw >> 2) % SPLIT;     // column / head-dim slice of this warp
     const int q4 = warp & 3;                // TMEM lane quarter
     const int row = q4 * 32 + lane;
+    constexpr int CW = 128 / SPLIT;         // score columns per warp
+    constexpr int OW = HD / SPLIT;          // O columns (head dims) per warp
     const uint32_t tX = tmem_base + g * 256 + (static_cast<uint32_t>(q4 * 32) << 16);
     const uint32_t sP_row = smem_u32(sP + g * CF::kPBytes) + row * 128;
     const uint32_t sP_base = smem_u32(sP + g * CF::kPBytes);
+    float* xm = xchg + (g * 128 + row) * 4;  // [2 buffers][2 parts] row maxima; the l exchange reuses the slots
+    auto pair_sync = [&]() {
+      if constexpr (SPLIT > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + g * 4 + q4), "n"(32 * SPLIT) : "memory");
+    };
     uint32_t sfull_cnt[2] = {0, 0}, ofull_cnt = 0;
     for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
       const int bh = static_cast<int>(item / args.npairs);
@@ -231,52 +245,46 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
       const int q0 = args.q_begin + (pair * NG + g) * 128;
       if (q0 >= args.ntok) continue;        // this group has no query tile in this item (warp-uniform)
       float m = -INFINITY, l = 0.f, corr_prev = 0.f;
-      float o[HD];
+      float o[OW];
 #pragma unroll
-      for (int i = 0; i < HD; ++i) o[i] = 0.f;
-      auto absorb = [&](uint32_t t) {       // O = O * corr_prev + (P V)(chunk) read from TMEM
+      for (int i = 0; i < OW; ++i) o[i] = 0.f;
+      auto absorb = [&](uint32_t t) {       // O = O * corr_prev + (P V)(chunk) read from TMEM (this warp's head dims)
 #pragma unroll
-        for (int h = 0; h < HD / 32; ++h) {
+        for (int h = 0; h < OW / 32; ++h) {
           uint32_t v[32];
-          tmem_ld32(t + h * 32, v);
+          tmem_ld32(t + part * OW + h * 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 32; ++c) o[h * 32 + c] = fmaf(o[h * 32 + c], corr_prev, __uint_as_float(v[c]));
         }
       };
       for (int j = 0; j < J; ++j) {
-        const uint32_t tS = tX + (j & 1) * 128;
+        const uint32_t tS = tX + (j & 1) * 128 + part * CW;
         mbar_wait(&s_full[2 * g + (j & 1)], sfull_cnt[j & 1] & 1);
         ++sfull_cnt[j & 1];
         tc_fence_after();
-        const int kbase = j * 128;
-        const bool tail = kbase + 128 > args.ntok;
-        // ---- pass 1: row max of the raw scores (scale > 0, applied once), TMEM loads software-pipelined
+        const int kbase = j * 128 + part * CW;
+        const bool tail = j * 128 + 128 > args.ntok;
+        // ---- pass 1: row max of the raw scores over this warp's columns (scale > 0, applied once)
         float mx = -INFINITY;
-        {
-          uint32_t va[32], vb[32];
-          auto red = [&](const uint32_t (&v)[32], int pc) {
-            if (!tail) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
-            } else {
+        for (int pc = 0; pc < CW / 32; ++pc) {
+          uint32_t v[32];
+          tmem_ld32(tS + pc * 32, v);
+          tmem_ld_wait();
+          if (!tail) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (kbase + pc * 32 + c < args.ntok) mx = fmaxf(mx, __uint_as_float(v[c]));
-            }
-          };
-          tmem_ld32(tS, va);
-          tmem_ld_wait();
-          tmem_ld32(tS + 32, vb);
-          red(va, 0);
-          tmem_ld_wait();
-          tmem_ld32(tS + 64, va);
-          red(vb, 1);
-          tmem_ld_wait();
-          tmem_ld32(tS + 96, vb);
-          red(va, 2);
-          tmem_ld_wait();
-          red(vb, 3);
+            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (kbase + pc * 32 + c < args.ntok) mx = fmaxf(mx, __uint_as_float(v[c]));
+          }
+        }
+        if constexpr (SPLIT > 1) {            // combine with the partner's columns (double-buffered slots, see above)
+          xm[(j & 1) * 2 + part] = mx;
+          pair_sync();
+          mx = fmaxf(mx, xm[(j & 1) * 2 + (part ^ 1)]);
         }
         const float m_new = fmaxf(m, mx * args.scale_log2e);   // chunk 0 always has valid keys -> finite
         const float corr = ex2(m - m_new);
@@ -291,14 +299,15 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
         }
         // ---- pass 2: P = exp2(s*scale - m) -> 16-bit -> swizzled smem (A operand of the PV MMA).
         // Two compiled bodies: only the last key chunk has columns >= ntok to zero; left as a runtime test inside the
-        // element loop the compiler if-converts it into an index add + compare + select PER ELEMENT of every chunk
-        // (30 % of the kernel's instructions).
+        // element loop the compiler if-converts it into an index add + compare + select PER ELEMENT of every chunk.
         float rs = 0.f;
         auto pass2 = [&](auto tail_c) {
           constexpr bool kTail = decltype(tail_c)::value;
-          uint32_t va[32], vb[32];
-          tmem_ld32(tS, va);
-          auto emit = [&](const uint32_t (&v)[32], int pc) {
+#pragma unroll
+          for (int pc = 0; pc < CW / 32; ++pc) {
+            uint32_t v[32];
+            tmem_ld32(tS + pc * 32, v);
+            tmem_ld_wait();
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
@@ -311,25 +320,15 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
               rs += a + b;                          // fp32 row sum of the un-rounded probabilities (as flash-attention)
               pk[c >> 1] = TT::pack2(a, b);
             }
-            // columns pc*32 .. +31 -> K-block pc>>1, 16-byte chunks (pc&1)*4 .. +3 of this row
-            const uint32_t base = sP_row + (pc >> 1) * (128 * 128);
+            // tile columns gc*32 .. +31 -> K-block gc>>1, 16-byte chunks (gc&1)*4 .. +3 of this row
+            const int gc = part * (CW / 32) + pc;
+            const uint32_t base = sP_row + (gc >> 1) * (128 * 128);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-              const int chunk = (pc & 1) * 4 + c4;
+              const int chunk = (gc & 1) * 4 + c4;
               sts128a(base + ((chunk ^ (row & 7)) << 4), pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
             }
-          };
-          tmem_ld_wait();
-          tmem_ld32(tS + 32, vb);
-          emit(va, 0);
-          tmem_ld_wait();
-          tmem_ld32(tS + 64, va);
-          emit(vb, 1);
-          tmem_ld_wait();
-          tmem_ld32(tS + 96, vb);
-          emit(va, 2);
-          tmem_ld_wait();
-          emit(vb, 3);
+          }
         };
         if (tail) pass2(std::true_type{});
         else pass2(std::false_type{});
@@ -346,25 +345,33 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
       absorb(tX + ((J - 1) & 1) * 128);
       tc_fence_before();
       mbar_arrive(&x_free[2 * g + ((J - 1) & 1)]);
-      // ---- normalise, stage this warp's 32 rows through (now free) P smem (64 dims per 16 KB block), coalesced store
+      // ---- row sums of the column slices add up (same running max in every warp of the row)
+      if constexpr (SPLIT > 1) {
+        pair_sync();                               // the partner has consumed the last row-max slots
+        xm[part] = l;
+        pair_sync();
+        l += xm[part ^ 1];
+      }
+      // ---- normalise, stage this warp's head dims of its 32 rows through (now free) P smem (64 dims per 16 KB block)
       const float inv = 1.f / l;
       __syncwarp();
 #pragma unroll
-      for (int hb = 0; hb < HD / 64; ++hb)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float* oo = o + hb * 64 + 8 * c;
-          sts128a(sP_row + hb * (128 * 128) + ((c ^ (row & 7)) << 4), TT::pack2(oo[0] * inv, oo[1] * inv),
-                  TT::pack2(oo[2] * inv, oo[3] * inv), TT::pack2(oo[4] * inv, oo[5] * inv), TT::pack2(oo[6] * inv, oo[7] * inv));
-        }
+      for (int c = 0; c < OW / 8; ++c) {
+        const int dim0 = part * OW + 8 * c;          // first head dim of this 16-byte chunk
+        const float* oo = o + 8 * c;
+        sts128a(sP_row + (dim0 >> 6) * (128 * 128) + ((((dim0 >> 3) & 7) ^ (row & 7)) << 4), TT::pack2(oo[0] * inv, oo[1] * inv),
+                TT::pack2(oo[2] * inv, oo[3] * inv), TT::pack2(oo[4] * inv, oo[5] * inv), TT::pack2(oo[6] * inv, oo[7] * inv));
+      }
       __syncwarp();
+      pair_sync();                                   // both dim slices of these 32 rows are staged
       const int b = bh / args.heads, hd = bh - b * args.heads;
       const int D = args.heads * HD;
       T* outp = reinterpret_cast<T*>(args.out);
 #pragma unroll
       for (int hb = 0; hb < HD / 64; ++hb)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int ii = 0; ii < 8 / SPLIT; ++ii) {     // the warps of a row quarter split its 32 rows
+          const int i = part * (8 / SPLIT) + ii;
           const int rr = q4 * 32 + i * 4 + (lane >> 3);
           const uint4 val = lds128a(sP_base + hb * (128 * 128) + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
           const int t = q0 + rr;
@@ -372,6 +379,7 @@ __global__ void __launch_bounds__(AtCfg<HD>::kThreads, 1) attn_tc_kernel(const _
             *reinterpret_cast<uint4*>(outp + (static_cast<long long>(b) * args.ntok + t) * D + hd * HD + hb * 64 + (lane & 7) * 8) = val;
         }
       __syncwarp();
+      pair_sync();                                   // the partner has read my staged chunks: P smem may be rewritten
     }
   }
   tc_fence_before();
@@ -555,18 +563,20 @@ extern "C" int b2u_attention_rows(const void* q, const void* k, const void* vt, 
   return check_launch("attention_rows");
 }
 
-template <typename T, int HD>
+template <typename T, int HD, int SPLIT>
 static int launch_attn_tc(const AttnMaps& maps, const AttnArgs& a, cudaStream_t stream) {
-  auto kern = attn_tc_kernel<T, HD>;
+  auto kern = attn_tc_kernel<T, HD, SPLIT>;
+  using CF = AtCfg<HD, SPLIT>;
+  static_assert(CF::kSmem <= 227 * 1024, "attention smem budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<HD>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kSmem);
     if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(attn_tc): %s", cudaGetErrorString(e));
     configured = true;
   }
   const int sms = num_sms();
   const int grid = static_cast<int>(a.items < sms ? a.items : sms);
-  kern<<<grid, AtCfg<HD>::kThreads, AtCfg<HD>::kSmem, stream>>>(maps, a);
+  kern<<<grid, CF::kThreads, CF::kSmem, stream>>>(maps, a);
   return check_launch("attention_tc");
 }
 
@@ -593,9 +603,15 @@ static int attention_tc_impl(const void* q, const void* k, const void* vt, void*
   if ((rc = make_map_3d(&maps.q, q, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
   if ((rc = make_map_3d(&maps.k, k, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
   if ((rc = make_map_3d(&maps.vt, vt, dtype, npad, hd, BH, npad, static_cast<uint64_t>(npad) * hd, 64, static_cast<uint32_t>(head_dim)))) return rc;
+  // option 4 (B2U_OPT_ATTN_SPLIT) = 1: one softmax warp per (query tile, TMEM lane quarter) instead of two (A/B switch)
+  if (get_option(4) == 1) {
+    if (head_dim == 64)
+      return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 64, 1>(maps, a, stream) : launch_attn_tc<__half, 64, 1>(maps, a, stream);
+    return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 128, 1>(maps, a, stream) : launch_attn_tc<__half, 128, 1>(maps, a, stream);
+  }
   if (head_dim == 64)
-    return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 64>(maps, a, stream) : launch_attn_tc<__half, 64>(maps, a, stream);
-  return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 128>(maps, a, stream) : launch_attn_tc<__half, 128>(maps, a, stream);
+    return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 64, 2>(maps, a, stream) : launch_attn_tc<__half, 64, 2>(maps, a, stream);
+  return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 128, 2>(maps, a, stream) : launch_attn_tc<__half, 128, 2>(maps, a, stream);
 }
 
 extern "C" int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,

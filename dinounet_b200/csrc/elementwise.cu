@@ -820,6 +820,60 @@ __global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, 
   if (labels) labels[static_cast<long long>(b) * rows + p] = static_cast<uint8_t>(best);
 }
 
+// <= 8 classes (the common case): everything unrolled, the activations are consumed as they are loaded.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) seg_head_kernel8(const T* __restrict__ x, const float* __restrict__ sums,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ logits, uint8_t* __restrict__ labels,
+                                                       int rows, int ncls) {
+  __shared__ float s_a[C], s_b[C];       // per-image affine: y = x*a + b
+  __shared__ float s_w[8 * C], s_bias[8];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float mean = sums[(static_cast<long long>(b) * C + c) * 2] / rows;
+    const float var = fmaxf(sums[(static_cast<long long>(b) * C + c) * 2 + 1] / rows - mean * mean, 0.f);
+    const float a = rsqrtf(var + eps) * gamma[c];
+    s_a[c] = a;
+    s_b[c] = beta[c] - mean * a;
+  }
+  for (int i = threadIdx.x; i < ncls * C; i += 256) s_w[i] = w[i];
+  if (threadIdx.x < ncls) s_bias[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= rows) return;
+  const T* xp = x + (static_cast<long long>(b) * rows + p) * C;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = k < ncls ? s_bias[k] : -INFINITY;
+#pragma unroll
+  for (int g = 0; g < C / 8; ++g) {
+    Vec8<T> v;
+    v.load(xp + g * 8);
+    float f[8];
+    v.to_float(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = f[j] * s_a[g * 8 + j] + s_b[g * 8 + j];
+      t = t > 0.f ? t : 0.01f * t;
+      t = T16<T>::to_f(T16<T>::from_f(t));  // the normalised activation is a 16-bit tensor in the reference regime
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < ncls) acc[k] = fmaf(t, s_w[k * C + g * 8 + j], acc[k]);
+    }
+  }
+  int best = 0;
+  float bv = acc[0];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < ncls) {
+      logits[(static_cast<long long>(b) * ncls + k) * rows + p] = acc[k];
+      if (acc[k] > bv) { bv = acc[k]; best = k; }
+    }
+  }
+  if (labels) labels[static_cast<long long>(b) * rows + p] = static_cast<uint8_t>(best);
+}
+
 extern "C" int b2u_seg_head(const void* x, const float* sums, const float* gamma, const float* beta, float eps,
                             const float* w, const float* b, float* logits, uint8_t* labels, int32_t B, int32_t rows,
                             int32_t C, int32_t ncls, int32_t dtype, b2u_stream_t stream_) {
@@ -827,7 +881,11 @@ extern "C" int b2u_seg_head(const void* x, const float* sums, const float* gamma
   if (C != 32) return set_error(-1, "b2u_seg_head: C must be 32 (plans features_per_stage[0])");
   if (ncls < 1 || ncls > kSegMaxClasses) return set_error(-1, "b2u_seg_head: 1 <= ncls <= %d", kSegMaxClasses);
   dim3 grid((rows + 255) / 256, B);
-  B2U_DISPATCH_T(dtype, (seg_head_kernel<T, 32><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
+  if (ncls <= 8) {
+    B2U_DISPATCH_T(dtype, (seg_head_kernel8<T, 32><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
+  } else {
+    B2U_DISPATCH_T(dtype, (seg_head_kernel<T, 32><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
+  }
   return check_launch("seg_head");
 }
 

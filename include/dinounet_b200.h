@@ -276,7 +276,9 @@ int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream);
  * (default), 1 = always the per-tap TMA walk. */
 /* key 3 (B2U_OPT_GEMM_PAIR): 0 = plain GEMMs with 256-wide tiles run on CTA pairs (tcgen05 cta_group::2, 256 x 256
  * tile per pair, each CTA stages half of the weight tile) (default), 1 = one CTA per tile. */
-enum { B2U_OPT_GEMM_IMPL = 0, B2U_OPT_MSDA_IMPL = 1, B2U_OPT_CONV_HALO = 2, B2U_OPT_GEMM_PAIR = 3 };
+/* key 4 (B2U_OPT_ATTN_SPLIT): 0 = two softmax warps per (query tile, TMEM lane quarter), each owning half of the key
+ * columns / head dims (default), 1 = one warp. */
+enum { B2U_OPT_GEMM_IMPL = 0, B2U_OPT_MSDA_IMPL = 1, B2U_OPT_CONV_HALO = 2, B2U_OPT_GEMM_PAIR = 3, B2U_OPT_ATTN_SPLIT = 4 };
 int b2u_set_option(int32_t key, int32_t value);
 
 const char* b2u_last_error(void);
