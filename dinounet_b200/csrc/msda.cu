@@ -83,29 +83,31 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const T* __restrict__ val
 // (three float4 from the fp32 offaw row), runs the softmax / location prologue, gathers 4 points x 4 corners x dh
 // channels from SHARED memory with 16-byte loads and writes dh contiguous 16-bit outputs.  HBM traffic is the
 // algorithmic minimum (offaw + out + value once per CTA); the random gather never leaves the SM.
-template <typename T, int DH, int HPC>
+template <typename T, int DH, int HPC, int PITCH = HPC * DH>
 __global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ value, const float* __restrict__ offaw,
                                                         T* __restrict__ out, int Hv, int Wv, int heads, int qsplit) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  T* slab = reinterpret_cast<T*>(sm_raw);                 // [HW][HPC*DH]
+  T* slab = reinterpret_cast<T*>(sm_raw);                 // [HW][PITCH]
   const int HW = Hv * Wv;
   const int Lq = (HW * 21) / 4;
   const int b = blockIdx.z, hg = blockIdx.y;
-  constexpr int ROW = HPC * DH;                           // elements per position in the slab
-  constexpr bool SWZ = (HPC == 1 && DH == 32);
-  // ---- stage the slab: value[b, pos, hg*HPC .. +HPC, :] -> slab[pos][:]  (ROW*2 bytes contiguous per position)
+  constexpr int ROW = HPC * DH;                           // payload elements per position
+  // PITCH (elements between positions) >= ROW.  One-head layouts pad the row to a power of two so that many small CTAs
+  // fit an SM (dh 32 / 24: 64 B rows = 64 KB slab, 3 CTAs per SM; dh 12: 32 B rows = 32 KB slab, 6 CTAs per SM).
+  // SWZ (64 B rows): 16-byte chunk c of position pos lives at c ^ ((pos >> 1) & 3), so the 8 lanes of a quarter-warp
+  // that sample 8 neighbouring positions (neighbouring queries do) hit 8 distinct bank groups instead of 2.
+  constexpr bool SWZ = (HPC == 1 && PITCH == 32);
+  // ---- stage the slab: value[b, pos, hg*HPC .. +HPC, :] -> slab[pos][0 .. ROW)  (8-byte granules)
   {
-    constexpr int V16 = ROW * 2 / 16;                     // 16-byte vectors per position
-    const uint4* src = reinterpret_cast<const uint4*>(value + (static_cast<long long>(b) * HW * heads + hg * HPC) * DH);
-    uint4* dst = reinterpret_cast<uint4*>(slab);
-    const int src_stride = heads * DH * 2 / 16;           // vectors between consecutive positions
-    for (int i = threadIdx.x; i < HW * V16; i += 256) {
-      const int pos = i / V16, v = i - pos * V16;
-      // SWZ (one head of 32 channels = 4 x 16 B per position): chunk c of position pos lives at c ^ ((pos >> 1) & 3), so
-      // the 8 lanes of a quarter-warp that sample 8 neighbouring positions (neighbouring queries do) hit 8 distinct
-      // 16-byte bank groups instead of 2
-      const int vs = SWZ ? (v ^ ((pos >> 1) & 3)) : v;
-      dst[pos * V16 + vs] = __ldg(src + static_cast<long long>(pos) * src_stride + v);
+    constexpr int V8 = ROW * 2 / 8;                       // 8-byte granules per position
+    const uint2* src = reinterpret_cast<const uint2*>(value + (static_cast<long long>(b) * HW * heads + hg * HPC) * DH);
+    const int src_stride = heads * DH * 2 / 8;            // granules between consecutive positions
+    for (int i = threadIdx.x; i < HW * V8; i += 256) {
+      const int pos = i / V8, v = i - pos * V8;
+      int off = v * 8;                                    // byte offset inside the row
+      if (SWZ) off = (((off >> 4) ^ ((pos >> 1) & 3)) << 4) | (off & 15);
+      *reinterpret_cast<uint2*>(sm_raw + static_cast<size_t>(pos) * (PITCH * 2) + off) =
+          __ldg(src + static_cast<long long>(pos) * src_stride + v);
     }
   }
   __syncthreads();
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ va
         if (yy < 0 || yy >= Hv || xx < 0 || xx >= Wv) continue;
         const float wt = aw * cw[c];
         const int pos = yy * Wv + xx;
-        const T* src = hb + pos * ROW;
+        const T* src = hb + pos * PITCH;
         const int sw = SWZ ? ((pos >> 1) & 3) : 0;
         if constexpr (DH % 8 == 0) {
 #pragma unroll
@@ -184,11 +186,11 @@ __global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ va
   }
 }
 
-template <typename T, int DH, int HPC>
+template <typename T, int DH, int HPC, int PITCH = HPC * DH>
 static int launch_msda_smem(const void* value, const float* offaw, void* out, int B, int Hv, int Wv, int heads,
                             cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(Hv) * Wv * HPC * DH * 2;
-  auto kern = msda_smem_kernel<T, DH, HPC>;
+  const size_t smem = static_cast<size_t>(Hv) * Wv * PITCH * 2;
+  auto kern = msda_smem_kernel<T, DH, HPC, PITCH>;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -196,8 +198,8 @@ static int launch_msda_smem(const void* value, const float* offaw, void* out, in
     configured = smem;
   }
   const int groups = heads / HPC;
-  // enough CTAs for ~2 waves of 148 SMs (x the CTAs that fit an SM); each re-stages its slab from L2
-  const int per_sm = static_cast<int>(std::max<size_t>(1, (200 * 1024) / std::max<size_t>(smem, 1)));
+  // enough CTAs for several waves of (CTAs that fit an SM) x 148 SMs; each re-stages its slab from L2
+  const int per_sm = static_cast<int>(std::min<size_t>(8, std::max<size_t>(1, (200 * 1024) / std::max<size_t>(smem, 1))));
   int qsplit = ((per_sm > 1 ? 6 : 2) * per_sm * num_sms() + B * groups - 1) / (B * groups);
   if (qsplit < 1) qsplit = 1;
   dim3 grid(qsplit, groups, B);
@@ -212,14 +214,14 @@ extern "C" int b2u_msda_forward(const void* value, const float* offaw, void* out
   if ((Hv & 1) || (Wv & 1)) return set_error(-1, "b2u_msda_forward: value map must have even size");
   // shared-memory slab path (default): per CTA HPC heads x Hv*Wv positions x dh channels must fit in 200 KB
   if (get_option(1) != 1) {
-    const size_t per_head = static_cast<size_t>(Hv) * Wv * dh * 2;
-#define B2U_MSDA_SMEM(DH_, HPC_)                                                                                          \
-    if (dh == DH_ && per_head * HPC_ <= 200 * 1024)                                                                        \
-      return dtype == B2U_BF16 ? launch_msda_smem<__nv_bfloat16, DH_, HPC_>(value, offaw, out, B, Hv, Wv, heads, stream) \
-                               : launch_msda_smem<__half, DH_, HPC_>(value, offaw, out, B, Hv, Wv, heads, stream);
-    // dh 32: one head per CTA (64 KB slab, 3 CTAs per SM, swizzled rows); option 1 == 2 keeps the two-heads-per-CTA layout
-    if (get_option(1) != 2) { B2U_MSDA_SMEM(32, 1) }
-    B2U_MSDA_SMEM(12, 8) B2U_MSDA_SMEM(24, 4) B2U_MSDA_SMEM(32, 2) B2U_MSDA_SMEM(12, 2) B2U_MSDA_SMEM(24, 1) B2U_MSDA_SMEM(32, 1)
+#define B2U_MSDA_SMEM(DH_, HPC_, PITCH_)                                                                                  \
+    if (dh == DH_ && static_cast<size_t>(Hv) * Wv * PITCH_ * 2 <= 200 * 1024)                                              \
+      return dtype == B2U_BF16 ? launch_msda_smem<__nv_bfloat16, DH_, HPC_, PITCH_>(value, offaw, out, B, Hv, Wv, heads, stream) \
+                               : launch_msda_smem<__half, DH_, HPC_, PITCH_>(value, offaw, out, B, Hv, Wv, heads, stream);
+    // one head per CTA with power-of-two padded rows (many small CTAs per SM); option 1 == 2 keeps the multi-head layouts
+    if (get_option(1) != 2) { B2U_MSDA_SMEM(32, 1, 32) B2U_MSDA_SMEM(24, 1, 32) B2U_MSDA_SMEM(12, 1, 16) }
+    B2U_MSDA_SMEM(12, 8, 96) B2U_MSDA_SMEM(24, 4, 96) B2U_MSDA_SMEM(32, 2, 64) B2U_MSDA_SMEM(12, 2, 24) B2U_MSDA_SMEM(24, 1, 24)
+    B2U_MSDA_SMEM(32, 1, 32)
 #undef B2U_MSDA_SMEM
   }
   const long long nq = static_cast<long long>(B) * ((Hv * Wv * 21) / 4);
