@@ -11,6 +11,7 @@ template <typename T> struct Vec8 {
   uint4 u;
   __device__ __forceinline__ void load(const T* p) { u = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void store(T* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ __forceinline__ void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
   __device__ __forceinline__ void to_float(float (&f)[8]) const {
     float2 a = T16<T>::unpack2(u.x), b = T16<T>::unpack2(u.y), c = T16<T>::unpack2(u.z), d = T16<T>::unpack2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
@@ -93,18 +94,77 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   }
 }
 
+// Row held in registers (NV vectors of 4 per lane, D = 128 * NV): one global read per element instead of three L1 passes.
+template <typename T, bool OUT32, bool IN16, int NV>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const void* __restrict__ in, void* __restrict__ out,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            int rows, float eps, int rows_in, int rows_out, int row_off) {
+  using In = LnIn<T, IN16>;
+  constexpr int D = 128 * NV;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  long long ir = r;
+  if (rows_out > 0) ir = static_cast<long long>(r / rows_out) * rows_in + row_off + (r % rows_out);
+  float v[NV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    In::load(in, ir, D, lane + 32 * k, v[k]);
+    s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float a = v[k][0] - mean, b = v[k][1] - mean, c = v[k][2] - mean, d = v[k][3] - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+    const float y0 = (v[k][0] - mean) * rstd * g.x + b.x, y1 = (v[k][1] - mean) * rstd * g.y + b.y;
+    const float y2 = (v[k][2] - mean) * rstd * g.z + b.z, y3 = (v[k][3] - mean) * rstd * g.w + b.w;
+    if (OUT32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<long long>(r) * D)[i] = make_float4(y0, y1, y2, y3);
+    } else {
+      uint2 pk = make_uint2(T16<T>::pack2(y0, y1), T16<T>::pack2(y2, y3));
+      reinterpret_cast<uint2*>(reinterpret_cast<T*>(out) + static_cast<long long>(r) * D)[i] = pk;
+    }
+  }
+}
+
+template <typename T, bool OUT32, bool IN16>
+static void layernorm_launch(const void* in, void* out, const float* gamma, const float* beta, int rows, int D, float eps,
+                             int rows_in, int rows_out, int row_off, cudaStream_t stream) {
+  const int grid = blocks_for(rows, 8);
+#define B2U_LN_REG(NV_)                                                                                                 \
+  case 128 * NV_:                                                                                                       \
+    layernorm_reg_kernel<T, OUT32, IN16, NV_><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, eps, rows_in, rows_out, row_off); \
+    return;
+  switch (D) {
+    B2U_LN_REG(3) B2U_LN_REG(6) B2U_LN_REG(8)      // 384 / 768 / 1024 (ViT-S/B/L and their adapters)
+    default: break;
+  }
+#undef B2U_LN_REG
+  layernorm_kernel<T, OUT32, IN16><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+}
+
 static int layernorm_impl(const void* in, bool in16, void* out, const float* gamma, const float* beta, int32_t rows,
                           int32_t D, float eps, int32_t rows_in, int32_t rows_out, int32_t row_off, int32_t out_fp32,
                           int32_t dtype, cudaStream_t stream) {
   if (D % 4) return set_error(-1, "b2u_layernorm: D %% 4 != 0");
-  const int grid = blocks_for(rows, 8);
   B2U_DISPATCH_T(dtype, {
     if (in16) {
-      if (out_fp32) layernorm_kernel<T, true, true><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
-      else layernorm_kernel<T, false, true><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+      if (out_fp32) layernorm_launch<T, true, true>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off, stream);
+      else layernorm_launch<T, false, true>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off, stream);
     } else {
-      if (out_fp32) layernorm_kernel<T, true, false><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
-      else layernorm_kernel<T, false, false><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+      if (out_fp32) layernorm_launch<T, true, false>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off, stream);
+      else layernorm_launch<T, false, false>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off, stream);
     }
   });
   return check_launch("layernorm");
@@ -366,12 +426,6 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, T
   const int y = static_cast<int>(t / pw), x0 = static_cast<int>(t - static_cast<long long>(y) * pw);
   const int C = C8 * 8;
   const T* base = in + (static_cast<long long>(b) * rows_per_img + poff) * C + c8 * 8;
-  float wr[9][8];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9 + k * C + c8 * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w9 + k * C + c8 * 8) + 1);
-    wr[k][0] = w0.x; wr[k][1] = w0.y; wr[k][2] = w0.z; wr[k][3] = w0.w; wr[k][4] = w1.x; wr[k][5] = w1.y; wr[k][6] = w1.z; wr[k][7] = w1.w;
-  }
   float acc[4][8];
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8) + 1);
@@ -380,24 +434,35 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, T
       acc[p][0] = b0.x; acc[p][1] = b0.y; acc[p][2] = b0.z; acc[p][3] = b0.w; acc[p][4] = b1.x; acc[p][5] = b1.y; acc[p][6] = b1.z; acc[p][7] = b1.w;
     }
   }
+  // per tap row: the 6 input vectors are requested together (6 independent 16-byte loads in flight), the 3 x 8 weights
+  // of the row come from L1 (keeping all 72 in registers cost 128 registers/thread = 512 threads/SM, latency-bound)
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = y + ky - 1;
-    if (iy < 0 || iy >= ph) continue;
+    if (iy < 0 || iy >= ph) continue;                 // warp-uniform for whole-row groups except at plane borders
+    Vec8<T> v[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const int ix = x0 - 1 + c;
+      if (ix >= 0 && ix < pw) v[c].load(base + (static_cast<long long>(iy) * pw + ix) * C);
+      else v[c].zero();
+    }
+    float wr[3][8];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9 + (ky * 3 + kx) * C + c8 * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w9 + (ky * 3 + kx) * C + c8 * 8) + 1);
+      wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w; wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
+    }
 #pragma unroll
     for (int c = 0; c < 6; ++c) {                      // input columns x0-1 .. x0+4
-      const int ix = x0 - 1 + c;
-      if (ix < 0 || ix >= pw) continue;
-      Vec8<T> v;
-      v.load(base + (static_cast<long long>(iy) * pw + ix) * C);
       float f[8];
-      v.to_float(f);
+      v[c].to_float(f);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int kx = c - p;                          // output pixel x0+p sees this column as tap kx
         if (kx < 0 || kx > 2) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(f[j], wr[ky * 3 + kx][j], acc[p][j]);
+        for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(f[j], wr[kx][j], acc[p][j]);
       }
     }
   }
@@ -511,27 +576,34 @@ __global__ void tail_fuse_up_kernel(const void* __restrict__ base, int base_fp32
     const int y = S * cy + S / 2 + ty;
     if (y < 0 || y >= H) continue;
     const float ly = (ty + 0.5f) / S;
+    // the S base vectors of this output row are requested together (S independent loads in flight per thread)
+    float f[S][8];
+    bool ok[S];
 #pragma unroll
     for (int tx = 0; tx < S; ++tx) {
       const int x = S * cx + S / 2 + tx;
-      if (x < 0 || x >= W) continue;
-      const float lx = (tx + 0.5f) / S;
-      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-      float f[8];
-      const long long pix = (static_cast<long long>(y) * W + x);
+      ok[tx] = x >= 0 && x < W;
+      const long long pix = static_cast<long long>(y) * W + (ok[tx] ? x : 0);
       if (base_fp32) {
-        ld8(reinterpret_cast<const float*>(base) + static_cast<long long>(b) * base_bstride + pix * D + c8 * 8, f);
+        ld8(reinterpret_cast<const float*>(base) + static_cast<long long>(b) * base_bstride + pix * D + c8 * 8, f[tx]);
       } else {
         Vec8<T> v;
         v.load(reinterpret_cast<const T*>(base) + static_cast<long long>(b) * base_bstride + pix * D + c8 * 8);
-        v.to_float(f);
+        v.to_float(f[tx]);
       }
+    }
+#pragma unroll
+    for (int tx = 0; tx < S; ++tx) {
+      if (!ok[tx]) continue;
+      const int x = S * cx + S / 2 + tx;
+      const float lx = (tx + 0.5f) / S;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        f[j] = (f[j] + (w00 * c00[j] + w01 * c01[j] + w10 * c10[j] + w11 * c11[j])) * sc[j] + sh[j];
+        f[tx][j] = (f[tx][j] + (w00 * c00[j] + w01 * c01[j] + w10 * c10[j] + w11 * c11[j])) * sc[j] + sh[j];
       Vec8<T> o;
-      o.from_float(f);
-      o.store(out + (static_cast<long long>(b) * H * W + pix) * D + c8 * 8);
+      o.from_float(f[tx]);
+      o.store(out + (static_cast<long long>(b) * H * W + static_cast<long long>(y) * W + x) * D + c8 * 8);
     }
   }
 }
