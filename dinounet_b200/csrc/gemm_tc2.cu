@@ -10,6 +10,9 @@
 //                                layout (per-column params are per-lane constants) and issue fully coalesced 16 B
 //                                loads/stores (residual / skip tensors / output).
 //   The accumulator of tile i+1 is produced while the epilogue drains tile i (TMEM: 2 x BN columns).
+//   PAIR variants (256-wide tiles of plain GEMMs): the scheduling unit is a cluster of two CTAs that issues
+//   tcgen05.mma.cta_group::2 (M = 256); each CTA stages its own 128 A rows and HALF of the W tile, both post their TMA
+//   bytes on the leader's mbarrier, commits are multicast to both CTAs, each CTA drains its own 128 accumulator rows.
 //   Convolution mode: A tiles are 4-D TMA halo boxes of the NHWC image (9 taps x channel blocks, OOB = zero padding).
 #include "common.cuh"
 #include "../../include/dinounet_b200.h"
