@@ -15,3 +15,4 @@ from .training import (  # noqa: F401
 __version__ = "0.1.0"
 from .sliding_window import SlidingWindowPredictor, compute_gaussian, compute_steps_for_sliding_window  # noqa: F401,E402
 from .inference import StreamedPredictor  # noqa: F401,E402
+from .checkpoint import load_network_weights  # noqa: F401,E402

@@ -125,6 +125,15 @@ class SlidingWindowPredictor:
         else:
             self.label_manager = SimpleNamespace(num_segmentation_heads=network.num_classes)
 
+    def initialize_from_checkpoint(self, network, filename_or_checkpoint, patch_size=(512, 512)):
+        """Weights + mirroring axes from a training checkpoint (`checkpoint_final.pth`), the part of
+        `initialize_from_trained_model_folder` (predict_from_raw_data.py:66-130) that concerns the network."""
+        from .checkpoint import load_network_weights
+        meta = load_network_weights(network, filename_or_checkpoint)
+        self.manual_initialization(network.to(self.device), None, SimpleNamespace(patch_size=list(patch_size)), None, {},
+                                   meta.get("trainer_name"), meta.get("inference_allowed_mirroring_axes"))
+        return meta
+
     def _internal_get_sliding_window_slicers(self, image_size: Tuple[int, ...]):
         patch = self.configuration_manager.patch_size
         if len(patch) != len(image_size) - 1:

@@ -110,3 +110,30 @@ def test_engine_rejects_unsupported_kernel_choices(built):
         ForwardEngine("dinounet_7b", {}, 2, torch.device("cpu"), attn_impl="mma")
     with pytest.raises(ValueError):
         ForwardEngine("dinounet_xl", {}, 2, torch.device("cpu"))
+
+
+def test_training_checkpoint_loads_into_the_b200_model(tmp_path):
+    """A checkpoint in the reference's format (nnUNetTrainer.py:1093-1104), with the DataParallel / torch.compile key
+    prefixes its loader tolerates (:1116-1121), loads strictly into the B200 module."""
+    import os
+    import torch
+    import dinounet_b200
+    from dinounet_b200 import config
+    from oracle import dinounet_oracle as O
+    os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
+    sd = O.make_state_dict("dinounet_s", 3, seed=2)
+    for prefix in ("", "module.", "_orig_mod."):
+        ckpt = {"network_weights": {prefix + k: v for k, v in sd.items()}, "optimizer_state": {}, "grad_scaler_state": None,
+                "logging": {}, "_best_ema": 0.5, "current_epoch": 7, "init_args": {"fold": 0}, "trainer_name": "DinoUNetTrainer_s",
+                "inference_allowed_mirroring_axes": (0, 1)}
+        path = str(tmp_path / f"checkpoint_final{len(prefix)}.pth")
+        torch.save(ckpt, path)
+        net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 3, None, "dinounet_s")
+        meta = dinounet_b200.load_network_weights(net, path)
+        assert meta["trainer_name"] == "DinoUNetTrainer_s" and meta["inference_allowed_mirroring_axes"] == (0, 1)
+        assert meta["current_epoch"] == 7
+        got = net.state_dict()
+        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    import pytest
+    with pytest.raises(KeyError):
+        dinounet_b200.load_network_weights(net, {"state_dict": {}})
