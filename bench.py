@@ -32,7 +32,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--vit-dtype", default="bf16")
     ap.add_argument("--rest-dtype", default="fp16")
-    ap.add_argument("--query-dtype", default="16", choices=["16", "fp32"], help="adapter query stream storage")
+    ap.add_argument("--query-dtype", default="fp32", choices=["16", "fp32"],
+                    help="adapter query stream storage: fp32 = the reference's dtype (default), 16 = opt-in reduced storage")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--gemm-impl", default="v2", choices=["v1", "v2"])
     ap.add_argument("--attn-impl", default="tc", choices=["tc", "mma"])

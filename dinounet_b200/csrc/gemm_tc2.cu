@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     tma_prefetch_desc(&maps.b);
     for (int s = 0; s < 8; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(w_bar, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 16 : 8); }
+    // BN <= 32: a tile is one 32-column chunk, drained by ONE warp per TMEM lane quarter; the two warp sets alternate
+    // tiles (set = accumulator buffer), so two epilogues are in flight instead of one set idling
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 16 : (BN <= 32 ? 4 : 8)); }
     fence_mbar_init();
   }
   if constexpr (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / multicast commit
@@ -322,6 +324,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     const uint32_t tempty0 = PAIR ? mapa_u32(smem_u32(tempty_bar), 0) : 0u;   // the leader CTA's "accumulator drained" barriers
     for (long long tile = unit_id; tile < total_tiles; tile += unit_cnt, ++it) {
       const int buf = it & 1;
+      if constexpr (BN <= 32) {
+        if (buf != half) continue;                     // the other warp set owns this accumulator buffer
+      }
       const int nt = static_cast<int>(tile % args.n_tiles);
       const int mt = PAIR ? 2 * static_cast<int>(tile / args.n_tiles) + static_cast<int>(cta_rank)
                           : static_cast<int>(tile / args.n_tiles);
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         constexpr int kChunks = BN / 32;
         constexpr int kPerHalf = kChunks >= 2 ? kChunks / 2 : 1;
         const int ch_begin = kChunks >= 2 ? half * kPerHalf : 0;
-        const int ch_end = kChunks >= 2 ? ch_begin + kPerHalf : (half == 0 ? 1 : 0);
+        const int ch_end = kChunks >= 2 ? ch_begin + kPerHalf : 1;   // BN 32: the owning warp set takes the only chunk
 #pragma unroll 1
         for (int ch = ch_begin; ch < ch_end; ++ch) {
           uint32_t v[32];

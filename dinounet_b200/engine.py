@@ -56,7 +56,7 @@ class Plan:
 class ForwardEngine:
     def __init__(self, variant: str, params: Dict[str, torch.Tensor], num_classes: int, device: torch.device,
                  vit_dtype: str = "bf16", rest_dtype: str = "fp16", features=(32, 64, 128, 256),
-                 attn_impl: str = "tc", query_dtype: str = "16"):
+                 attn_impl: str = "tc", query_dtype: str = "fp32"):
         if variant not in cfg.VARIANTS:
             raise ValueError(f"Unknown model: {variant}")
         self.v = cfg.VARIANTS[variant]
@@ -74,9 +74,10 @@ class ForwardEngine:
         self.tv, self.tr = _TORCH16[self.vt], _TORCH16[self.rt]
         self.features = tuple(features)
         self.attn_impl = attn_impl   # "tc" = tcgen05/TMEM kernel (default), "mma" = first-generation mma.sync kernel
-        # The adapter's query stream c [B, 5376, D] (dinov3_adapter.py:210-231).  "16": stored in rest_dtype, every
-        # residual update rounded to 16 bits - what the reference's autocast regime does (there in bf16: conv outputs and
-        # `query + attn` are 16-bit tensors); "fp32": kept in fp32 (2x the HBM traffic of the 12 stream passes per step).
+        # The adapter's query stream c [B, 5376, D] (dinov3_adapter.py:210-231).  "fp32" (default) = the reference's dtype
+        # under autocast: the 16-bit SPM outputs are promoted to fp32 by `c + level_embed` (fp32 parameter) and stay fp32
+        # through `query + attn`.  "16" = opt-in: stored in rest_dtype, every residual update rounded to 16 bits (half the
+        # HBM traffic of the 12 stream passes per step; measured +4.4 % throughput, rel err 7.8e-3 -> 8.0e-3).
         if query_dtype not in ("16", "fp32"):
             raise ValueError("query_dtype must be '16' or 'fp32'")
         self.c16 = query_dtype == "16"

@@ -494,9 +494,9 @@ class DinoUNet(nn.Module):
     vit_dtype = "bf16"
     rest_dtype = "fp16"
     attn_impl = "tc"
-    #: adapter query stream c: "16" = rest_dtype with 16-bit residual updates (the reference regime keeps it in bf16),
-    #: "fp32" = fp32 stream (more HBM traffic, marginally closer to the fp32 reference)
-    query_dtype = "16"
+    #: adapter query stream c: "fp32" = the reference's dtype under autocast (default), "16" = rest_dtype with 16-bit
+    #: residual updates (opt-in: +4 % throughput, slightly below the reference's precision for that one tensor)
+    query_dtype = "fp32"
 
     def __init__(self, network_config: dict = None, input_channels: int = None, num_classes: int = None,
                  dinov3_pretrained_path: str = "dinounet/checkpoints/dinov3_vits16_pretrain_lvd1689m-08c60483.pth",
@@ -582,7 +582,7 @@ class DinoUNet(nn.Module):
             sd = {k: t for k, t in self.state_dict().items() if not k.startswith("decoder.encoder.")}
             self._engine = ForwardEngine(self.dinov3_model_name, sd, self.num_classes, device, self.vit_dtype,
                                          self.rest_dtype, tuple(self.encoder.target_channels), self.attn_impl,
-                                         getattr(self, "query_dtype", "16"))
+                                         getattr(self, "query_dtype", "fp32"))
         return self._engine
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

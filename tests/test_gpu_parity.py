@@ -24,7 +24,7 @@ from oracle import dinounet_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _net(model, sd, vit="bf16", rest="fp16", query="16"):
+def _net(model, sd, vit="bf16", rest="fp16", query="fp32"):
     os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
     net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, model)
     net.load_state_dict(sd, strict=True)
@@ -112,7 +112,8 @@ def test_forward_multiclass_matches_oracle(ncls):
 
 
 def test_query_stream_fp32_vs_16bit(golden_dir):
-    """The adapter's query stream in fp32 vs rest_dtype (default): both inside the tolerance; prints both errors."""
+    """The adapter's query stream in fp32 (default = the reference's dtype) vs the opt-in 16-bit storage: both inside the
+    tolerance; prints both errors."""
     model, B, S = "dinounet_l", 1, 256
     sd = O.make_state_dict(model, 2, seed=0)
     x = O.make_input(B, S, 0)
