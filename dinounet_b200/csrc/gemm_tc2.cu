@@ -46,13 +46,6 @@ template <int BN, int EPI = 0, bool PAIR = false> struct Cfg2 {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
-__device__ __forceinline__ float apply_act2(float v, int act) {
-  if (act == B2U_ACT_GELU) return gelu_erf(v);
-  if (act == B2U_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == B2U_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
-  return v;
-}
-
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
