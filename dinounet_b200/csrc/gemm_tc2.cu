@@ -24,6 +24,7 @@ namespace b2u {
 constexpr int kHaloW = 130;                           // 128 output pixels + 1 halo pixel on each side
 constexpr int kHaloBytes = 3 * kHaloW * 128;           // one TMA box: 3 rows x 130 px x 64 ch x 2 B
 constexpr int kHaloStageBytes = 49 * 1024;             // box rounded up to the 1024 B swizzle period
+constexpr int kHaloPrefetch = 6;                       // L2 prefetch distance of the halo boxes, in tiles of one CTA
 
 constexpr int kRopeBytes = 128 * 32 * 2 * 4;   // (rope_h + rope_w <= 128) rows x <=32 angles x {sin, cos} fp32
 
@@ -207,6 +208,18 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           x0 = (r % args.tiles_x) * args.TW;
         }
         if (halo) {
+          // The ring holds only 2-3 of these 49 KB boxes, so the tile rate is (stages / load latency): pull the box this CTA
+          // will need kHaloPrefetch tiles from now into L2, so that its TMA load later costs an L2 hit, not a DRAM miss.
+          {
+            const long long tf = tile + static_cast<long long>(kHaloPrefetch) * unit_cnt;
+            if (tf < total_tiles) {
+              const int mtf = static_cast<int>(tf / args.n_tiles);
+              const int per_img = args.tiles_x * args.tiles_y;
+              const int imgf = mtf / per_img;
+              const int rf = mtf - imgf * per_img;
+              tma_prefetch_4d(&maps.a[0], 0, (rf % args.tiles_x) * args.TW - 1, (rf / args.tiles_x) * args.TH - 1, imgf);
+            }
+          }
           // one TMA box per tile: channels [0,64) x pixels [x0-1, x0+129) x rows [y0-1, y0+2) (OOB = zero padding)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kHaloBytes);
