@@ -45,3 +45,40 @@ def sharded_forward(forward: Callable[[torch.Tensor], torch.Tensor], x_global: t
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_bounds(x_global.shape[0], world, rank)
     return gather_logits(forward(x_global[lo:hi]), x_global.shape[0], group)
+
+
+def sharded_sliding_window(predict: Callable[[torch.Tensor], torch.Tensor], volume: torch.Tensor, group=None) -> torch.Tensor:
+    """Sliding-window prediction of a [c, slices, H, W] volume with the SLICES sharded across ranks: a 2D configuration
+    predicts every slice independently (predict_from_raw_data.py:502-521 enumerates tiles slice by slice), so each rank
+    runs `predict` (e.g. `SlidingWindowPredictor.predict_sliding_window_return_logits`) on its contiguous slice range
+    and one all-gather of the [heads, slices_r, H, W] results rebuilds the volume on every rank.  A rank with no slice
+    (more ranks than slices) contributes an empty shard."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = volume.shape[1]
+    lo, hi = shard_bounds(n, world, rank)
+    if world == 1:
+        return predict(volume)
+    sizes = [shard_bounds(n, world, r) for r in range(world)]
+    per = max(h - l for l, h in sizes)
+    local = predict(volume[:, lo:hi]) if hi > lo else None
+    # every rank needs the output geometry even when it owns no slice: take it from the lowest rank (always non-empty)
+    if local is not None:
+        dev = local.device
+    elif dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = volume.device
+    meta = torch.zeros(3, dtype=torch.int64, device=dev)
+    if rank == 0:
+        meta[0], meta[1], meta[2] = local.shape[0], local.shape[2], local.shape[3]
+    dist.broadcast(meta, src=0, group=group)
+    heads, H, W = (int(t) for t in meta.tolist())
+    dtype = torch.float16
+    pad = torch.zeros((per, heads, H, W), dtype=dtype, device=dev)     # slice-major so that shards are contiguous
+    if local is not None:
+        pad[: hi - lo] = local.to(dtype).transpose(0, 1)
+    buf = torch.empty((world * per, heads, H, W), dtype=dtype, device=dev)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    out = torch.cat([buf[r * per: r * per + (h - l)] for r, (l, h) in enumerate(sizes)], 0)
+    return out.transpose(0, 1).contiguous()

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dinounet_b200.parallel import gather_logits, shard_bounds, sharded_forward
+from dinounet_b200.parallel import gather_logits, shard_bounds, sharded_forward, sharded_sliding_window
 
 
 def test_shard_bounds_cover_batch_exactly():
@@ -57,3 +57,36 @@ def test_two_rank_gloo_gather_matches_single_process(B):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(shape == (B, 2, 8, 8) for _, _, shape in res)
+
+
+def _fake_predict(vol):  # stand-in sliding-window predictor: [c, d, H, W] -> fp16 [2, d, H, W], slice-independent
+    return torch.stack([vol.sum(0), vol.mean(0) - 1.0], 0).half()
+
+
+def _sw_worker(rank, world, port, n_slices, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vol = torch.randn(3, n_slices, 6, 5, generator=torch.Generator().manual_seed(1))
+        got = sharded_sliding_window(_fake_predict, vol)
+        q.put((rank, bool(torch.equal(got, _fake_predict(vol))), tuple(got.shape), str(got.dtype)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_slices", [1, 4, 5])
+def test_two_rank_gloo_slice_sharded_sliding_window(n_slices):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sw_worker, args=(r, 2, port, n_slices, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
+    assert all(shape == (2, n_slices, 6, 5) and dt == "torch.float16" for _, _, shape, dt in res)
