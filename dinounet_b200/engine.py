@@ -253,8 +253,10 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ plan
     def build_plan(self, B: int, S: int) -> Tuple[Plan, dict]:
-        if S % 32 or S < 128:
-            raise ValueError("input size must be a multiple of 32 (>= 128)")
+        if S < 128 or (S & (S - 1)):
+            # the conv tiles want power-of-two row widths below 128 px and 128-multiples above, on every pyramid level
+            # (S/2 ... S/32), and the three-plane depthwise conv needs S/16 % 8 == 0; the reference's plans force 512
+            raise ValueError("input size must be a power of two >= 128 (the reference's plan forces 512x512)")
         v, w, lib = self.v, self.w, self.lib
         vt, rt, tv, tr = self.vt, self.rt, self.tv, self.tr
         D, Hh = v.embed_dim, v.num_heads

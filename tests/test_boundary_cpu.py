@@ -137,3 +137,17 @@ def test_training_checkpoint_loads_into_the_b200_model(tmp_path):
     import pytest
     with pytest.raises(KeyError):
         dinounet_b200.load_network_weights(net, {"state_dict": {}})
+
+
+def test_engine_rejects_unsupported_patch_sizes_with_a_clear_error():
+    """Host-side validation (no kernel runs): sizes the tiling does not cover raise ValueError, not a late kernel error."""
+    import os
+    import pytest
+    import torch
+    from dinounet_b200.engine import ForwardEngine
+    from oracle import dinounet_oracle as O
+    sd = {k: v for k, v in O.make_state_dict("dinounet_s", 2, seed=0).items() if not k.startswith("decoder.encoder.")}
+    eng = ForwardEngine.__new__(ForwardEngine)          # build_plan's size check comes before any device work
+    for S in (96, 160, 384, 500):
+        with pytest.raises(ValueError, match="power of two"):
+            ForwardEngine.build_plan(eng, 1, S)
