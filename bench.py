@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--attn-impl", default="tc", choices=["tc", "mma"])
     ap.add_argument("--gemm-pair", default="on", choices=["on", "off"], help="CTA-pair (cta_group::2) GEMM tiles (A/B switch)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="patches in the bounded CPU-baseline sample (0 = skip)")
+    ap.add_argument("--eager-steps", type=int, default=10, help="timed steps of the torch-eager CUDA arm at N=1 (0 = skip)")
     ap.add_argument("--ops-out", default="", help="write the per-kernel timing breakdown (JSON) here")
     return ap.parse_args()
 
@@ -137,6 +138,27 @@ def run_reference(a):
     }))
 
 
+def eager_cuda_patches_per_s(model, B, S, steps, warmup, dev):
+    import torch
+    from oracle import dinounet_oracle as O
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(model, 2, seed=0).items()}
+    xs = [O.make_input(B, S, 300 + i).to(dev) for i in range(2)]
+    with torch.no_grad():
+        for i in range(warmup):
+            O.forward(sd, model, xs[i % 2], autocast_like_reference=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            O.forward(sd, model, xs[i % 2], autocast_like_reference=True)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / ms * 1e3, "unit": "patches/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "what": "reference algorithm (oracle port) as torch eager on the same GPU: cuBLAS/cuDNN/SDPA kernels, outer fp16 / "
+                    "inner bf16 autocast, inputs resident in HBM, batch %d" % B}
+
+
 def run_reference_cuda(a):
     """the same oracle port run by PyTorch eager on the B200 in the reference's GPU precision
     regime (outer fp16 autocast, inner bf16 ViT, fp32 MSDA) — what a user gets from the reference code on this GPU
@@ -177,7 +199,7 @@ def main():
     os.environ.setdefault("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "1")
     import dinounet_b200
     from dinounet_b200 import config, lib
-    from dinounet_b200.parallel import gather_logits
+    from dinounet_b200.parallel import AsyncGatherer
     from oracle import dinounet_oracle as O   # synthetic weights/inputs + FLOP model + cpu_baseline only
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,10 +230,15 @@ def main():
     xs = [O.make_input(B, S, 100 + rank * 7 + i).to(dev) for i in range(3)]
     use_graph = not a.no_graph
 
+    # the ONE collective of the step: NCCL all-gather of the fp16 logits (33.5 MB/rank), enqueued on a
+    # side stream right after the forward and double-buffered, so it overlaps the next step's kernels; every gather is
+    # joined into the timed stream before the closing event.
+    gat = AsyncGatherer(B * world, dev, torch.float16) if world > 1 else None
+
     def step(i):
         logits, _ = eng.forward(xs[i % 3], use_graph=use_graph)
-        if world > 1:
-            return gather_logits(logits, B * world)      # the ONE collective of the step (NCCL all-gather)
+        if gat is not None:
+            gat.submit(logits)
         return logits
 
     with torch.no_grad(), ClockSampler(local) as clk:
@@ -226,6 +253,8 @@ def main():
         e0.record()
         for i in range(K):
             step(i)
+        if gat is not None:
+            gat.wait_all()
         e1.record()
         torch.cuda.synchronize()
         t_region1 = time.perf_counter()
@@ -244,7 +273,9 @@ def main():
         # (copies on side streams overlap the kernels of the neighbouring steps; nothing is skipped).
         from dinounet_b200.inference import StreamedPredictor
         hx = [O.make_input(B, S, 200 + i).pin_memory() for i in range(3)]
-        pred = StreamedPredictor(net, use_graph=use_graph)
+        # N > 1: the gather happens on the device, straight from the forward's output and before / independent of this
+        # rank's own D2H copy (no host round trip of the logits)
+        pred = StreamedPredictor(net, use_graph=use_graph, gatherer=gat)
         acc = 0.0
         for y in pred.run(hx[i % 3] for i in range(3)):       # warm-up of the streamed path
             acc += float(y[0, 0, 0, 0])
@@ -253,9 +284,9 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         for y in pred.run(hx[i % 3] for i in range(K)):
-            if world > 1:
-                gather_logits(y.to(dev, non_blocking=True), B * world)   # the step's one collective (device-side)
             acc += float(y[0, 0, 0, 0])                           # touch the downloaded result on the host
+        if gat is not None:
+            gat.wait_all()
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
@@ -263,7 +294,7 @@ def main():
         e2e = world * B * K / te.item()
 
         # ---- per-kernel timing (one extra eager step with CUDA events around every launch, same stream)
-        breakdown, roof = {}, None
+        breakdown, roof, roof_hbm = {}, None, None
         if rank == 0:
             stream = torch.cuda.current_stream(dev)
             evs = []
@@ -301,6 +332,17 @@ def main():
                     "algorithmic_bytes_per_launch": (T * v.embed_dim * 2 * 2 + T * v.ffn_hidden * 2 * 2 + T * 3 * v.embed_dim * 2 + 2 * T * v.embed_dim * 8
                                                      + 2 * (4 * v.embed_dim * v.embed_dim + 2 * v.embed_dim * v.ffn_hidden)) / 4,
                     "peak_source": pk["src"] + " (bf16 sustained)", "share_of_step": t_gemm / sum(fam.values())}
+            # top HBM-bound kernel: the 512^2 decoder conv (2f -> f channels, implicit GEMM, halo mode): reads the concat
+            # buffer once, writes the conv output once (+ the per-(n,c) statistics); SURVEY.md section 8(d): bytes = (Cin+Cout)*2 B/px
+            per_op = {n: s_.elapsed_time(e_) for n, s_, e_ in evs}
+            f0 = eng.features[0]
+            hb = B * S * S * (2 * f0 + f0) * 2 + 9 * 2 * f0 * f0 * 2
+            t_conv = per_op.get("d2.conv0")
+            if t_conv:
+                ach_h = hb / (t_conv * 1e-3) / 1e9
+                roof_hbm = {"bound": "hbm", "kernel": "gemm_tc2_kernel<32,...> conv3x3 halo mode (decoder stage 2 conv 0, %d->%d ch @ %dx%d)" % (2 * f0, f0, S, S),
+                            "achieved": ach_h, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_h / pk["hbm_gbs"],
+                            "algorithmic_bytes_per_launch": hb, "us": t_conv * 1e3, "traffic": None, "peak_source": pk["src"]}
             if a.ops_out:
                 os.makedirs(os.path.dirname(a.ops_out) or ".", exist_ok=True)
                 json.dump({"per_family_ms": breakdown, "per_op_ms": [(n, s_.elapsed_time(e_)) for n, s_, e_ in evs]},
@@ -312,6 +354,13 @@ def main():
             v_cpu, cores, dt = cpu_forward_patches_per_s(a.model, S, a.cpu_sample)
             cpu = {"value": v_cpu, "unit": "patches/s", "cores": cores, "kind": "port",
                    "sample": f"{a.cpu_sample} x 1 patch {a.model}@{S} fp32 eval forward ({dt:.1f} s), oracle port of the reference"}
+        eager = None
+        if world == 1 and a.eager_steps > 0 and a.model != "dinounet_7b":
+            # the reference algorithm as PyTorch eager on THIS GPU (library kernels, the reference's autocast regime):
+            # the "reference already on Blackwell libraries" bar of SURVEY.md section 8(d), same box, same batch
+            eng.clear_plans()
+            torch.cuda.empty_cache()
+            eager = eager_cuda_patches_per_s(a.model, B, S, a.eager_steps, 3, dev)
         total_flops = O.algorithmic_flops_per_patch(a.model, S)
         out = {
             "metric": "2D patches/sec (512x512) forward", "value": value, "unit": "patches/s", "n_gpus": world, "steps": K,
@@ -319,14 +368,14 @@ def main():
             "dtype": f"{a.vit_dtype} (ViT GEMMs/attention) + {a.rest_dtype} (adapter/FAPM/decoder), fp32 accumulate/residuals",
             "data": "synthetic", "impl": "b200",
             "config": {"workload": f"{a.model} forward, {S}x{S}x3, per-GPU batch {B}, random-init weights (seed 0)",
-                       "global_batch": B * world, "parallelism": f"batch-sharded dp{world} + 1 NCCL all-gather of logits" if world > 1 else "single GPU",
+                       "global_batch": B * world, "parallelism": f"batch-sharded dp{world} + 1 NCCL all-gather of fp16 logits per step (side stream, double-buffered)" if world > 1 else "single GPU",
                        "l2": "3 resident input batches rotated (3x%.0f MB) and a per-step activation working set >> 126 MB L2" % (B * 3 * S * S * 4 / 1e6),
                        "cuda_graph": use_graph},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                     "d2h_bytes_per_step": B * 2 * S * S * 4},
             "gpu_launches": K * n_kernels, "kernels_per_step": n_kernels,
             "clocks": clk.summary(t_region0, t_region1),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "eager_cuda": eager,
             "model_tflops": value / world * total_flops / 1e12,
             "breakdown_ms": {k: round(v, 3) for k, v in list(breakdown.items())[:14]},
         }

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -82,9 +83,13 @@ class ForwardEngine:
             raise ValueError("query_dtype must be '16' or 'fp32'")
         self.c16 = query_dtype == "16"
         self.w: Dict[str, torch.Tensor] = {}
-        self._plans: Dict[Tuple[int, int], Tuple[Plan, dict]] = {}
+        # (B, S) -> (plan, buffers) in LRU order; every entry owns a full activation buffer set (GBs at B=32, 512^2) and
+        # possibly a CUDA graph, so ragged last batches / varying tile batches must not accumulate without bound
+        self._plans: "OrderedDict[Tuple[int, int], Tuple[Plan, dict]]" = OrderedDict()
         self._graphs: Dict[Tuple[int, int], object] = {}
-        self.pack(params)
+        self.max_plans = 4
+        with torch.cuda.device(self.device):
+            self.pack(params)
 
     # ------------------------------------------------------------------ weight packing
     def _dev(self, t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
@@ -530,9 +535,20 @@ class ForwardEngine:
     # ------------------------------------------------------------------ execution
     def get_plan(self, B: int, S: int) -> Tuple[Plan, dict]:
         key = (B, S)
-        if key not in self._plans:
+        if key in self._plans:
+            self._plans.move_to_end(key)
+            return self._plans[key]
+        while len(self._plans) >= max(1, self.max_plans):      # evict the least recently used buffer set + graph
+            old, _ = self._plans.popitem(last=False)
+            self._graphs.pop(old, None)
+        with torch.cuda.device(self.device):                   # kernels, TMA maps and num_sms() use the current device
             self._plans[key] = self.build_plan(B, S)
         return self._plans[key]
+
+    def clear_plans(self):
+        """Frees every cached (batch, size) buffer set and CUDA graph."""
+        self._plans.clear()
+        self._graphs.clear()
 
     def forward(self, x: torch.Tensor, use_graph: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """x: fp32 [B, 3, S, S] on the engine's device -> (logits fp32 [B, ncls, S, S], labels uint8 [B, S, S]).
@@ -542,6 +558,8 @@ class ForwardEngine:
         B, Cc, S, S_ = x.shape
         if Cc != 3 or S != S_:
             raise ValueError("expected [B, 3, S, S]")
+        if x.device != self.device:
+            raise ValueError(f"input on {x.device}, engine on {self.device}")
         plan, bufs = self.get_plan(B, S)
         bufs["x"].copy_(x, non_blocking=True)
         return self.run_resident(B, S, use_graph)
@@ -550,18 +568,19 @@ class ForwardEngine:
         """Runs the (B, S) plan on whatever `get_plan(B, S)[1]["x"]` holds (a producer kernel, e.g. the sliding-window
         tile gather, wrote the batch there on the current stream)."""
         plan, bufs = self.get_plan(B, S)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        if use_graph:
-            key = (B, S)
-            g = self._graphs.get(key)
-            if g is None:
-                plan.run(stream)  # warm-up (cudaFuncSetAttribute etc. must happen outside capture)
-                torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    plan.run(torch.cuda.current_stream(self.device).cuda_stream)
-                self._graphs[key] = g
-            g.replay()
-        else:
-            plan.run(stream)
+        with torch.cuda.device(self.device):     # the model may live on a device that is not the process's current one
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            if use_graph:
+                key = (B, S)
+                g = self._graphs.get(key)
+                if g is None:
+                    plan.run(stream)  # warm-up (cudaFuncSetAttribute etc. must happen outside capture)
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        plan.run(torch.cuda.current_stream(self.device).cuda_stream)
+                    self._graphs[key] = g
+                g.replay()
+            else:
+                plan.run(stream)
         return bufs["logits"], bufs["labels"]

@@ -12,10 +12,17 @@ import torch
 
 
 class StreamedPredictor:
-    def __init__(self, net, use_graph: bool = True, want_labels: bool = False):
+    N_HOST = 3   # pinned host staging buffers: the one the caller holds, the one being filled, one in flight
+
+    def __init__(self, net, use_graph: bool = True, want_labels: bool = False, gatherer=None):
+        """`gatherer` (parallel.AsyncGatherer, optional): every batch's device result (labels if want_labels else logits)
+        is also submitted to it right after the forward — the multi-GPU step's one all-gather, on the device, before and
+        independent of the D2H copy of this rank's own shard."""
         self.net = net
         self.use_graph = use_graph
         self.want_labels = want_labels
+        self.gatherer = gatherer
+        self.tickets: List[int] = []
         self._dev = next(net.parameters()).device
         if self._dev.type != "cuda":
             raise RuntimeError("StreamedPredictor needs the model on a CUDA device (no CPU fallback)")
@@ -31,18 +38,21 @@ class StreamedPredictor:
         self._xin = [torch.empty((B, 3, H, W), dtype=torch.float32, device=self._dev) for _ in range(2)]
         odt, oshape = (torch.uint8, (B, H, W)) if self.want_labels else (torch.float32, (B, ncls, H, W))
         self._yout = [torch.empty(oshape, dtype=odt, device=self._dev) for _ in range(2)]
-        self._yhost = [torch.empty(oshape, dtype=odt).pin_memory() for _ in range(2)]
+        self._yhost = [torch.empty(oshape, dtype=odt).pin_memory() for _ in range(self.N_HOST)]
         self._ev_in = [torch.cuda.Event() for _ in range(2)]
         self._ev_out = [torch.cuda.Event() for _ in range(2)]
-        self._ev_host = [torch.cuda.Event() for _ in range(2)]
+        self._ev_dl = [torch.cuda.Event() for _ in range(2)]            # device slot s downloaded
+        self._ev_host = [torch.cuda.Event() for _ in range(self.N_HOST)]  # host buffer h filled
         self._ev_consumed = [torch.cuda.Event() for _ in range(2)]
         self._shape = tuple(x.shape)
 
     @torch.no_grad()
     def run(self, batches: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
         """`batches`: host tensors [B,3,H,W] fp32 (pinned for true overlap), all of one shape.  Yields, in order, the
-        host result of each batch (fp32 logits, or uint8 labels with want_labels=True).  A yielded tensor is a pinned
-        staging buffer that is reused two batches later — consume or copy it before advancing twice."""
+        host result of each batch (fp32 logits, or uint8 labels with want_labels=True).  A yielded tensor is one of
+        three pinned staging buffers: it stays intact while the generator is advanced ONCE more (so the caller may hold
+        result i-1 while fetching result i, e.g. to overlap post-processing) and is overwritten after the second
+        advance — copy it if it must live longer."""
         eng = self.net._get_engine(self._dev)
         cur = torch.cuda.current_stream(self._dev)
         pending: List[int] = []
@@ -61,17 +71,22 @@ class StreamedPredictor:
             # forward batch i on the caller's stream
             cur.wait_event(self._ev_in[s])
             if i >= 2:
-                cur.wait_event(self._ev_host[s])          # slot s of the device result was downloaded
+                cur.wait_event(self._ev_dl[s])            # slot s of the device result was downloaded
             logits, labels = eng.forward(self._xin[s], use_graph=self.use_graph)
             self._ev_consumed[s].record(cur)
-            self._yout[s].copy_(labels if self.want_labels else logits, non_blocking=True)
+            res = labels if self.want_labels else logits
+            if self.gatherer is not None:
+                self.tickets.append(self.gatherer.submit(res))
+            self._yout[s].copy_(res, non_blocking=True)
             self._ev_out[s].record(cur)
-            # download batch i
+            # download batch i into host buffer h (the caller may still hold buffer (i-2) % 3; (i-3) % 3 == h is released)
+            h = i % self.N_HOST
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(self._ev_out[s])
-                self._yhost[s].copy_(self._yout[s], non_blocking=True)
-                self._ev_host[s].record(self._d2h)
-            pending.append(s)
+                self._yhost[h].copy_(self._yout[s], non_blocking=True)
+                self._ev_dl[s].record(self._d2h)
+                self._ev_host[h].record(self._d2h)
+            pending.append(h)
             if len(pending) == 2:                         # hand out batch i-1 while batch i computes
                 p = pending.pop(0)
                 self._ev_host[p].synchronize()

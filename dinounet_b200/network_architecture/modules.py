@@ -540,6 +540,11 @@ class DinoUNet(nn.Module):
             n_conv_per_stage_decoder = list(n_conv_per_stage_decoder)[:3] if len(n_conv_per_stage_decoder) >= 3 else [2, 2, 2]
         self.num_classes = num_classes
         self.dinov3_model_name = dinov3_model_name
+        # what the kernels bake in (the planner's default block): checked when the engine is built
+        self._block_spec = dict(conv_op=conv_op, conv_bias=conv_bias, norm_op=norm_op, norm_op_kwargs=dict(norm_op_kwargs or {}),
+                                dropout_op=dropout_op, nonlin=nonlin, nonlin_kwargs=dict(nonlin_kwargs or {}),
+                                kernel_sizes=kernel_sizes, strides=strides,
+                                n_conv_per_stage_decoder=list(n_conv_per_stage_decoder or []), nonlin_first=nonlin_first)
         self.encoder = self._create_dinov3_encoder(dinov3_pretrained_path, dinov3_model_name, list(features_per_stage),
                                                    conv_op, norm_op, norm_op_kwargs, dropout_op, dropout_op_kwargs,
                                                    nonlin, nonlin_kwargs, conv_bias, adapter_type)
@@ -576,9 +581,39 @@ class DinoUNet(nn.Module):
         """Call after mutating parameters in place (e.g. an optimizer step) to refresh the packed kernel weights."""
         self._engine = None
 
+    def _check_block_spec(self):
+        """The conv blocks are compiled for Conv2d(3x3, bias) -> InstanceNorm2d(eps 1e-5, affine) -> LeakyReLU(0.01), two
+        per decoder stage: any other plan must fail loudly instead of silently computing the default block."""
+        sp = self._block_spec
+        bad = []
+        if sp["conv_op"] is not nn.Conv2d:
+            bad.append(f"conv_op={sp['conv_op']}")
+        if not sp["conv_bias"]:
+            bad.append("conv_bias=False")
+        if sp["norm_op"] is not nn.InstanceNorm2d:
+            bad.append(f"norm_op={sp['norm_op']}")
+        nk = sp["norm_op_kwargs"]
+        if abs(float(nk.get("eps", 1e-5)) - cfg.IN_EPS) > 1e-12 or not nk.get("affine", False) or nk.get("track_running_stats", False):
+            bad.append(f"norm_op_kwargs={nk}")
+        if sp["dropout_op"] is not None:
+            bad.append(f"dropout_op={sp['dropout_op']}")
+        if sp["nonlin"] is not nn.LeakyReLU or abs(float(sp["nonlin_kwargs"].get("negative_slope", 0.01)) - 0.01) > 1e-12:
+            bad.append(f"nonlin={sp['nonlin']} {sp['nonlin_kwargs']}")
+        if sp["nonlin_first"]:
+            bad.append("nonlin_first=True")
+        if list(sp["n_conv_per_stage_decoder"])[:3] != [2, 2, 2]:
+            bad.append(f"n_conv_per_stage_decoder={sp['n_conv_per_stage_decoder']}")
+        if sp["kernel_sizes"] is not None and any(tuple(k) != (3, 3) for k in sp["kernel_sizes"]):
+            bad.append(f"kernel_sizes={sp['kernel_sizes']}")
+        if bad:
+            raise NotImplementedError("dinounet_b200 kernels implement the planner's default block (Conv2d 3x3 + bias, "
+                                      "InstanceNorm2d(eps=1e-5, affine), LeakyReLU(0.01), 2 convs per decoder stage); "
+                                      "unsupported plan entries: " + "; ".join(bad))
+
     def _get_engine(self, device):
         from ..engine import ForwardEngine
         if self._engine is None or self._engine.device != device:
+            self._check_block_spec()
             sd = {k: t for k, t in self.state_dict().items() if not k.startswith("decoder.encoder.")}
             self._engine = ForwardEngine(self.dinov3_model_name, sd, self.num_classes, device, self.vit_dtype,
                                          self.rest_dtype, tuple(self.encoder.target_channels), self.attn_impl,

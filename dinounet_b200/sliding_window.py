@@ -67,6 +67,8 @@ def compute_gaussian(tile_size: Sequence[int], sigma_scale: float = 1. / 8, valu
     g = torch.from_numpy(g)
     g = (g / g.max() * value_scaling_factor).to(dtype).to(device)
     g[g == 0] = g[g != 0].min()          # the importance map must not contain zeros (:29-30)
+    while len(_GAUSSIAN_CACHE) >= 2:     # the reference keeps two (lru_cache(maxsize=2), sliding_window_prediction.py:10)
+        _GAUSSIAN_CACHE.pop(next(iter(_GAUSSIAN_CACHE)))
     _GAUSSIAN_CACHE[key] = g
     return g
 

@@ -419,7 +419,7 @@ def test_dwconv_three_planes_gelu():
 
 
 @pytest.mark.parametrize("impl", [0, 1, 2])
-@pytest.mark.parametrize("dh", [12, 24, 32])
+@pytest.mark.parametrize("dh", [12, 24, 32, 128])
 def test_msda_forward_matches_reference_sampling(dh, impl):
     """the op the reference itself pins in ops/test.py: CUDA sampling == grid_sample formulation."""
     lib = L.load()

@@ -4,9 +4,11 @@
   (c) the oracle run in the reference's own GPU precision regime (outer fp16 / inner bf16 autocast) with torch eager.
 
 Tolerances (stated, per the contract in BASELINE.json north_star and the noise floors in BASELINE.md section 5):
-  * 16-bit tier: max|dlogit| / max|logit| <= 3e-2 against the fp32 oracle.  The north_star figure (1e-3) is tighter than
-    the reference's OWN mixed-precision GPU forward achieves against fp32 (1.1e-2 measured in the survey, re-measured
-    here in (c)), so the binding assertion is: our error vs the fp32 truth <= 1.5 x the reference-regime error + 2e-3.
+  * 16-bit tier: max|dlogit| / max|logit| <= 1.2e-2 (bf16 ViT, the reference's inner autocast dtype) and <= 5e-3 (fp16
+    ViT) against the fp32 reference goldens = 1.4x the measured band (6.4-8.6e-3 / 3.4e-3).  The north_star figure
+    (1e-3) is tighter than the reference's OWN mixed-precision GPU forward achieves against fp32 (1.1e-2 measured in the
+    survey, re-measured here in (c)), so the second binding assertion is: our error vs the fp32 truth <= 1.5 x the
+    reference-regime error + 2e-3.  The fp32 tier (tests/test_gpu_fp32_tier.py) is the one held to 1e-5.
   * argmax masks: identical wherever the fp32 class margin exceeds 4x the measured max logit error; the flip count on
     all pixels is reported and must not exceed the reference-regime's own flip count by more than 25 %.
 """
@@ -32,7 +34,10 @@ def _net(model, sd, vit="bf16", rest="fp16", query="fp32"):
     return net.to("cuda").eval()
 
 
-def _compare(y, ref, ref_regime=None, name=""):
+TOL_BF16, TOL_FP16 = 1.2e-2, 5e-3
+
+
+def _compare(y, ref, ref_regime=None, name="", tol=TOL_BF16):
     y, ref = y.float().cpu(), ref.float().cpu()
     scale = ref.abs().max().item()
     err = (y - ref).abs().max().item() / scale
@@ -54,7 +59,7 @@ def _compare(y, ref, ref_regime=None, name=""):
         assert int(flips.sum()) <= 1.25 * int(flips_r.sum()) + 8, msg
     else:
         print(msg)
-    assert err <= 3e-2, msg
+    assert err <= tol, msg
     safe = margin > 4 * err * scale
     assert not (flips & safe).any(), msg
     return err
@@ -79,6 +84,40 @@ def test_forward_matches_oracle_and_golden(model, B, S, golden_dir):
     assert (labels.cpu().long() == y.argmax(1).cpu()).all()
 
 
+@pytest.mark.parametrize("model,B,S,xseed", [("dinounet_l", 2, 512, 3), ("dinounet_b", 1, 512, 4), ("dinounet_s", 4, 512, 5)])
+def test_forward_benchmarked_shapes_match_reference(model, B, S, xseed, golden_dir):
+    """The configurations bench.py / BASELINE.json quote (512^2; dinounet_l at B >= 2 so that batch strides, the 9 query
+    tiles of N = 1029 tokens and the CTA-pair GEMMs at M = B*1029 are exercised): every pixel against the oracle run
+    live on the host cores (bit-identical to the reference), the subsampled logits and the full argmax mask against the
+    golden written by the REAL reference (oracle/make_golden.py BENCH_CASES)."""
+    sd = O.make_state_dict(model, 2, seed=0)
+    x = O.make_input(B, S, xseed)
+    net = _net(model, sd)
+    with torch.no_grad():
+        y = net(x.cuda()).float().cpu()
+        y_graph, lab = net._engine.forward(x.cuda(), use_graph=True)
+        y_graph, lab = y_graph.float().cpu(), lab.cpu()
+    g = np.load(os.path.join(golden_dir, f"{model}_b{B}_s{S}_w0_x{xseed}.npz"))
+    sub = int(g["sub"])
+    gs = torch.from_numpy(g["logits_sub"])
+    scale = float(g["absmax"])
+    err_g = (y[:, :, ::sub, ::sub] - gs).abs().max().item() / scale
+    ref = O.forward(sd, model, x)
+    assert torch.equal(ref[:, :, ::sub, ::sub], gs), "live oracle != committed reference golden"
+    gmask = torch.from_numpy(np.unpackbits(g["argmax_bits"])[: B * S * S].reshape(B, S, S).astype(np.int64))
+    assert torch.equal(ref.argmax(1), gmask)
+    err = _compare(y, ref, None, f"{model} B{B} S{S} (bench shape) vs oracle==reference")
+    print(f"  golden(reference) subsample 1/{sub}: rel err {err_g:.3e}; full: {err:.3e}")
+    assert err_g <= err + 1e-9
+    assert torch.equal(y_graph, y), "CUDA-graph replay differs from eager launches at the bench shape"
+    assert torch.equal(lab.long(), y.argmax(1))
+    for b in range(B):     # batch items are independent: item b alone gives the same logits bit for bit
+        if B > 1 and b in (0, B - 1):
+            with torch.no_grad():
+                yb = net(x[b:b + 1].cuda()).float().cpu()
+            assert torch.equal(yb, y[b:b + 1]), f"batch item {b} depends on its neighbours"
+
+
 @pytest.mark.parametrize("ncls", [5, 14])
 def test_forward_multiclass_matches_oracle(ncls):
     """More than two segmentation heads (the plans' label set decides; nnUNetTrainer.py:201-208): logits and argmax
@@ -101,7 +140,7 @@ def test_forward_multiclass_matches_oracle(ncls):
     flips = int((y.argmax(1).cpu() != ref.argmax(1)).sum())
     flips_r = int((regime.argmax(1) != ref.argmax(1)).sum())
     print(f"{ncls} classes: rel err {err:.3e} (reference regime {err_r:.3e}), flips {flips} (regime {flips_r}) / {ref[:, 0].numel()}")
-    assert y.shape == (1, ncls, 256, 256) and torch.isfinite(y).all() and err < 3e-2
+    assert y.shape == (1, ncls, 256, 256) and torch.isfinite(y).all() and err < TOL_BF16
     if torch.isfinite(regime).all():       # the reference's own fp16 regime overflows on some synthetic weight sets
         assert err <= 1.5 * err_r + 2e-3 and flips <= 1.25 * flips_r + 8
     else:
@@ -136,8 +175,7 @@ def test_forward_512_golden_and_fp16_vit(golden_dir):
         y = _net(model, sd)(x.cuda())
         y16 = _net(model, sd, vit="fp16")(x.cuda())
     _compare(y, golden, None, "s 512 bf16-vit vs golden")
-    e16 = _compare(y16, golden, None, "s 512 fp16-vit vs golden")
-    assert e16 <= 1.5e-2
+    _compare(y16, golden, None, "s 512 fp16-vit vs golden", tol=TOL_FP16)
 
 
 def test_intermediate_stages_match_oracle():
@@ -169,7 +207,7 @@ def test_intermediate_stages_match_oracle():
     for name, got, ref in checks:
         e = ((got.float() - ref).abs().max() / ref.abs().max()).item()
         print(f"  stage {name}: rel err {e:.3e}")
-        if not e < 4e-2:
+        if not e < (1.2e-2 if name.startswith("vit_tap") else 2e-2):
             bad.append((name, e))
     assert not bad, bad
 
@@ -211,6 +249,14 @@ def test_streamed_predictor_matches_direct_forward():
         direct = [net(x.cuda()).cpu() for x in xs]
     outs = [y.clone() for y in StreamedPredictor(net).run(xs)]
     assert len(outs) == 5 and all(torch.equal(a, b) for a, b in zip(outs, direct))
+    # the documented lifetime: a yielded buffer survives ONE further advance (hold result i-1 while fetching i)
+    held, prev = [], None
+    for y in StreamedPredictor(net).run(xs):
+        if prev is not None:
+            held.append(prev.clone())       # read the previous result only after the generator advanced once more
+        prev = y
+    held.append(prev.clone())
+    assert all(torch.equal(a, b) for a, b in zip(held, direct))
     labs = [y.clone() for y in StreamedPredictor(net, want_labels=True).run(xs)]
     assert all(torch.equal(l.long(), d.argmax(1)) for l, d in zip(labs, direct))
 

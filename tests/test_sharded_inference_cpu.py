@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dinounet_b200.parallel import gather_logits, shard_bounds, sharded_forward, sharded_sliding_window
+from dinounet_b200.parallel import AsyncGatherer, gather_logits, shard_bounds, sharded_forward, sharded_sliding_window
 
 
 def test_shard_bounds_cover_batch_exactly():
@@ -36,6 +36,14 @@ def _worker(rank, world, port, B, q):
         ok = torch.equal(full, _fake_forward(x))
         lo, hi = shard_bounds(B, world, rank)
         ok = ok and torch.equal(gather_logits(_fake_forward(x[lo:hi]), B), _fake_forward(x))
+        ok = ok and torch.equal(gather_logits(_fake_forward(x[lo:hi]), B, dtype=torch.float16), _fake_forward(x).half())
+        if B % world == 0:     # the side-stream gatherer (synchronous on CPU/gloo): fp16 logits and uint8 label maps
+            ag, al = AsyncGatherer(B, x.device, torch.float16), AsyncGatherer(B, x.device, torch.uint8)
+            for _ in range(3):
+                t = ag.submit(_fake_forward(x[lo:hi]))
+                tl = al.submit(_fake_forward(x[lo:hi]).argmax(1).to(torch.uint8))
+            ok = ok and torch.equal(ag.result(t), _fake_forward(x).half())
+            ok = ok and torch.equal(al.result(tl), _fake_forward(x).argmax(1).to(torch.uint8))
         q.put((rank, bool(ok), tuple(full.shape)))
     finally:
         dist.destroy_process_group()
