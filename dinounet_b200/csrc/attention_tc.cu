@@ -18,19 +18,9 @@
 #include "../../include/dinounet_b200.h"
 #include "host_util.h"
 #include "gemm_common.h"
+#include "attention_common.h"
 
 namespace b2u {
-
-struct alignas(64) AttnMaps {
-  CUtensorMap q, k, vt;
-};
-struct AttnArgs {
-  int BH, heads, ntok, npairs, nchunks;
-  int q_begin;   // first query row handled by this launch (rows [q_begin, ntok)); keys always span [0, ntok)
-  long long items;
-  float scale_log2e;
-  void* out;
-};
 
 // Per-head-dim configuration.  HD = 64 (ViT-S/B/L): two query-tile groups per CTA, 4-stage K/V ring.
 // HD = 128 (ViT-7B): one group (the fp32 O accumulator needs 128 registers per thread), 2-stage ring.
@@ -46,27 +36,6 @@ template <int HD, int SPLIT = 1> struct AtCfg {
   static constexpr int kXchgBytes = SPLIT > 1 ? 2 * 128 * 4 * 4 : 0;   // [2 groups][128 rows][4] fp32 exchange slots
   static constexpr int kSmem = kGroups * (kQBytes + kPBytes) + kStages * (kKBytes + kVBytes) + 1024 + 256 + kXchgBytes;
 };
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void sts128a(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint4 lds128a(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
-  return r;
-}
-__device__ __forceinline__ float ex2(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 
 template <typename T, int HD, int SPLIT>
 __global__ void __launch_bounds__(AtCfg<HD, SPLIT>::kThreads, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
@@ -594,7 +563,9 @@ static int attention_tc_impl(const void* q, const void* k, const void* vt, void*
   a.q_begin = q_begin;
   a.nchunks = (ntok + 127) / 128;
   const int groups = head_dim == 64 ? 2 : 1;
-  a.npairs = ((ntok - q_begin + 127) / 128 + groups - 1) / groups;
+  const int ntiles = (ntok - q_begin + 127) / 128;
+  a.npairs = (ntiles + groups - 1) / groups;
+  a.pairs_full = ntiles / groups;
   a.items = static_cast<long long>(a.BH) * a.npairs;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.out = out;
@@ -603,7 +574,10 @@ static int attention_tc_impl(const void* q, const void* k, const void* vt, void*
   if ((rc = make_map_3d(&maps.q, q, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
   if ((rc = make_map_3d(&maps.k, k, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
   if ((rc = make_map_3d(&maps.vt, vt, dtype, npad, hd, BH, npad, static_cast<uint64_t>(npad) * hd, 64, static_cast<uint32_t>(head_dim)))) return rc;
-  // option 4 (B2U_OPT_ATTN_SPLIT) = 1: one softmax warp per (query tile, TMEM lane quarter) instead of two (A/B switch)
+  // default: third-generation kernel (attention_tc3.cu).  option 4 = 2: second-generation kernel (A/B switch);
+  // option 4 = 1: second generation with one softmax warp per (query tile, TMEM lane quarter)
+  // option 4 = 3: third generation with the single-pass softmax (64 live scores; head_dim 128 always uses it)
+  if (get_option(4) == 0 || get_option(4) == 3) return attention_tc3_dispatch(maps, a, head_dim, dtype, get_option(4) == 3, stream);
   if (get_option(4) == 1) {
     if (head_dim == 64)
       return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 64, 1>(maps, a, stream) : launch_attn_tc<__half, 64, 1>(maps, a, stream);

@@ -276,6 +276,32 @@ def test_attention_tcgen05(dtype, B, Hh, N):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("hd", [64, 128])
+@pytest.mark.parametrize("N", [1029, 300, 144, 129])
+def test_attention_tcgen05_lazy_rescale_and_narrow_tail(hd, N):
+    """Scores that keep growing along the key axis (|k| ramps up 5x) force the lazily updated running maximum to move
+    by more than 2^8 several times -> the in-TMEM O rescale path; N = 1029 / 300 / 144 / 129 give last key chunks of
+    5 / 44 / 16 / 1 valid keys (MMA widths 16 / 48 / 16 / 16) and partially / fully dead query-row quarters."""
+    lib = L.load()
+    dtype, td = L.BF16, torch.bfloat16
+    B, Hh = 2, 2
+    q, k, v = (_rand(B, Hh, N, hd, dt=torch.float32, seed=10 + s) for s in range(3))
+    k = k * (1.0 + 4.0 * torch.arange(N, device=DEV, dtype=torch.float32) / N)[None, None, :, None]
+    q, k, v = q.to(td), k.to(td), v.to(td)
+    npad = (N + 7) // 8 * 8
+    vt = torch.zeros(B, Hh, hd, npad, device=DEV, dtype=td)
+    vt[..., :N] = v.transpose(2, 3)
+    out = torch.full((B, N, Hh * hd), float("nan"), device=DEV, dtype=td)
+    if hd == 64:
+        L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out), B, Hh, N, npad, 0, hd ** -0.5, dtype, stream()), "attn")
+    else:
+        L.check(lib.b2u_attention_tc_hd(P(q), P(k), P(vt), P(out), B, Hh, N, npad, hd, hd ** -0.5, dtype, stream()), "attn")
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, Hh * hd)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 2 ** -6, rel_err(out, ref)
+
+
 @pytest.mark.parametrize("dtype", [L.BF16, L.F16])
 @pytest.mark.parametrize("B,Hh,N", [(1, 2, 1029), (2, 3, 261), (1, 1, 128)])
 def test_attention_tcgen05_head_dim_128(dtype, B, Hh, N):
