@@ -571,13 +571,17 @@ static int attention_tc_impl(const void* q, const void* k, const void* vt, void*
   a.out = out;
   int rc;
   const uint64_t BH = static_cast<uint64_t>(a.BH), hd = static_cast<uint64_t>(head_dim);
+  // option 4 (A/B switch): 0 = third generation (default; 128-key chunks, 1.5-pass softmax), 4 = its single-pass softmax,
+  // 5 = fourth generation (64-key chunks, double-buffered S and P: measured slower), 2 / 1 = second generation
+  const int gen = get_option(4);
+  const uint32_t kc = gen == 5 ? 64u : 128u;
+  if (gen == 5) a.nchunks = (ntok + 63) / 64;
   if ((rc = make_map_3d(&maps.q, q, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
-  if ((rc = make_map_3d(&maps.k, k, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
+  if ((rc = make_map_3d(&maps.k, k, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, kc))) return rc;
   if ((rc = make_map_3d(&maps.vt, vt, dtype, npad, hd, BH, npad, static_cast<uint64_t>(npad) * hd, 64, static_cast<uint32_t>(head_dim)))) return rc;
-  // default: third-generation kernel (attention_tc3.cu).  option 4 = 2: second-generation kernel (A/B switch);
-  // option 4 = 1: second generation with one softmax warp per (query tile, TMEM lane quarter)
-  // option 4 = 3: third generation with the single-pass softmax (64 live scores; head_dim 128 always uses it)
-  if (get_option(4) == 0 || get_option(4) == 3) return attention_tc3_dispatch(maps, a, head_dim, dtype, get_option(4) == 3, stream);
+  // (option 4 = 1: second generation with one softmax warp per (query tile, TMEM lane quarter))
+  if (gen == 5) return attention_tc4_dispatch(maps, a, head_dim, dtype, stream);
+  if (gen == 0 || gen == 4) return attention_tc3_dispatch(maps, a, head_dim, dtype, gen == 4, stream);
   if (get_option(4) == 1) {
     if (head_dim == 64)
       return dtype == B2U_BF16 ? launch_attn_tc<__nv_bfloat16, 64, 1>(maps, a, stream) : launch_attn_tc<__half, 64, 1>(maps, a, stream);

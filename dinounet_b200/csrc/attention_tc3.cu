@@ -42,8 +42,8 @@ template <int HD> struct At3Cfg {
   static constexpr int kPBytes = 2 * 128 * 128;             // two key blocks of [128 rows x 64 keys]
   static constexpr int kKBytes = 128 * HD * 2;
   static constexpr int kVBytes = 2 * HD * 128;              // two key blocks of [HD rows x 64 keys]
-  static constexpr int kCtrlWarps = 2;                      // TMA producer, MMA issuer
-  // 18 warps (head_dim 64) -> 112 registers per thread: 64 scores + state fit without spills (19-20 warps compile to 96)
+  static constexpr int kCtrlWarps = 4;                      // TMA producer, MMA issuer A, MMA issuer B, (idle)
+  // 20 warps compile to 96 registers per thread (registers are allocated per 4-warp granule: 65536 / 640)
   static constexpr int kThreads = kCtrlWarps * 32 + kGroups * 128 * kSplit;
   static constexpr int kXchgBytes = 2 * 128 * 4 * 4;        // [2 groups][128 rows][4] fp32 exchange slots
   static constexpr int kGroupCols = 128 + HD;               // S | O
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
       mbar_init(&s_full[g], 1); mbar_init(&s_free[g], kArr);
       mbar_init(&p_full[g], kArr); mbar_init(&o_full[g], 1); mbar_init(&o_free[g], kArr);
     }
-    for (int s = 0; s < 4; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], NG); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -320,83 +320,74 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread, event loop over both query-tile groups) =====================
-    // Each group has two in-order action streams, S(0..J-1) and PV(0..J-1); an action is issued as soon as its barriers
-    // allow it (non-blocking mbarrier.test_wait polls), so group B's S never queues behind a wait for group A's P.
+  } else if (warp <= NG) {
+    // ===================== MMA issuer of group g (one thread per group, warps 1 and 2) =====================
+    // In-order stream per group: S(0), then per chunk j: S(j+1) (its conditions - K chunk j+1 landed, S(j) read by the
+    // softmax warps - come true before P(j) is complete), PV(j).  (A single thread polling both groups added its polling
+    // period to every hand-over.)
     if (lane == 0) {
+      const int g = warp - 1;
       constexpr uint32_t idesc_s = make_idesc_f16(TT::kFmt, 128, 128);
       constexpr uint32_t idesc_o = make_idesc_f16(TT::kFmt, 128, HD);
       const uint32_t idesc_s_tail = make_idesc_f16(TT::kFmt, 128, tail_n);
-      uint32_t c0 = 0;                        // K/V chunks consumed before this item (ring position = chunk % NST)
-      uint32_t n_s[2] = {0, 0}, n_p[2] = {0, 0}, n_items[2] = {0, 0}, qcnt[2] = {0, 0};
+      const uint32_t tS = tmem_base + g * CF::kGroupCols;
+      int st_s = 0, st_p = 0;                 // ring position of the next S chunk / the next PV chunk
+      uint32_t ph_s = 0, ph_p = 0;
+      uint32_t n_s = 0, n_p = 0, n_items = 0, qcnt = 0;
+      auto issue_s = [&](bool last) {
+        mbar_wait(&kv_full[st_s], ph_s);
+        mbar_wait(&s_free[g], (n_s & 1) ^ 1);                // the softmax warps have read the previous S
+        ++n_s;
+        tc_fence_after();
+        const uint32_t idesc = last ? idesc_s_tail : idesc_s;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t da = make_desc_k128(smem_u32(sQ + g * CF::kQBytes + kb * (128 * 128)));
+          const uint64_t db = make_desc_k128(smem_u32(sK + st_s * CF::kKBytes + kb * (128 * 128)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tS, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[g]);
+        if (last) tc_commit(&q_free[g]);                     // no later MMA of this item reads Q
+        if (++st_s == NST) { st_s = 0; ph_s ^= 1; }
+      };
       for (long long item = blockIdx.x; item < args.items; item += gridDim.x) {
         const ItemDec d = decode_item<NG>(item, args);
-        for (int g = 0; g < d.nq; ++g) { mbar_wait(&q_full[g], qcnt[g] & 1); ++qcnt[g]; }
-        int js[2] = {0, 0}, jp[2] = {0, 0};
-        int rel = 0;                          // chunks of this item whose K/V stage has been released
-        int remaining = d.nq * 2 * J;
-        while (remaining > 0) {
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            if (g >= d.nq) continue;
-            const uint32_t tS = tmem_base + g * CF::kGroupCols;
-            if (js[g] < J) {
-              const uint32_t cs = c0 + js[g];
-              const int st = cs % NST;
-              if (mbar_test(&kv_full[st], (cs / NST) & 1) && mbar_test(&s_free[g], (n_s[g] & 1) ^ 1)) {
-                // K chunk js is in smem and the softmax warps have read the previous S into registers
-                ++n_s[g];
-                tc_fence_after();
-                const bool last = js[g] + 1 == J;
-                const uint32_t idesc = last ? idesc_s_tail : idesc_s;
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                  const uint64_t da = make_desc_k128(smem_u32(sQ + g * CF::kQBytes + kb * (128 * 128)));
-                  const uint64_t db = make_desc_k128(smem_u32(sK + st * CF::kKBytes + kb * (128 * 128)));
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    tc_mma_f16(tS, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                }
-                tc_commit(&s_full[g]);
-                if (last) tc_commit(&q_free[g]);                 // no later MMA of this item reads Q
-                ++js[g];
-                --remaining;
-              }
-            }
-            if (jp[g] < js[g]) {
-              // P_g(jp) is in smem; the first PV of an item overwrites O: the previous item's O must have been read out
-              if (mbar_test(&p_full[g], n_p[g] & 1) && (jp[g] > 0 || mbar_test(&o_free[g], (n_items[g] & 1) ^ 1))) {
-                ++n_p[g];
-                tc_fence_after();
-                const uint32_t cp = c0 + jp[g];
-                const int st = cp % NST;
-                const int nk = (jp[g] + 1 == J) ? (tail_n >> 4) : 8;     // K = 16 steps of this chunk
-                for (int t = 0; t < nk; ++t) {
-                  const int kb = t >> 2, k = t & 3;
-                  const uint64_t da = make_desc_k128(smem_u32(sP + g * CF::kPBytes + kb * 128 * 128));
-                  const uint64_t db = make_desc_k128(smem_u32(sV + st * CF::kVBytes + kb * HD * 128));
-                  tc_mma_f16(tS + 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_o, (jp[g] | t) != 0 ? 1u : 0u);
-                }
-                tc_commit(&o_full[g]);
-                ++jp[g];
-                --remaining;
-                // a K/V stage is free once every group's PV of that chunk has been issued (the commit covers all MMAs
-                // issued by this thread so far)
-                const int done = d.nq == 2 ? (jp[0] < jp[1] ? jp[0] : jp[1]) : jp[0];
-                while (rel < done) {
-                  tc_commit(&kv_empty[(c0 + rel) % NST]);
-                  ++rel;
-                }
-              }
-            }
+        if (g >= d.nq) {
+          // this group sits the item out, but the K/V ring counts one release per group and stage
+          for (int j = 0; j < J; ++j) {
+            mbar_wait(&kv_full[st_p], ph_p);
+            tc_commit(&kv_empty[st_p]);
+            if (++st_p == NST) { st_p = 0; ph_p ^= 1; }
           }
+          st_s = st_p; ph_s = ph_p;
+          continue;
         }
-        for (int g = 0; g < d.nq; ++g) ++n_items[g];
-        c0 += J;
+        mbar_wait(&q_full[g], qcnt & 1);
+        ++qcnt;
+        issue_s(J == 1);
+        for (int j = 0; j < J; ++j) {
+          if (j + 1 < J) issue_s(j + 2 == J);
+          mbar_wait(&p_full[g], n_p & 1);                    // P_g(j) is in smem
+          ++n_p;
+          if (j == 0) mbar_wait(&o_free[g], (n_items & 1) ^ 1);   // the previous item's O has been read out
+          tc_fence_after();
+          const int nk = (j + 1 == J) ? (tail_n >> 4) : 8;    // K = 16 steps of this chunk
+          for (int t = 0; t < nk; ++t) {
+            const int kb = t >> 2, k = t & 3;
+            const uint64_t da = make_desc_k128(smem_u32(sP + g * CF::kPBytes + kb * 128 * 128));
+            const uint64_t db = make_desc_k128(smem_u32(sV + st_p * CF::kVBytes + kb * HD * 128));
+            tc_mma_f16(tS + 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_o, (j | t) != 0 ? 1u : 0u);
+          }
+          tc_commit(&o_full[g]);
+          tc_commit(&kv_empty[st_p]);
+          if (++st_p == NST) { st_p = 0; ph_p ^= 1; }
+        }
+        ++n_items;
       }
     }
-  } else {
+  } else if (warp >= CF::kCtrlWarps) {
     // ===================== softmax / output warps =====================
     const int set = (warp - CF::kCtrlWarps) >> 2;
     const int g = set / SPLIT;              // query tile of the pair
