@@ -57,7 +57,7 @@ class Plan:
 class ForwardEngine:
     def __init__(self, variant: str, params: Dict[str, torch.Tensor], num_classes: int, device: torch.device,
                  vit_dtype: str = "bf16", rest_dtype: str = "fp16", features=(32, 64, 128, 256),
-                 attn_impl: str = "tc", query_dtype: str = "fp32"):
+                 attn_impl: str = "tc", query_dtype: str = "fp32", precision: str = "16"):
         if variant not in cfg.VARIANTS:
             raise ValueError(f"Unknown model: {variant}")
         self.v = cfg.VARIANTS[variant]
@@ -71,8 +71,17 @@ class ForwardEngine:
         self.lib = L.load()
         self.device = device
         self.ncls = int(num_classes)
+        # precision "16" (default): bf16/fp16 tensor-core path.  "fp32": the parity tier of engine_fp32.py / csrc/fp32_tier.cu
+        # (plain fp32 SIMT kernels, same layouts and packing with dtype float32; held to 1e-5 against the reference's fp32
+        # forward, not benchmarked).
+        if precision not in ("16", "fp32"):
+            raise ValueError("precision must be '16' or 'fp32'")
+        self.precision = precision
         self.vt, self.rt = _CODE[vit_dtype], _CODE[rest_dtype]
-        self.tv, self.tr = _TORCH16[self.vt], _TORCH16[self.rt]
+        if precision == "fp32":
+            self.tv = self.tr = torch.float32
+        else:
+            self.tv, self.tr = _TORCH16[self.vt], _TORCH16[self.rt]
         self.features = tuple(features)
         self.attn_impl = attn_impl   # "tc" = tcgen05/TMEM kernel (default), "mma" = first-generation mma.sync kernel
         # The adapter's query stream c [B, 5376, D] (dinov3_adapter.py:210-231).  "fp32" (default) = the reference's dtype
@@ -88,6 +97,8 @@ class ForwardEngine:
         self._plans: "OrderedDict[Tuple[int, int], Tuple[Plan, dict]]" = OrderedDict()
         self._graphs: Dict[Tuple[int, int], object] = {}
         self.max_plans = 4
+        if self.device.type != "cuda":
+            raise L.NativeLibraryError("dinounet_b200 runs on CUDA devices only (no CPU fallback)")
         with torch.cuda.device(self.device):
             self.pack(params)
 
@@ -155,6 +166,8 @@ class ForwardEngine:
         S = A + "spm."
         w["stem0.w"] = f32(P[S + "stem.0.weight"])
         w["stem0.sc"], w["stem0.sh"] = self._bn_fold(P, S + "stem.1")
+        if self.precision == "fp32":
+            w["stem0.w3"] = self._conv3(P[S + "stem.0.weight"], torch.float32)
         for name, conv, bn in (("stem3", "stem.3", "stem.4"), ("stem6", "stem.6", "stem.7"), ("conv2", "conv2.0", "conv2.1"),
                                ("conv3", "conv3.0", "conv3.1"), ("conv4", "conv4.0", "conv4.1")):
             w[name + ".w"] = self._conv3(P[S + conv + ".weight"], tr)
@@ -542,7 +555,11 @@ class ForwardEngine:
             old, _ = self._plans.popitem(last=False)
             self._graphs.pop(old, None)
         with torch.cuda.device(self.device):                   # kernels, TMA maps and num_sms() use the current device
-            self._plans[key] = self.build_plan(B, S)
+            if self.precision == "fp32":
+                from .engine_fp32 import build_plan_fp32
+                self._plans[key] = build_plan_fp32(self, B, S)
+            else:
+                self._plans[key] = self.build_plan(B, S)
         return self._plans[key]
 
     def clear_plans(self):

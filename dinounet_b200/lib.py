@@ -52,6 +52,23 @@ class QkvParams(C.Structure):
     ]
 
 
+class F32GemmParams(C.Structure):
+    """b2u_f32_gemm_params (fp32 parity tier)."""
+    _fields_ = [
+        ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("a_rows_in", C.c_int32), ("a_rows_out", C.c_int32), ("a_row_off", C.c_int32),
+        ("W", C.c_void_p), ("ldw", C.c_int64),
+        ("conv", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("C", C.c_int32), ("Cpad", C.c_int32),
+        ("out", C.c_void_p), ("ldc", C.c_int64), ("col_off", C.c_int32),
+        ("rows_in", C.c_int32), ("rows_out", C.c_int32), ("row_off", C.c_int32),
+        ("ps_cout", C.c_int32), ("ps_h", C.c_int32), ("ps_w", C.c_int32),
+        ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("act1", C.c_int32), ("act2", C.c_int32),
+        ("residual", C.c_void_p), ("ldres", C.c_int64),
+    ]
+
+
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/dinounet_b200.h one to one
@@ -89,6 +106,19 @@ SIGNATURES = {
     "b2u_se_apply": [vp, vp, i64, vp, vp, i32, i32, i32, i32, vp],
     "b2u_seg_head": [vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "b2u_zero": [vp, i64, vp],
+    "b2u_f32_gemm": [C.POINTER(F32GemmParams), vp],
+    "b2u_f32_layernorm": [vp, vp, vp, vp, i64, i32, f32, i32, i32, i32, vp],
+    "b2u_f32_patchify": [vp, vp, i32, i32, vp],
+    "b2u_f32_nchw_to_nhwc": [vp, vp, i32, i32, i64, vp],
+    "b2u_f32_seg_out": [vp, vp, vp, i32, i64, i32, vp],
+    "b2u_f32_maxpool3x3s2": [vp, vp, i32, i32, i32, i32, vp],
+    "b2u_f32_dwconv3x3": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "b2u_f32_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp],
+    "b2u_f32_msda": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "b2u_f32_instnorm": [vp, i64, vp, i64, vp, vp, i32, i64, i32, f32, i32, vp],
+    "b2u_f32_se": [vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],
+    "b2u_f32_film": [vp, vp, vp, i64, i32, vp],
+    "b2u_f32_tail": [vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "b2u_set_option": [i32, i32],
     "b2u_last_error": [],
     "b2u_version": [],

@@ -497,6 +497,9 @@ class DinoUNet(nn.Module):
     #: adapter query stream c: "fp32" = the reference's dtype under autocast (default), "16" = rest_dtype with 16-bit
     #: residual updates (opt-in: +4 % throughput, slightly below the reference's precision for that one tensor)
     query_dtype = "fp32"
+    #: "16" = the bf16/fp16 tensor-core kernels (default, benchmarked); "fp32" = the fp32 parity tier (plain SIMT kernels,
+    #: within 1e-5 of the reference's fp32 forward; set before the first forward or call repack())
+    precision = "16"
 
     def __init__(self, network_config: dict = None, input_channels: int = None, num_classes: int = None,
                  dinov3_pretrained_path: str = "dinounet/checkpoints/dinov3_vits16_pretrain_lvd1689m-08c60483.pth",
@@ -617,7 +620,7 @@ class DinoUNet(nn.Module):
             sd = {k: t for k, t in self.state_dict().items() if not k.startswith("decoder.encoder.")}
             self._engine = ForwardEngine(self.dinov3_model_name, sd, self.num_classes, device, self.vit_dtype,
                                          self.rest_dtype, tuple(self.encoder.target_channels), self.attn_impl,
-                                         getattr(self, "query_dtype", "fp32"))
+                                         getattr(self, "query_dtype", "fp32"), getattr(self, "precision", "16"))
         return self._engine
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -279,6 +279,57 @@ int b2u_zero(void* ptr, int64_t bytes, b2u_stream_t stream);
 /* key 4 (B2U_OPT_ATTN_SPLIT): 0 = two softmax warps per (query tile, TMEM lane quarter), each owning half of the key
  * columns / head dims (default), 1 = one warp. */
 enum { B2U_OPT_GEMM_IMPL = 0, B2U_OPT_MSDA_IMPL = 1, B2U_OPT_CONV_HALO = 2, B2U_OPT_GEMM_PAIR = 3, B2U_OPT_ATTN_SPLIT = 4 };
+/* ---------------------------------------------------------------------------------------------------------------
+ * fp32 parity tier (csrc/fp32_tier.cu): the same forward in IEEE fp32 with plain SIMT kernels, selected by
+ * `DinoUNet.precision = "fp32"`.  It is the path held to north_star's 1e-5 against the reference's fp32 (CPU) forward;
+ * it is not the benchmarked path.  All tensors fp32, same layouts as above (tokens [rows, C], images NHWC).
+ * Epilogue of b2u_f32_gemm (same meaning as b2u_epilogue): v = acc + bias[n]; v = act1(v); v = v*scale[n] + shift[n];
+ * v = act2(v); v += residual[orow, ocol]; out[orow, ocol] = v.  conv != 0: A is an NHWC image, W is [N, 9*Cpad].
+ * A-row remap (a_rows_in > 0): arow = (m / a_rows_in) * a_rows_out + a_row_off + m % a_rows_in. */
+typedef struct b2u_f32_gemm_params {
+  int64_t M;
+  int32_t N, K;
+  const float* A;
+  int64_t lda;
+  int32_t a_rows_in, a_rows_out, a_row_off;
+  const float* W;
+  int64_t ldw;
+  int32_t conv, Hin, Win, C, Cpad;
+  float* out;
+  int64_t ldc;
+  int32_t col_off;
+  int32_t rows_in, rows_out, row_off;
+  int32_t ps_cout, ps_h, ps_w;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int32_t act1, act2;
+  const float* residual;
+  int64_t ldres;
+} b2u_f32_gemm_params;
+int b2u_f32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream);   /* F.linear / Conv2d 1x1, 3x3 / ConvTranspose2d k2 s2 */
+/* F.layer_norm; input row = (r / out_per_b) * in_per_b + in_off + r % out_per_b when in_per_b > 0 (ViT taps drop the prefix) */
+int b2u_f32_layernorm(const float* in, float* out, const float* w, const float* b, int64_t rows, int32_t D, float eps,
+                      int32_t in_per_b, int32_t out_per_b, int32_t in_off, b2u_stream_t stream);
+int b2u_f32_patchify(const float* x_nchw, float* rows768, int32_t B, int32_t S, b2u_stream_t stream);   /* patch_embed.py:64-76 */
+int b2u_f32_nchw_to_nhwc(const float* x, float* out, int32_t B, int32_t C, int64_t HW, b2u_stream_t stream);
+int b2u_f32_seg_out(const float* lin, float* logits_nchw, uint8_t* labels, int32_t B, int64_t HW, int32_t ncls, b2u_stream_t stream);
+int b2u_f32_maxpool3x3s2(const float* in, float* out, int32_t B, int32_t H, int32_t W, int32_t C, b2u_stream_t stream);
+int b2u_f32_dwconv3x3(const float* in, float* out, const float* w9, const float* bias, int32_t B, int32_t H, int32_t W,
+                      int32_t C, int32_t planes, int32_t act, b2u_stream_t stream);              /* dinov3_adapter.py:99-109 */
+/* attention.py:66-118 on the fused qkv rows [B*N, 3D]: RoPE on tokens >= prefix, exact softmax, fp32 */
+int b2u_f32_attention(const float* qkv, const float* rope_sin, const float* rope_cos, float* out, int32_t B, int32_t N,
+                      int32_t heads, int32_t head_dim, int32_t prefix, float scale, b2u_stream_t stream);
+int b2u_f32_msda(const float* value, const float* offaw, float* out, int32_t B, int32_t Hv, int32_t Wv, int32_t heads,
+                 int32_t dh, b2u_stream_t stream);                                                 /* ms_deform_attn.py:158-216 */
+int b2u_f32_instnorm(const float* in, int64_t ld_in, float* out, int64_t ld_out, const float* w, const float* b, int32_t B,
+                     int64_t HW, int32_t C, float eps, int32_t lrelu, b2u_stream_t stream);
+int b2u_f32_se(const float* t, const float* shortcut, int64_t ld_shortcut, float* pooled_work, const float* w1, const float* b1,
+               const float* w2, const float* b2, float* out, int32_t B, int64_t HW, int32_t C, int32_t hidden, b2u_stream_t stream);
+int b2u_f32_film(const float* gamma_beta, const float* zs_zp, float* z, int64_t px, int32_t R, b2u_stream_t stream);
+int b2u_f32_tail(const float* c, int64_t c_rows_per_b, int64_t c_off, const float* tap, float* out, const float* bn_scale,
+                 const float* bn_shift, int32_t B, int32_t r, int32_t h, int32_t D, b2u_stream_t stream);   /* dinov3_adapter.py:468-482 */
+
 int b2u_set_option(int32_t key, int32_t value);
 
 const char* b2u_last_error(void);
