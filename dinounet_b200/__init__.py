@@ -9,10 +9,11 @@ from . import config  # noqa: F401
 from .network_architecture import DinoUNet, DINOv3EncoderAdapter, FAPM, UNetDecoder, DINOv3_Adapter, MSDeformAttn  # noqa: F401
 from .training import (  # noqa: F401
     DinoUNetTrainer, DinoUNetTrainer_s, DinoUNetTrainer_b, DinoUNetTrainer_l, DinoUNetTrainer_7b, DINOV3_TRAINERS,
-    get_dinov3_trainer,
+    get_dinov3_trainer, install_discoverable_trainers,
 )
 
 __version__ = "0.1.0"
 from .sliding_window import SlidingWindowPredictor, compute_gaussian, compute_steps_for_sliding_window  # noqa: F401,E402
 from .inference import StreamedPredictor  # noqa: F401,E402
 from .checkpoint import load_network_weights  # noqa: F401,E402
+from .export import labels_to_original_geometry  # noqa: F401,E402

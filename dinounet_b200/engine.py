@@ -39,13 +39,14 @@ class Plan:
     def __init__(self):
         self.calls: List[Tuple[str, object, tuple]] = []
         self.keep: list = []
+        self.vit_end = 0        # calls[:vit_end] = the frozen ViT (patch embed .. taps); calls[vit_end:] = adapter/FAPM/decoder
 
     def add(self, name: str, fn, *args):
         self.calls.append((name, fn, args))
 
-    def run(self, stream: int):
+    def run(self, stream: int, start: int = 0, end: Optional[int] = None):
         s = C.c_void_p(stream)
-        for name, fn, args in self.calls:
+        for name, fn, args in self.calls[start:end]:
             rc = fn(*args, s)
             if rc != 0:
                 raise L.NativeLibraryError(f"{name} failed (rc={rc}): {L.last_error()}")
@@ -360,6 +361,8 @@ class ForwardEngine:
                          B * P, D, cfg.LN_EPS_VIT, N, P, cfg.N_PREFIX, 1, vt)
                 tap_k += 1
 
+        plan.vit_end = len(plan.calls)     # everything above depends only on the input image and the FROZEN backbone
+
         # ================= SPM (dinov3_adapter.py:279-302) =================
         S2, S4, S8, S16, S32 = S // 2, S // 4, S // 8, S // 16, S // 32
         sA = buf("spmA", (B * S2 * S2, 64), tr)
@@ -553,7 +556,8 @@ class ForwardEngine:
             return self._plans[key]
         while len(self._plans) >= max(1, self.max_plans):      # evict the least recently used buffer set + graph
             old, _ = self._plans.popitem(last=False)
-            self._graphs.pop(old, None)
+            for gk in [k for k in self._graphs if k[:2] == old]:
+                self._graphs.pop(gk)
         with torch.cuda.device(self.device):                   # kernels, TMA maps and num_sms() use the current device
             if self.precision == "fp32":
                 from .engine_fp32 import build_plan_fp32
@@ -581,23 +585,48 @@ class ForwardEngine:
         bufs["x"].copy_(x, non_blocking=True)
         return self.run_resident(B, S, use_graph)
 
-    def run_resident(self, B: int, S: int, use_graph: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    def run_resident(self, B: int, S: int, use_graph: bool = False, part: str = "all") -> Tuple[torch.Tensor, torch.Tensor]:
         """Runs the (B, S) plan on whatever `get_plan(B, S)[1]["x"]` holds (a producer kernel, e.g. the sliding-window
-        tile gather, wrote the batch there on the current stream)."""
+        tile gather, wrote the batch there on the current stream).  part: "all", "vit" (patch embed .. ViT taps only) or
+        "rest" (everything after the taps: SPM, extractors, FAPM, decoder - on whatever the tap buffers hold)."""
         plan, bufs = self.get_plan(B, S)
+        lo, hi = {"all": (0, None), "vit": (0, plan.vit_end), "rest": (plan.vit_end, None)}[part]
         with torch.cuda.device(self.device):     # the model may live on a device that is not the process's current one
             stream = torch.cuda.current_stream(self.device).cuda_stream
             if use_graph:
-                key = (B, S)
+                key = (B, S, part)
                 g = self._graphs.get(key)
                 if g is None:
-                    plan.run(stream)  # warm-up (cudaFuncSetAttribute etc. must happen outside capture)
+                    plan.run(stream, lo, hi)  # warm-up (cudaFuncSetAttribute etc. must happen outside capture)
                     torch.cuda.synchronize(self.device)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        plan.run(torch.cuda.current_stream(self.device).cuda_stream)
+                        plan.run(torch.cuda.current_stream(self.device).cuda_stream, lo, hi)
                     self._graphs[key] = g
                 g.replay()
             else:
-                plan.run(stream)
+                plan.run(stream, lo, hi)
         return bufs["logits"], bufs["labels"]
+
+    # ------------------------------------------------------------------ frozen-ViT feature caching (SURVEY.md 8f rank 3)
+    def extract_vit_features(self, x: torch.Tensor, use_graph: bool = False) -> List[torch.Tensor]:
+        """The four tapped, final-LayerNorm'ed ViT outputs [B, P, D] (fp32) of the FROZEN backbone
+        (dinov3_adapter.py:422-426: `with torch.no_grad()` around get_intermediate_layers).  In eval mode they depend only
+        on the image, so a caller that sees a sample repeatedly (every training epoch, every mirrored / overlapping
+        sliding-window pass over the same tile) may cache them and skip 57-88 % of the forward FLOPs with
+        `forward_from_vit_features`.  Returns fresh tensors (not the engine's buffers)."""
+        B, _, S, _ = x.shape
+        plan, bufs = self.get_plan(B, S)
+        bufs["x"].copy_(x, non_blocking=True)
+        self.run_resident(B, S, use_graph, part="vit")
+        P = (S // 16) ** 2
+        return [bufs[f"tap{k}"].view(B, P, -1).clone() for k in range(4)]
+
+    def forward_from_vit_features(self, x: torch.Tensor, feats: List[torch.Tensor], use_graph: bool = False):
+        """Everything after the backbone (SPM needs the image, the extractors need the cached taps)."""
+        B, _, S, _ = x.shape
+        plan, bufs = self.get_plan(B, S)
+        bufs["x"].copy_(x, non_blocking=True)
+        for k in range(4):
+            bufs[f"tap{k}"].view(feats[k].shape).copy_(feats[k], non_blocking=True)
+        return self.run_resident(B, S, use_graph, part="rest")

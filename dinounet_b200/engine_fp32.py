@@ -103,6 +103,8 @@ def build_plan_fp32(eng, B: int, S: int):
             ln(f"tap{tap_k}", X, taps[tap_k], "norm.w", "norm.b", B * P, cfg.LN_EPS_VIT, (N, P, cfg.N_PREFIX))
             tap_k += 1
 
+    plan.vit_end = len(plan.calls)
+
     # ================= SPM (dinov3_adapter.py:279-302) =================
     S2, S4, S8, S16, S32 = S // 2, S // 4, S // 8, S // 16, S // 32
     xh = buf("x_nhwc", (B * S * S, 3))

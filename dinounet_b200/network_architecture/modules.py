@@ -646,6 +646,29 @@ class DinoUNet(nn.Module):
         _, labels = self._get_engine(x.device).forward(x)
         return labels.clone()
 
+    # ---- frozen-backbone feature caching --------------------------------------------
+    def _three_channels(self, x: torch.Tensor) -> torch.Tensor:
+        Cc = x.shape[1]
+        if Cc == 1:                       # dinounet_training.py:491-497
+            x = x.repeat(1, 3, 1, 1)
+        elif Cc != 3:
+            x = x.repeat(1, 3 // Cc + (1 if 3 % Cc != 0 else 0), 1, 1)[:, :3] if Cc < 3 else x[:, :3]
+        return x.float().contiguous()
+
+    @torch.no_grad()
+    def extract_vit_features(self, x: torch.Tensor):
+        """The frozen DINOv3 backbone's four tapped token maps [B, P, D] for `x` (eval mode: a pure function of the image,
+        dinov3_adapter.py:422-426) - cache them per sample and feed `forward_from_vit_features` to skip the ViT."""
+        x = self._three_channels(x)
+        return self._get_engine(x.device).extract_vit_features(x)
+
+    @torch.no_grad()
+    def forward_from_vit_features(self, x: torch.Tensor, feats) -> torch.Tensor:
+        """Logits from the image plus cached backbone features: runs only SPM + extractors + FAPM + decoder."""
+        x = self._three_channels(x)
+        logits, _ = self._get_engine(x.device).forward_from_vit_features(x, feats)
+        return logits.clone()
+
     def compute_conv_feature_map_size(self, input_size):
         assert len(input_size) == 2, "just give the image size without color/feature channels or batch channel. " \
                                      "Do not give input_size=(b, c, x, y(, z)). Give input_size=(x, y(, z))!"

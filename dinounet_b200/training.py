@@ -102,6 +102,39 @@ DINOV3_TRAINERS = {"dinounet_s": DinoUNetTrainer_s, "dinounet_b": DinoUNetTraine
                    "dinounet_7b": DinoUNetTrainer_7b}
 
 
+_DISCOVERABLE_STUB = '''"""Makes the B200-native Dino U-Net trainers visible to nnU-Net's name-based trainer lookup.
+
+`recursive_find_python_class` (dinounet/utilities/find_class_by_name.py:7-24) walks dinounet/training/nnUNetTrainer/*.py;
+the reference's own `DinoUNetTrainer_*` classes live in the top-level script dinounet_training.py and are therefore
+invisible to `get_trainer_from_args` (run/run_training.py:39-47) and to the standalone predictor
+(`nnUNetPredictor.initialize_from_trained_model_folder`, predict_from_raw_data.py:99-100).  This file is written by
+`dinounet_b200.training.install_discoverable_trainers()`.
+"""
+from dinounet_b200.training import (DinoUNetTrainer, DinoUNetTrainer_s, DinoUNetTrainer_b, DinoUNetTrainer_l,  # noqa: F401
+                                    DinoUNetTrainer_7b)
+'''
+
+
+def install_discoverable_trainers(dinounet_package_dir: str = None, filename: str = "DinoUNetTrainer_b200.py") -> str:
+    """Writes a one-import module into `<dinounet>/training/nnUNetTrainer/` so that the reference's filesystem-based class
+    lookup (find_class_by_name.py:7-24) finds `DinoUNetTrainer_s/_b/_l/_7b` by name - what the standalone predictor and
+    `nnUNetv2_train -tr DinoUNetTrainer_l` need (SURVEY.md section 8a, quirk list).  Returns the path written."""
+    import os
+    if dinounet_package_dir is None:
+        import importlib.util
+        spec = importlib.util.find_spec("dinounet")
+        if spec is None or not spec.submodule_search_locations:
+            raise ModuleNotFoundError("the reference package `dinounet` is not importable; pass its directory")
+        dinounet_package_dir = list(spec.submodule_search_locations)[0]
+    target = os.path.join(dinounet_package_dir, "training", "nnUNetTrainer")
+    if not os.path.isdir(target):
+        raise FileNotFoundError(f"{target} does not exist (not a dinounet package directory?)")
+    path = os.path.join(target, filename)
+    with open(path, "w") as f:
+        f.write(_DISCOVERABLE_STUB)
+    return path
+
+
 def get_dinov3_trainer(model_name: str):
     if model_name not in DINOV3_TRAINERS:
         raise ValueError(f"Unsupported model: {model_name}. Supported models: {list(DINOV3_TRAINERS)}")

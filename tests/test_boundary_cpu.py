@@ -35,7 +35,8 @@ def test_struct_layouts_match_header(tmp_path):
     """ctypes mirrors vs the real C layout: compile a probe against the header with gcc and compare every offset."""
     import ctypes as C
     import subprocess
-    structs = {"b2u_epilogue": lib.Epilogue, "b2u_gemm_params": lib.GemmParams, "b2u_qkv_params": lib.QkvParams}
+    structs = {"b2u_epilogue": lib.Epilogue, "b2u_gemm_params": lib.GemmParams, "b2u_qkv_params": lib.QkvParams,
+               "b2u_f32_gemm_params": lib.F32GemmParams}
     lines = []
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -151,3 +152,47 @@ def test_engine_rejects_unsupported_patch_sizes_with_a_clear_error():
     for S in (96, 160, 384, 500):
         with pytest.raises(ValueError, match="power of two"):
             ForwardEngine.build_plan(eng, 1, S)
+
+
+def test_discoverable_trainer_stub_is_found_by_the_reference_lookup(tmp_path):
+    """find_class_by_name.py:7-24 walks <pkg>/training/nnUNetTrainer/*.py with pkgutil + importlib: the stub written by
+    install_discoverable_trainers must expose the trainer classes there by name (restated lookup, same mechanism)."""
+    import importlib
+    import pkgutil
+    import sys
+    import dinounet_b200
+    pkg = tmp_path / "fakeunet"
+    tdir = pkg / "training" / "nnUNetTrainer"
+    tdir.mkdir(parents=True)
+    for d in (pkg, pkg / "training", tdir):
+        (d / "__init__.py").write_text("")
+    path = dinounet_b200.install_discoverable_trainers(str(pkg))
+    assert path.endswith("DinoUNetTrainer_b200.py")
+    sys.path.insert(0, str(tmp_path))
+    try:
+        found = None
+        for _, modname, ispkg in pkgutil.iter_modules([str(tdir)]):     # == recursive_find_python_class
+            if not ispkg:
+                m = importlib.import_module("fakeunet.training.nnUNetTrainer." + modname)
+                if hasattr(m, "DinoUNetTrainer_l"):
+                    found = getattr(m, "DinoUNetTrainer_l")
+        assert found is dinounet_b200.DinoUNetTrainer_l
+    finally:
+        sys.path.remove(str(tmp_path))
+
+
+def test_label_export_reverts_cropping_and_transpose():
+    """export_prediction.py:43-52 on GPU-side label maps."""
+    import numpy as np
+    from dinounet_b200.export import labels_to_original_geometry, needs_resampling
+    rng = np.random.default_rng(0)
+    labels = rng.integers(0, 3, size=(4, 6, 5)).astype(np.uint8)
+    props = {"shape_after_cropping_and_before_resampling": (4, 6, 5), "shape_before_cropping": (7, 9, 8),
+             "bbox_used_for_cropping": [[2, 6], [1, 7], [3, 8]]}
+    seg = labels_to_original_geometry(torch.from_numpy(labels), props, (2, 0, 1), 2)
+    ref = np.zeros((7, 9, 8), np.uint8)
+    ref[2:6, 1:7, 3:8] = labels
+    assert seg.dtype == np.uint8 and np.array_equal(seg, ref.transpose(2, 0, 1))
+    assert needs_resampling((4, 6, 4), props)
+    with pytest.raises(ValueError):
+        labels_to_original_geometry(labels[:, :, :4], props, (0, 1, 2))

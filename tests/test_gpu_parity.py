@@ -285,3 +285,24 @@ def test_7b_recipe_forward_matches_reference_golden(golden_dir):
         _compare(y, golden, regime, "7b-recipe tiny B1 S256 vs golden(reference)")
     finally:
         cfgmod.VARIANTS.pop(name, None)
+
+
+def test_frozen_vit_feature_caching_is_bit_identical():
+    """the tapped ViT outputs depend only on the image (frozen backbone, eval mode): caching them and
+    running only SPM + extractors + FAPM + decoder must reproduce the full forward bit for bit."""
+    model = "dinounet_s"
+    sd = O.make_state_dict(model, 2, seed=0)
+    net = _net(model, sd)
+    x = O.make_input(2, 256, 21).cuda()
+    with torch.no_grad():
+        y = net(x)
+        feats = net.extract_vit_features(x)
+        n0 = lib.launch_count()
+        y2 = net.forward_from_vit_features(x, feats)
+        n_rest = lib.launch_count() - n0
+        other = net(O.make_input(2, 256, 22).cuda())      # overwrite the engine's tap buffers in between
+        y3 = net.forward_from_vit_features(x, [f.clone() for f in feats])
+    assert len(feats) == 4 and feats[0].shape == (2, 256, 384) and feats[0].dtype == torch.float32
+    assert torch.equal(y2, y) and torch.equal(y3, y) and not torch.equal(other, y)
+    plan, _ = net._engine.get_plan(2, 256)
+    assert n_rest == len(plan.calls) - plan.vit_end and plan.vit_end > 0.3 * len(plan.calls)
