@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t kv_phase = 0;
       uint32_t qfree_cnt[2] = {0, 0};
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
     // In-order stream per group: S(0), then per chunk j: S(j+1) (its conditions - K chunk j+1 landed, S(j) read by the
     // softmax warps - come true before P(j) is complete), PV(j).  (A single thread polling both groups added its polling
     // period to every hand-over.)
-    if (lane == 0) {
+    if (elect_one()) {
       const int g = warp - 1;
       constexpr uint32_t idesc_s = make_idesc_f16(TT::kFmt, 128, 128);
       constexpr uint32_t idesc_o = make_idesc_f16(TT::kFmt, 128, HD);

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(At4Cfg<HD>::kThreads, 1) attn_tc4_kernel(const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t kv_phase = 0;
       uint32_t qfree_cnt[2] = {0, 0};
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(At4Cfg<HD>::kThreads, 1) attn_tc4_kernel(const
     // was measured to be the bottleneck at 64-key chunks (35 % of the softmax stall samples waiting for S).
     // Chunk j uses S / P buffer j & 1; every per-buffer barrier advances one phase per use and cannot run two phases ahead
     // of its waiter (a buffer is re-armed only after its previous use has been consumed): parity waits are unambiguous.
-    if (lane == 0) {
+    if (elect_one()) {
       const int g = warp - 1;
       constexpr uint32_t idesc_s = make_idesc_f16(TT::kFmt, 128, KC);
       constexpr uint32_t idesc_o = make_idesc_f16(TT::kFmt, 128, HD);

@@ -83,6 +83,22 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// One elected lane of a fully converged warp (PTX elect.sync).  Unlike `lane == 0`, the compiler KNOWS that exactly one
+// thread executes the guarded region, so uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) are emitted straight
+// instead of inside an ELECT / BRA.U.ANY waterfall loop each (about 8 extra SASS instructions per tcgen05.mma, which made
+// the single MMA-issuer thread the bottleneck of the small-N convolution tiles).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA (cp.async.bulk.tensor)
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -224,6 +240,16 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// same, with an explicit stride between 8-row groups (a window into a wider swizzled tile: one group per tile row)
+__device__ __forceinline__ uint64_t make_desc_k128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;

@@ -21,10 +21,17 @@
 
 namespace b2u {
 
-constexpr int kHaloW = 130;                           // 128 output pixels + 1 halo pixel on each side
-constexpr int kHaloBytes = 3 * kHaloW * 128;           // one TMA box: 3 rows x 130 px x 64 ch x 2 B
-constexpr int kHaloStageBytes = 49 * 1024;             // box rounded up to the 1024 B swizzle period
-constexpr int kHaloPrefetch = 6;                       // L2 prefetch distance of the halo boxes, in tiles of one CTA
+// Halo-reuse 3x3 mode: an output tile is 16 rows x 8 pixels (= 128 MMA rows); ONE TMA box of 18 rows x 10 px x 64 ch feeds
+// all 9 taps.  Read amplification L2 -> SM is 180 / 128 = 1.4x.  (Round 1 used 1 row x 128 px tiles with a 3 x 130 halo:
+// 3.05x, and ncu showed that kernel bound by exactly that L2 -> SM traffic: 40 % of the stall samples were the epilogue
+// warps waiting for an accumulator, L2 hit rate 57 %, DRAM 26 %.)  The A operand of tap (dy, dx) is the shifted window
+// starting at halo pixel (dy, dx): 16 groups of 8 consecutive pixels, group stride = one halo row = 10 x 128 B - which is
+// what the descriptor's stride-byte-offset expresses (1280 instead of the dense 1024).
+constexpr int kHaloW = 10;                             // 8 output pixels + 1 halo pixel on each side
+constexpr int kHaloH = 18;                             // 16 output rows + 1 halo row above and below
+constexpr int kHaloBytes = kHaloH * kHaloW * 128;      // one TMA box: 18 rows x 10 px x 64 ch x 2 B = 23040 B
+constexpr int kHaloStageBytes = 23 * 1024;             // box rounded up to the 1024 B swizzle period
+constexpr int kHaloPrefetch = 8;                       // L2 prefetch distance of the halo boxes, in tiles of one CTA
 
 constexpr int kRopeBytes = 128 * 32 * 2 * 4;   // (rope_h + rope_w <= 128) rows x <=32 angles x {sin, cos} fp32
 
@@ -42,7 +49,7 @@ template <int BN, int EPI = 0, bool PAIR = false> struct Cfg2 {
   static constexpr int kBiasBytes = BN * 4;
   static constexpr int kRope = EPI == 2 ? kRopeBytes : 0;   // (EPI 3 reuses s_bias only)
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + kRope + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kHaloStages = BN <= 32 ? 3 : 2;
+  static constexpr int kHaloStages = BN <= 32 ? 6 : 5;
   static constexpr int kSmemHalo = kHaloStages * kHaloStageBytes + 9 * kBBytes + kStagingBytes + kBiasBytes + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       if (halo) {   // the 9 weight taps stay resident in smem for the whole kernel (n_tiles == 1)
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
               tma_prefetch_4d(&maps.a[0], 0, (rf % args.tiles_x) * args.TW - 1, (rf / args.tiles_x) * args.TH - 1, imgf);
             }
           }
-          // one TMA box per tile: channels [0,64) x pixels [x0-1, x0+129) x rows [y0-1, y0+2) (OOB = zero padding)
+          // one TMA box per tile: channels [0,64) x pixels [x0-1, x0+9) x rows [y0-1, y0+17) (OOB = zero padding)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kHaloBytes);
           tma_load_4d(smem + stage * stage_bytes, &maps.a[0], &full_bar[stage], 0, x0 - 1, y0 - 1, img);
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(TT::kFmt, PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -285,14 +292,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           tc_fence_after();
           const uint32_t sH = smem_u32(smem + stage * stage_bytes);
           const uint32_t sW = smem_u32(s_wtaps);
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {       // fully unrolled: every descriptor is base + compile-time constant
             const int dy = tap / 3, dx = tap - dy * 3;
-            // A = 128 consecutive pixels of halo row dy starting at pixel dx: a shifted window of the swizzled halo tile.
+            // A = the 16 x 8 pixel window of the halo tile that starts at halo pixel (dy, dx): 8-pixel groups, one per halo row.
             // Its start is only 128 B-aligned; measured on B200 (tools/halo_probe.py): the 128B swizzle is a function of the
             // absolute smem address, so the descriptor needs NO base_offset (setting it to (addr>>7)&7 gives wrong data).
             const uint32_t aaddr = sH + (dy * kHaloW + dx) * 128;
-            const uint64_t da = make_desc_k128(aaddr);
+            const uint64_t da = make_desc_k128_sbo(aaddr, kHaloW * 128);
             const uint64_t db = make_desc_k128(sW + tap * C::kBBytes);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)

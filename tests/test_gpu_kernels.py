@@ -179,28 +179,30 @@ def test_conv3x3_implicit_gemm(gemm_impl, stride, cin, cout, hw, B):
     assert rel_err(got, ref2) < 3e-3, rel_err(got, ref2)
 
 
-@pytest.mark.parametrize("cin,cout,hw,B", [(64, 32, 256, 1), (64, 64, 128, 2), (32, 32, 256, 1), (64, 64, 256, 1)])
-def test_conv3x3_halo_mode_matches_per_tap_walk(cin, cout, hw, B):
-    """Halo-reuse conv (one 3x130-px TMA box per tile, 9 shifted descriptor windows) == per-tap TMA walk, bit for bit."""
+@pytest.mark.parametrize("cin,cout,hh,ww,B", [(64, 32, 256, 256, 1), (64, 64, 128, 128, 2), (32, 32, 256, 256, 1),
+                                              (64, 64, 256, 256, 1), (64, 64, 24, 32, 3), (32, 64, 40, 16, 1)])
+def test_conv3x3_halo_mode_matches_per_tap_walk(cin, cout, hh, ww, B):
+    """Halo-reuse conv (one 18x10-px TMA box per 16x8 output tile, 9 shifted descriptor windows with a 1280 B group stride)
+    == per-tap TMA walk, bit for bit; the 24- and 40-row images end in partial tiles."""
     lib = L.load()
     dtype, td = L.F16, torch.float16
-    x = _rand(B, hw, hw, cin, dt=td)
+    x = _rand(B, hh, ww, cin, dt=td)
     w = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=1)
     bias = _rand(cout, seed=2)
     outs = {}
     for opt in (1, 0):
         lib.b2u_set_option(2, opt)
         try:
-            out = torch.full((B * hw * hw, cout), float("nan"), device=DEV, dtype=td)
+            out = torch.full((B * hh * ww, cout), float("nan"), device=DEV, dtype=td)
             gemm(x.view(-1, cin), _pack_conv(w, td), out, dtype, M=0, K=9 * cin, lda=cin, bias=bias, conv=L.CONV3X3_S1,
-                 img=(B, hw, hw, cin))
+                 img=(B, hh, ww, cin))
             torch.cuda.synchronize()
             outs[opt] = out
         finally:
             lib.b2u_set_option(2, 0)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(td).float(), bias, stride=1, padding=1)
     for opt, out in outs.items():
-        got = out.view(B, hw, hw, cout).permute(0, 3, 1, 2).float()
+        got = out.view(B, hh, ww, cout).permute(0, 3, 1, 2).float()
         assert torch.isfinite(got).all(), opt
         assert rel_err(got, ref) < 2e-3, (opt, rel_err(got, ref))
     assert torch.equal(outs[0], outs[1])
