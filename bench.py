@@ -35,8 +35,6 @@ def parse():
     ap.add_argument("--query-dtype", default="fp32", choices=["16", "fp32"],
                     help="adapter query stream storage: fp32 = the reference's dtype (default), 16 = opt-in reduced storage")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--gemm-impl", default="v2", choices=["v1", "v2"])
-    ap.add_argument("--attn-impl", default="tc", choices=["tc", "mma"])
     ap.add_argument("--gemm-pair", default="on", choices=["on", "off"], help="CTA-pair (cta_group::2) GEMM tiles (A/B switch)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="patches in the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--eager-steps", type=int, default=10, help="timed steps of the torch-eager CUDA arm at N=1 (0 = skip)")
@@ -108,6 +106,74 @@ def cpu_forward_patches_per_s(model, size, n_patches, threads=None):
         O.forward(sd, model, O.make_input(1, size, i + 1))
     dt = time.perf_counter() - t0
     return n_patches / dt, threads, dt
+
+
+class SyntheticParams(dict):
+    """Reference-keyed random parameters generated ON THE DEVICE, tensor by tensor, when the engine packs them (same shapes
+    and per-kind magnitudes as oracle.make_state_dict; values differ).  Only for the 7B benchmark line: materialising its
+    6.95 B fp32 parameters in host memory once per rank (8 x 28 GB) is what this avoids; throughput does not depend on the
+    weight values."""
+
+    def __init__(self, model, num_classes, device):
+        super().__init__()
+        import torch
+        from oracle import dinounet_oracle as O
+        self._spec = {k: (shape, kind) for k, shape, kind in O.param_spec(model, num_classes)}
+        self._dev, self._torch, self._O = device, torch, O
+
+    def __contains__(self, k):
+        return k in self._spec
+
+    def get(self, k, default=None):
+        return self[k] if k in self._spec else default
+
+    def __getitem__(self, k):
+        import math
+        import zlib
+        torch = self._torch
+        shape, kind = self._spec[k]
+        g = torch.Generator(device=self._dev).manual_seed(zlib.crc32(k.encode()) & 0x7FFFFFFF)
+        rn = lambda: torch.randn(*shape, generator=g, device=self._dev, dtype=torch.float32)
+        ru = lambda lo, hi: torch.rand(*shape, generator=g, device=self._dev, dtype=torch.float32) * (hi - lo) + lo
+        if kind in ("w", "w_off"):
+            return rn() / math.sqrt(max(1, math.prod(shape[1:]) if kind == "w" else shape[1]))
+        if kind == "wT":
+            return rn() / math.sqrt(shape[0])
+        if kind in ("b", "b_off"):
+            return rn() * 0.05
+        if kind in ("nw",):
+            return ru(0.8, 1.2)
+        if kind in ("nb", "rm"):
+            return rn() * 0.1
+        if kind == "rv":
+            return ru(0.5, 1.5)
+        if kind == "ls":
+            return ru(0.25, 0.75)
+        if kind == "tok":
+            return rn() * 0.5
+        if kind == "bias_mask":
+            D = shape[0] // 3
+            return torch.cat([torch.ones(D), torch.zeros(D), torch.ones(D)]).to(self._dev)
+        if kind == "periods":
+            d4 = shape[0]
+            return (100.0 ** (2 * torch.arange(d4, dtype=torch.float32) / (2 * d4))).to(self._dev)
+        if kind == "nbt":
+            return torch.zeros((), dtype=torch.int64, device=self._dev)
+        return torch.zeros(*shape, device=self._dev)
+
+
+class _EngineNet:
+    """What StreamedPredictor needs from a network, around a bare ForwardEngine (7B line: no host-side nn.Module)."""
+
+    def __init__(self, eng, dev):
+        import torch
+        self._eng, self._p = eng, torch.zeros(1, device=dev)
+
+    def parameters(self):
+        yield self._p
+
+    def _get_engine(self, dev):
+        return self._eng
 
 
 def run_reference(a):
@@ -212,17 +278,21 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    lib.load().b2u_set_option(0, 1 if a.gemm_impl == "v1" else 0)
     lib.load().b2u_set_option(3, 1 if a.gemm_pair == "off" else 0)
 
     B, S, K, W = a.batch, a.size, a.steps, max(3, a.warmup)
-    sd = O.make_state_dict(a.model, 2, seed=0)
-    net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, a.model)
-    net.load_state_dict(sd, strict=True)
-    net.vit_dtype, net.rest_dtype, net.attn_impl, net.query_dtype = a.vit_dtype, a.rest_dtype, a.attn_impl, a.query_dtype
-    net = net.to(dev).eval()
-    del sd
-    eng = net._get_engine(dev)
+    if a.model == "dinounet_7b":
+        from dinounet_b200.engine import ForwardEngine
+        eng = ForwardEngine(a.model, SyntheticParams(a.model, 2, dev), 2, dev, a.vit_dtype, a.rest_dtype, query_dtype=a.query_dtype)
+        net = _EngineNet(eng, dev)
+    else:
+        sd = O.make_state_dict(a.model, 2, seed=0)
+        net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, a.model)
+        net.load_state_dict(sd, strict=True)
+        net.vit_dtype, net.rest_dtype, net.query_dtype = a.vit_dtype, a.rest_dtype, a.query_dtype
+        net = net.to(dev).eval()
+        del sd
+        eng = net._get_engine(dev)
     plan, bufs = eng.get_plan(B, S)
     n_kernels = len(plan.calls)
     # three resident input batches (3 x 100 MB at B=32 > 126 MB L2) rotated between steps; the per-step activation
@@ -367,7 +437,7 @@ def main():
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": f"{a.vit_dtype} (ViT GEMMs/attention) + {a.rest_dtype} (adapter/FAPM/decoder), fp32 accumulate/residuals",
             "data": "synthetic", "impl": "b200",
-            "config": {"workload": f"{a.model} forward, {S}x{S}x3, per-GPU batch {B}, random-init weights (seed 0)",
+            "config": {"workload": f"{a.model} forward, {S}x{S}x3, per-GPU batch {B}, random-init weights" + (" (generated on device)" if a.model == "dinounet_7b" else " (seed 0)"),
                        "global_batch": B * world, "parallelism": f"batch-sharded dp{world} + 1 NCCL all-gather of fp16 logits per step (side stream, double-buffered)" if world > 1 else "single GPU",
                        "l2": "3 resident input batches rotated (3x%.0f MB) and a per-step activation working set >> 126 MB L2" % (B * 3 * S * S * 4 / 1e6),
                        "cuda_graph": use_graph},

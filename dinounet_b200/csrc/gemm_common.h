@@ -1,4 +1,4 @@
-// Shared between the GEMM kernel generations (gemm_tc.cu: v1 one-tile-per-CTA, gemm_tc2.cu: v2 persistent).
+// Shared between the GEMM host API (gemm_api.cu) and the persistent tcgen05 kernel family (gemm_tc2.cu).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -39,7 +39,6 @@ struct GemmArgs {
 };
 
 int num_sms();
-int gemm_v1_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
 int gemm_v2_dispatch_bf16(bool qkv, int bn, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
 int gemm_v2_dispatch_f16(bool qkv, int bn, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream);
 inline int gemm_v2_dispatch(bool qkv, int bn, int dtype, const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {

@@ -65,8 +65,9 @@ class ForwardEngine:
         self.hd = self.v.embed_dim // self.v.num_heads
         if self.hd not in (64, 128) or self.v.ffn_layer not in ("mlp", "swiglu64"):
             raise NotImplementedError(f"{variant}: kernels exist for head_dim 64/128 and mlp / swiglu64 FFNs")
-        if self.hd == 128 and attn_impl != "tc":
-            raise NotImplementedError("head_dim 128 needs the tcgen05 attention kernel (attn_impl='tc')")
+        if attn_impl != "tc":
+            raise NotImplementedError("the only attention kernel is the tcgen05 / TMEM one (attn_impl='tc'); the first-generation "
+                                      "mma.sync kernel was removed in round 2")
         if tuple(features) != (32, 64, 128, 256):
             raise NotImplementedError("kernels are built for the planner's features_per_stage=(32,64,128,256)")
         self.lib = L.load()
@@ -84,7 +85,7 @@ class ForwardEngine:
         else:
             self.tv, self.tr = _TORCH16[self.vt], _TORCH16[self.rt]
         self.features = tuple(features)
-        self.attn_impl = attn_impl   # "tc" = tcgen05/TMEM kernel (default), "mma" = first-generation mma.sync kernel
+        self.attn_impl = attn_impl   # "tc" = tcgen05/TMEM kernel
         # The adapter's query stream c [B, 5376, D] (dinov3_adapter.py:210-231).  "fp32" (default) = the reference's dtype
         # under autocast: the 16-bit SPM outputs are promoted to fp32 by `c + level_embed` (fp32 parameter) and stay fp32
         # through `query + attn`.  "16" = opt-in: stored in rest_dtype, every residual update rounded to 16 bits (half the
@@ -304,10 +305,8 @@ class ForwardEngine:
         npad = (N + 7) // 8 * 8
         hd = self.hd
         Q, K_ = buf("Q", (B, Hh, N, hd), tv), buf("K", (B, Hh, N, hd), tv)
-        if self.attn_impl == "tc":   # V^T with zeroed padding columns (never written by the QKV epilogue)
-            V = bufs["V"] = torch.zeros((B, Hh, hd, npad), dtype=tv, device=dev)
-        else:
-            V = buf("V", (B, Hh, N, hd), tv)
+        # V^T with zeroed padding columns (never written by the QKV epilogue)
+        V = bufs["V"] = torch.zeros((B, Hh, hd, npad), dtype=tv, device=dev)
         O = buf("O", (T, D), tv)
         Hid = buf("Hid", (T, v.ffn_hidden), tv)
         taps = [buf(f"tap{k}", (B * P, D), torch.float32) for k in range(4)]
@@ -328,22 +327,18 @@ class ForwardEngine:
             qp.bias = _ptr(w.get(f"b{i}.qkvb"))
             qp.rope_sin, qp.rope_cos = _ptr(sin), _ptr(cos)
             qp.q, qp.k, qp.v, qp.dtype = _ptr(Q), _ptr(K_), _ptr(V), vt
-            qp.v_transposed, qp.npad = (1, npad) if self.attn_impl == "tc" else (0, 0)
+            qp.v_transposed, qp.npad = 1, npad
             qp.rope_w = h
             plan.keep.append(qp)
             plan.add(f"b{i}.qkv", lib.b2u_qkv_rope, C.byref(qp))
-            if self.attn_impl == "tc":
-                # one launch over all ntok query rows.  (Splitting off the 5 cls/storage rows so that the 1024 patch rows fill
-                # whole tile pairs was measured: tcgen05 part 370 -> 326 us/layer, but the few-row kernel costs more than
-                # the 45 us it saves, so q_begin stays 0; b2u_attention_rows remains available.)
-                if hd == 64:
-                    plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 0,
-                             hd ** -0.5, vt)
-                else:
-                    plan.add(f"b{i}.attn", lib.b2u_attention_tc_hd, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, hd,
-                             hd ** -0.5, vt)
+            # one launch over all ntok query rows (the 5 cls/storage rows form a ninth query tile whose out-of-range row
+            # quarters only run the barrier protocol; b2u_attention_rows remains available for a split launch)
+            if hd == 64:
+                plan.add(f"b{i}.attn", lib.b2u_attention_tc, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, 0,
+                         hd ** -0.5, vt)
             else:
-                plan.add(f"b{i}.attn", lib.b2u_attention, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, 64 ** -0.5, vt)
+                plan.add(f"b{i}.attn", lib.b2u_attention_tc_hd, _ptr(Q), _ptr(K_), _ptr(V), _ptr(O), B, Hh, N, npad, hd,
+                         hd ** -0.5, vt)
             self._gemm(plan, f"b{i}.proj", O, T, D, D, w[f"b{i}.proj"], D, X, D, vt, out_fp32=True, bias=w[f"b{i}.projb"],
                        scale=w[f"b{i}.ls1"], residual=X, ldres=D)
             plan.add(f"b{i}.ln2", lib.b2u_layernorm, _ptr(X), _ptr(Y), _ptr(w[f"b{i}.n2w"]), _ptr(w[f"b{i}.n2b"]), T, D,

@@ -75,7 +75,6 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 SIGNATURES = {
     "b2u_gemm": [C.POINTER(GemmParams), vp],
     "b2u_qkv_rope": [C.POINTER(QkvParams), vp],
-    "b2u_attention": [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp],
     "b2u_attention_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp],
     "b2u_attention_tc_hd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp],
     "b2u_attention_rows": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp],

@@ -105,12 +105,8 @@ typedef struct b2u_qkv_params {
 
 int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream);
 
-/* Non-causal softmax attention, head_dim 64 (attention.py:106-118 -> F.scaled_dot_product_attention):
- *   q,k,v [B, heads, ntok, 64] -> out [B, ntok, heads*64]. */
-int b2u_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t heads, int32_t ntok,
-                  float scale, int32_t dtype, b2u_stream_t stream);
-
-/* tcgen05 / TMEM flash attention (same math as b2u_attention): q,k [B, heads, ntok, 64], vt = V^T [B, heads, 64, npad]
+/* tcgen05 / TMEM flash attention, non-causal softmax attention (attention.py:106-118 -> F.scaled_dot_product_attention):
+ * q,k [B, heads, ntok, 64], vt = V^T [B, heads, 64, npad]
  * with zero padding columns (see b2u_qkv_params.v_transposed) -> out [B, ntok, heads*64].  Only the query rows
  * [q_begin, ntok) are produced (128-row tiles, two per work item); keys always span [0, ntok).  With q_begin = the
  * number of cls/storage tokens the ViT's 1024 patch rows fill whole tiles and b2u_attention_rows does the prefix. */

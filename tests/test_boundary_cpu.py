@@ -107,7 +107,7 @@ def test_no_cpu_fallback(built):
 
 def test_engine_rejects_unsupported_kernel_choices(built):
     from dinounet_b200.engine import ForwardEngine
-    with pytest.raises(NotImplementedError):   # head_dim 128 exists only in the tcgen05 attention kernel
+    with pytest.raises(NotImplementedError):   # the tcgen05 attention kernel is the only one
         ForwardEngine("dinounet_7b", {}, 2, torch.device("cpu"), attn_impl="mma")
     with pytest.raises(ValueError):
         ForwardEngine("dinounet_xl", {}, 2, torch.device("cpu"))

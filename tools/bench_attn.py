@@ -66,7 +66,7 @@ def time_case(B, H, N, hd, opt, reps=12):
 
 
 rows = []
-for opt in (2, 0):
+for opt in (0, 4, 5):
     rows.append(time_case(32, 16, 1029, 64, opt))
     print(rows[-1], flush=True)
 if "--sweep" in sys.argv:

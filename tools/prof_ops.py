@@ -47,10 +47,6 @@ elif op == "qkv":
     p.rope_sin, p.rope_cos, p.q, p.k, p.v, p.dtype = P(sin), P(cos), P(q), P(k), P(vt), L.BF16
     p.v_transposed, p.npad, p.rope_w = 1, 1032, 32
     run = lambda: L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv")
-elif op == "attn":
-    q, k, v = (rnd(32, 16, 1029, 64) for _ in range(3))
-    o = torch.empty(32, 1029, 1024, device=dev, dtype=bf)
-    run = lambda: L.check(lib.b2u_attention(P(q), P(k), P(v), P(o), 32, 16, 1029, 0.125, L.BF16, stream()), "attn")
 elif op == "attn_tc":
     q, k = (rnd(32, 16, 1029, 64) for _ in range(2))
     vt = torch.zeros(32, 16, 64, 1032, device=dev, dtype=bf)
