@@ -56,14 +56,23 @@ __global__ void __launch_bounds__(256) f32_gemm_kernel(const b2u_f32_gemm_params
   }
   long long arow = am;
   if (!p.conv && p.a_rows_in > 0 && am < p.M) arow = (am / p.a_rows_in) * p.a_rows_out + p.a_row_off + am % p.a_rows_in;
-  for (int k0 = 0; k0 < p.K; k0 += FK) {
+  // split-K (backward weight gradients: K = number of rows / pixels): slice blockIdx.z of the K range, atomic epilogue
+  int k_lo = 0, k_hi = p.K;
+  if (p.ksplit > 1) {
+    const int per = ((p.K + p.ksplit - 1) / p.ksplit + FK - 1) / FK * FK;
+    k_lo = blockIdx.z * per;
+    k_hi = min(p.K, k_lo + per);
+  }
+  for (int k0 = k_lo; k0 < k_hi; k0 += FK) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = k0 + lk + e;
       float a = 0.f, w = 0.f;
-      if (k < p.K) {
+      if (k < k_hi) {
         if (am < p.M) {
-          if (!p.conv) {
+          if (p.a_trans) {
+            a = A[static_cast<long long>(k) * p.lda + am];            // A'(m, k) = A[k][m]
+          } else if (!p.conv) {
             a = A[arow * p.lda + k];
           } else {
             const int tap = k / p.Cpad, c = k - tap * p.Cpad;
@@ -73,7 +82,17 @@ __global__ void __launch_bounds__(256) f32_gemm_kernel(const b2u_f32_gemm_params
               a = A[((static_cast<long long>(cb) * p.Hin + iy) * p.Win + ix) * p.C + c];
           }
         }
-        if (n0 + lr < p.N) w = W[static_cast<long long>(n0 + lr) * p.ldw + k];
+        if (n0 + lr < p.N) {
+          if (p.w_mode == 0) {
+            w = W[static_cast<long long>(n0 + lr) * p.ldw + k];
+          } else if (p.w_mode == 1) {
+            w = W[static_cast<long long>(k) * p.ldw + n0 + lr];          // W'(n, k) = W[k][n]
+          } else {
+            // 3x3 data gradient: this call convolves dY (C = Cout channels) with W'(c, (tap', n)) = W[n][(8 - tap')*wc + c]
+            const int tap = k / p.Cpad, nn = k - tap * p.Cpad;
+            if (nn < p.C) w = W[static_cast<long long>(nn) * p.ldw + (8 - tap) * p.w_cpad + n0 + lr];
+          }
+        }
       }
       sA[lk + e][lr] = a;
       sW[lk + e][lr] = w;
@@ -126,7 +145,8 @@ __global__ void __launch_bounds__(256) f32_gemm_kernel(const b2u_f32_gemm_params
       if (p.shift) v += p.shift[n];
       v = f32_act(v, p.act2);
       if (p.residual) v += p.residual[r * p.ldres + oc];
-      p.out[r * p.ldc + oc] = v;
+      if (p.ksplit > 1 || p.accumulate) atomicAdd(&p.out[r * p.ldc + oc], v);
+      else p.out[r * p.ldc + oc] = v;
     }
   }
 }
@@ -136,7 +156,9 @@ extern "C" int b2u_f32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream_) 
   if (!p || !p->A || !p->W || !p->out) return set_error(-1, "b2u_f32_gemm: null pointer");
   if (p->M <= 0 || p->N <= 0 || p->K <= 0) return set_error(-1, "b2u_f32_gemm: bad shape");
   if (p->conv && (p->Cpad < p->C || p->K != 9 * p->Cpad)) return set_error(-1, "b2u_f32_gemm: conv needs K = 9 * Cpad");
-  dim3 grid((p->N + FT - 1) / FT, static_cast<unsigned>((p->M + FT - 1) / FT));
+  if (p->ksplit > 1 && (p->bias || p->scale || p->shift || p->act1 || p->act2 || p->residual))
+    return set_error(-1, "b2u_f32_gemm: split-K accumulates raw products only");
+  dim3 grid((p->N + FT - 1) / FT, static_cast<unsigned>((p->M + FT - 1) / FT), p->ksplit > 1 ? p->ksplit : 1);
   f32_gemm_kernel<<<grid, 256, 0, stream>>>(*p);
   return check_launch("f32_gemm");
 }

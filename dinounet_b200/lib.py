@@ -66,6 +66,7 @@ class F32GemmParams(C.Structure):
         ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("act1", C.c_int32), ("act2", C.c_int32),
         ("residual", C.c_void_p), ("ldres", C.c_int64),
+        ("a_trans", C.c_int32), ("w_mode", C.c_int32), ("w_cpad", C.c_int32), ("ksplit", C.c_int32), ("accumulate", C.c_int32),
     ]
 
 
@@ -118,6 +119,23 @@ SIGNATURES = {
     "b2u_f32_se": [vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],
     "b2u_f32_film": [vp, vp, vp, i64, i32, vp],
     "b2u_f32_tail": [vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2u_f32_act_bwd": [vp, vp, vp, i64, i32, vp],
+    "b2u_f32_colsum": [vp, i64, i64, i32, vp, vp],
+    "b2u_f32_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp],
+    "b2u_f32_instnorm_bwd": [vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, i32, i64, i32, f32, i32, vp],
+    "b2u_f32_bn_act": [vp, vp, vp, vp, vp, vp, f32, i64, i32, i32, vp],
+    "b2u_f32_bn_act_bwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, i64, i32, i32, vp],
+    "b2u_f32_dwconv_wgrad": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "b2u_f32_maxpool3x3s2_bwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2u_f32_film_bwd": [vp, vp, vp, vp, vp, i64, i32, vp],
+    "b2u_f32_se_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],
+    "b2u_f32_msda_prep": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2u_f32_msda_prep_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2u_f32_unshuffle": [vp, i64, i32, vp, i32, i32, i32, i32, vp],
+    "b2u_f32_conv3x3_dgrad": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "b2u_f32_conv3x3_wgrad": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "b2u_f32_sqsum": [vp, i64, vp, vp],
+    "b2u_f32_sgd_nesterov": [vp, vp, vp, i64, f32, f32, f32, vp, f32, i32, vp],
     "b2u_set_option": [i32, i32],
     "b2u_last_error": [],
     "b2u_version": [],

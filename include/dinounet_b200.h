@@ -302,6 +302,11 @@ typedef struct b2u_f32_gemm_params {
   int32_t act1, act2;
   const float* residual;
   int64_t ldres;
+  /* backward-pass addressing (csrc/train_bwd.cu callers): a_trans: A'(m, k) = A[k][m]; w_mode 1: W'(n, k) = W[k][n];
+   * w_mode 2 (with conv != 0): 3x3 data gradient, W'(c, (tap', n)) = W[n][(8 - tap') * w_cpad + c];
+   * ksplit > 1: the K range is split over gridDim.z and the raw products are atomically ADDED to out (zero it first);
+   * accumulate: out += instead of out =. */
+  int32_t a_trans, w_mode, w_cpad, ksplit, accumulate;
 } b2u_f32_gemm_params;
 int b2u_f32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream);   /* F.linear / Conv2d 1x1, 3x3 / ConvTranspose2d k2 s2 */
 /* F.layer_norm; input row = (r / out_per_b) * in_per_b + in_off + r % out_per_b when in_per_b > 0 (ViT taps drop the prefix) */
@@ -325,6 +330,46 @@ int b2u_f32_se(const float* t, const float* shortcut, int64_t ld_shortcut, float
 int b2u_f32_film(const float* gamma_beta, const float* zs_zp, float* z, int64_t px, int32_t R, b2u_stream_t stream);
 int b2u_f32_tail(const float* c, int64_t c_rows_per_b, int64_t c_off, const float* tap, float* out, const float* bn_scale,
                  const float* bn_shift, int32_t B, int32_t r, int32_t h, int32_t D, b2u_stream_t stream);   /* dinov3_adapter.py:468-482 */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Backward of the trainable part + optimizer (csrc/train_bwd.cu; SURVEY.md section 8f rank 2, BASELINE config 3).
+ * fp32, same layouts as the fp32 tier.  Matrix-product gradients use b2u_f32_gemm (a_trans / w_mode / ksplit).  Every
+ * parameter-gradient output is ACCUMULATED with atomics: zero it first.  Replaces ATen autograd kernels of
+ * nnUNetTrainer.train_step (nnUNetTrainer.py:899-929); the one native backward op of the reference is b2u_msda_backward_f32. */
+int b2u_f32_act_bwd(const float* x_pre, const float* dy, float* dx, int64_t n, int32_t act, b2u_stream_t stream);
+int b2u_f32_colsum(const float* in, int64_t ld, int64_t rows, int32_t C, float* out_accum, b2u_stream_t stream);
+int b2u_f32_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows,
+                          int32_t D, float eps, b2u_stream_t stream);
+int b2u_f32_instnorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, const float* w, const float* b, float* dx,
+                         int64_t lddx, float* dw, float* db, int32_t B, int64_t HW, int32_t C, float eps, int32_t lrelu,
+                         b2u_stream_t stream);
+/* eval-mode (Sync)BatchNorm + optional ReLU, forward and backward (the gradient oracle's semantics) */
+int b2u_f32_bn_act(const float* x, float* y, const float* gamma, const float* beta, const float* running_mean,
+                   const float* running_var, float eps, int64_t rows, int32_t C, int32_t act, b2u_stream_t stream);
+int b2u_f32_bn_act_bwd(const float* x, const float* dy, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                       int32_t act, b2u_stream_t stream);
+int b2u_f32_dwconv_wgrad(const float* x, const float* dy, float* dw9, float* db, int32_t B, int32_t H, int32_t W, int32_t C,
+                         int32_t planes, b2u_stream_t stream);
+int b2u_f32_maxpool3x3s2_bwd(const float* x, const float* dy, float* dx_zeroed, int32_t B, int32_t H, int32_t W, int32_t C,
+                             b2u_stream_t stream);
+int b2u_f32_film_bwd(const float* gamma_beta, const float* zs_zp, const float* dz, float* dgb, float* dzz, int64_t px, int32_t R,
+                     b2u_stream_t stream);
+int b2u_f32_se_bwd(const float* t, const float* dy, const float* pooled, const float* w1, const float* b1, const float* w2,
+                   const float* b2, float* work_3BC, float* dt, float* dw1, float* db1, float* dw2, float* db2, int32_t B,
+                   int64_t HW, int32_t C, int32_t hidden, b2u_stream_t stream);
+int b2u_f32_msda_prep(const float* offaw, float* loc, float* attw, int32_t B, int32_t Hv, int32_t Wv, int32_t heads, b2u_stream_t stream);
+int b2u_f32_msda_prep_bwd(const float* attw, const float* dloc, const float* dattw, float* doffaw, int32_t B, int32_t Hv, int32_t Wv,
+                          int32_t heads, b2u_stream_t stream);
+int b2u_f32_unshuffle(const float* dy_image, int64_t ld, int32_t col_off, float* rows_4cout, int32_t B, int32_t h, int32_t w,
+                      int32_t Cout, b2u_stream_t stream);
+int b2u_f32_conv3x3_dgrad(const float* dy, const float* W, float* dx, int32_t B, int32_t H, int32_t Wd, int32_t C, int32_t Cpad,
+                          int32_t N, int32_t stride, b2u_stream_t stream);
+int b2u_f32_conv3x3_wgrad(const float* x, const float* dy, float* dW_accum, int32_t B, int32_t H, int32_t Wd, int32_t C, int32_t Cpad,
+                          int32_t N, int32_t stride, b2u_stream_t stream);
+int b2u_f32_sqsum(const float* g, int64_t n, double* out_accum, b2u_stream_t stream);
+int b2u_f32_sgd_nesterov(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum, float weight_decay,
+                         const double* grad_sqsum, float max_norm, int32_t first_step, b2u_stream_t stream);
 
 int b2u_set_option(int32_t key, int32_t value);
 
