@@ -165,8 +165,8 @@ extern "C" int b2u_attention_rows(const void* q, const void* k, const void* vt, 
   if (nrows > AR_MAXROWS) return set_error(-1, "b2u_attention_rows: at most 8 rows");
   const size_t smem = (static_cast<size_t>(AR_MAXROWS) * (64 + npad + 8 + 1) + 4 * AR_MAXROWS * 64) * sizeof(float);
   if (smem > 200 * 1024) return set_error(-1, "b2u_attention_rows: ntok too large for the few-row kernel");
-  static bool configured[2] = {false, false};
-  const int di = dtype == B2U_BF16 ? 1 : 0;
+  static bool configured[128] = {};
+  const int di = current_device_index() * 2 + (dtype == B2U_BF16 ? 1 : 0);
   if (!configured[di]) {
     cudaError_t e = dtype == B2U_BF16
                         ? cudaFuncSetAttribute(attn_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)

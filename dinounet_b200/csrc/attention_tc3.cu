@@ -495,7 +495,8 @@ static int launch_attn_tc3(const AttnMaps& maps, const AttnArgs& a, cudaStream_t
   auto kern = attn_tc3_kernel<T, HD, kOne>;
   using CF = At3Cfg<HD>;
   static_assert(CF::kSmem <= 227 * 1024, "attention smem budget");
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[current_device_index()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kSmem);
     if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(attn_tc3): %s", cudaGetErrorString(e));

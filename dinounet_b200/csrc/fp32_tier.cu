@@ -386,7 +386,8 @@ extern "C" int b2u_f32_attention(const float* qkv, const float* sin, const float
   if (hd > 128) return set_error(-1, "b2u_f32_attention: head_dim <= 128");
   const size_t smem = (static_cast<size_t>(FQ) * hd + static_cast<size_t>(FQ) * N + FQ * 8) * sizeof(float);
   if (smem > 200 * 1024) return set_error(-1, "b2u_f32_attention: too many tokens for the shared-memory score rows");
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[current_device_index()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(f32_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(f32_attention): %s", cudaGetErrorString(e));

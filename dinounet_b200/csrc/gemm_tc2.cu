@@ -725,7 +725,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
 template <int BN, int EPI, int ACT1, int ACT2, typename T>
 static int launch_pair2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t stream) {
   auto kern = gemm_tc2_kernel<BN, EPI, ACT1, ACT2, T, true>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[current_device_index()];
   constexpr int kSmem = Cfg2<BN, EPI, true>::kSmem;
   static_assert(kSmem <= 227 * 1024, "pair variant exceeds the shared memory of an SM");
   if (!configured) {
@@ -758,7 +759,8 @@ static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStrea
     if (args.pair) return launch_pair2<BN, EPI, ACT1, ACT2, T>(maps, args, stream);
   }
   auto kern = gemm_tc2_kernel<BN, EPI, ACT1, ACT2, T>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[current_device_index()];
   constexpr int kMaxSmem = (BN <= 64 && Cfg2<BN, EPI>::kSmemHalo > Cfg2<BN, EPI>::kSmem) ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);

@@ -62,6 +62,12 @@ int encode_tensor_map(CUtensorMap* map, int dtype, int rank, const void* base, c
 namespace b2u {
 static int g_options[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 int get_option(int key) { return (key >= 0 && key < 8) ? g_options[key] : 0; }
+int current_device_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
 int num_sms() {
   static int sms[64] = {0};
   int dev = 0;

@@ -7,6 +7,8 @@
 namespace b2u {
 
 int set_error(int code, const char* fmt, ...);
+// Index of the current CUDA device (0..63): cudaFuncSetAttribute is PER DEVICE, so "already configured" flags are arrays.
+int current_device_index();
 // cudaGetLastError() after a launch; bumps the launch counter on success.
 int check_launch(const char* what);
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency): 16-bit elements,

@@ -191,7 +191,8 @@ static int launch_msda_smem(const void* value, const float* offaw, void* out, in
                             cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(Hv) * Wv * PITCH * 2;
   auto kern = msda_smem_kernel<T, DH, HPC, PITCH>;
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};
+  size_t& configured = configured_dev[current_device_index()];
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(msda_smem): %s", cudaGetErrorString(e));

@@ -36,6 +36,30 @@ extern "C" int b2u_f32_act_bwd(const float* x, const float* dy, float* dx, int64
   return check_launch("f32_act_bwd");
 }
 
+__global__ void f32_act_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int act) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  float r = v;
+  if (act == B2U_ACT_GELU) r = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  else if (act == B2U_ACT_RELU) r = fmaxf(v, 0.f);
+  else if (act == B2U_ACT_LRELU) r = v > 0.f ? v : 0.01f * v;
+  y[i] = r;
+}
+extern "C" int b2u_f32_act(const float* x, float* y, int64_t n, int32_t act, b2u_stream_t s) {
+  f32_act_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(s)>>>(x, y, n, act);
+  return check_launch("f32_act");
+}
+
+__global__ void f32_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+extern "C" int b2u_f32_add(const float* a, const float* b, float* out, int64_t n, b2u_stream_t s) {
+  f32_add_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(s)>>>(a, b, out, n);
+  return check_launch("f32_add");
+}
+
 // out[c] += sum_r in[r*ld + c]      (bias gradients; grid (C/32, splits), block 32 x 8)
 __global__ void __launch_bounds__(256) f32_colsum_kernel(const float* __restrict__ in, long long ld, long long rows, int Cc, float* __restrict__ out) {
   __shared__ float red[8][33];

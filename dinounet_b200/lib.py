@@ -119,6 +119,8 @@ SIGNATURES = {
     "b2u_f32_se": [vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],
     "b2u_f32_film": [vp, vp, vp, i64, i32, vp],
     "b2u_f32_tail": [vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "b2u_f32_add": [vp, vp, vp, i64, vp],
+    "b2u_f32_act": [vp, vp, i64, i32, vp],
     "b2u_f32_act_bwd": [vp, vp, vp, i64, i32, vp],
     "b2u_f32_colsum": [vp, i64, i64, i32, vp, vp],
     "b2u_f32_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp],

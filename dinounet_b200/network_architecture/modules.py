@@ -628,8 +628,11 @@ class DinoUNet(nn.Module):
             raise NotImplementedError("deep supervision outputs are not produced by the B200 forward path "
                                       "(DinoUNetTrainer derives from nnUNetTrainerNoDeepSupervision)")
         if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError("dinounet_b200 implements the forward (inference / validation) path; call "
-                                      "under torch.no_grad() / .eval(). Backward kernels are a later-round item.")
+            # training step (nnUNetTrainer.py:899-929): frozen ViT on the engine, everything else differentiable through the
+            # autograd Functions of train_path.py (forward and backward on hand-written fp32 kernels).  Semantics of the
+            # gradient oracle: BatchNorm uses running statistics and DropPath is off in BOTH module modes (the reference's
+            # train-mode stochasticity of the frozen ViT, SURVEY.md fact 8, is deliberately not reproduced).
+            return self.train_forward(x)
         B, Cc, H, W = x.shape
         if Cc == 1:                       # dinounet_training.py:491-497
             x = x.repeat(1, 3, 1, 1)
@@ -638,6 +641,18 @@ class DinoUNet(nn.Module):
         x = x.float().contiguous()
         logits, _ = self._get_engine(x.device).forward(x)
         return logits.clone()
+
+    def train_forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Differentiable logits [B, C, H, W] (fp32): gradients for the 289 trainable tensors outside the frozen backbone."""
+        from ..train_path import trainable_forward
+        if x.device.type != "cuda":
+            from ..lib import NativeLibraryError
+            raise NativeLibraryError("dinounet_b200 runs on CUDA devices only (no CPU fallback)")
+        x = self._three_channels(x)
+        with torch.no_grad():
+            taps = self._get_engine(x.device).extract_vit_features(x)
+        P = self.state_dict(keep_vars=True)
+        return trainable_forward(P, self.dinov3_model_name, x, taps, self.num_classes)
 
     @torch.no_grad()
     def predict_labels(self, x: torch.Tensor) -> torch.Tensor:

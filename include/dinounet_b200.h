@@ -336,6 +336,8 @@ int b2u_f32_tail(const float* c, int64_t c_rows_per_b, int64_t c_off, const floa
  * fp32, same layouts as the fp32 tier.  Matrix-product gradients use b2u_f32_gemm (a_trans / w_mode / ksplit).  Every
  * parameter-gradient output is ACCUMULATED with atomics: zero it first.  Replaces ATen autograd kernels of
  * nnUNetTrainer.train_step (nnUNetTrainer.py:899-929); the one native backward op of the reference is b2u_msda_backward_f32. */
+int b2u_f32_add(const float* a, const float* b, float* out, int64_t n, b2u_stream_t stream);
+int b2u_f32_act(const float* x, float* y, int64_t n, int32_t act, b2u_stream_t stream);
 int b2u_f32_act_bwd(const float* x_pre, const float* dy, float* dx, int64_t n, int32_t act, b2u_stream_t stream);
 int b2u_f32_colsum(const float* in, int64_t ld, int64_t rows, int32_t C, float* out_accum, b2u_stream_t stream);
 int b2u_f32_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows,

@@ -101,7 +101,7 @@ def test_no_cpu_fallback(built):
     net = _build("dinounet_s").eval()
     with torch.no_grad(), pytest.raises(lib.NativeLibraryError):
         net(torch.zeros(1, 3, 64, 64))
-    with pytest.raises(NotImplementedError):   # training-mode forward is not silently emulated either
+    with pytest.raises(lib.NativeLibraryError):   # the training path (train_path.py) is CUDA-only as well
         net.train()(torch.zeros(1, 3, 64, 64))
 
 
