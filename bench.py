@@ -27,6 +27,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train = BASELINE.json config 3: forward + backward (Dice+CE) + SGD step of the trainable parameters")
     ap.add_argument("--model", default="dinounet_l", choices=["dinounet_s", "dinounet_b", "dinounet_l", "dinounet_7b"])
     ap.add_argument("--batch", type=int, default=32, help="patches per GPU per step")
     ap.add_argument("--size", type=int, default=512)
@@ -225,6 +227,81 @@ def eager_cuda_patches_per_s(model, B, S, steps, warmup, dev):
                     "inner bf16 autocast, inputs resident in HBM, batch %d" % B}
 
 
+def run_train(a):
+    """BASELINE.json configs[2]: `dinounet_b random-init, batch 64x512x512x3 synthetic, 1xB200 fwd+bwd (Dice+CE loss)`.
+    One step = nnUNetTrainer.train_step: frozen ViT on the 16-bit tensor-core engine, trainable part forward + backward on the
+    fp32 kernels of train_path.py, Dice+CE, (N > 1: one NCCL all-reduce of the gradients), clip + SGD-nesterov."""
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "1")
+    import dinounet_b200
+    from dinounet_b200 import config, lib
+    from dinounet_b200.loss import DC_and_CE_loss
+    from dinounet_b200.train_path import FusedSGD, train_step
+    from oracle import dinounet_oracle as O
+    rank, local, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, K, W = a.batch, a.size, a.steps, max(3, a.warmup)
+    sd = O.make_state_dict(a.model, 2, seed=0)
+    net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, a.model)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).train()
+    crit = DC_and_CE_loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": False}, {}, weight_ce=1, weight_dice=1)
+    opt = FusedSGD(net.parameters(), lr=1e-2, weight_decay=3e-5)
+    xs = [O.make_input(B, S, 100 + rank * 7 + i).to(dev) for i in range(2)]
+    ts = [torch.randint(0, 2, (B, 1, S, S), generator=torch.Generator().manual_seed(i)).float().to(dev) for i in range(2)]
+    n0 = lib.launch_count()
+    with ClockSampler(local) as clk:
+        for i in range(W):
+            loss = train_step(net, crit, opt, xs[i % 2], ts[i % 2])
+        torch.cuda.synchronize()
+        launches_per_step = (lib.launch_count() - n0) // W
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            loss = train_step(net, crit, opt, xs[i % 2], ts[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item()
+    if rank == 0:
+        v = config.VARIANTS[a.model]
+        fwd = O.algorithmic_flops_per_patch(a.model, S)
+        T = (S // 16) ** 2 + config.N_PREFIX
+        vit = v.depth * (2 * T * v.embed_dim * 3 * v.embed_dim + 4 * T * T * v.embed_dim + 2 * T * v.embed_dim ** 2 +
+                         4 * T * v.embed_dim * v.ffn_hidden) + 2 * (S // 16) ** 2 * 768 * v.embed_dim
+        flops = fwd + 2 * (fwd - vit)                       # backward of the trainable (non-ViT) part = 2x its forward
+        value = world * B * K / (ms / 1e3)
+        pk = peaks()
+        print(json.dumps({
+            "metric": "2D patches/sec (512x512) fwd+bwd (Dice+CE) + SGD step", "value": value, "unit": "patches/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16/fp16 frozen ViT (tcgen05) + fp32 trainable part (SIMT forward/backward kernels)", "data": "synthetic",
+            "impl": "b200", "mode": "train",
+            "config": {"workload": f"{a.model} train step, {S}x{S}x3, per-GPU batch {B}, Dice+CE, SGD-nesterov + clip 12",
+                       "global_batch": B * world, "l2": "two resident batches alternated; the per-step working set is >> 126 MB L2",
+                       "parallelism": f"dp{world} + 1 NCCL all-reduce of the gradients" if world > 1 else "single GPU"},
+            "gpu_launches": K * launches_per_step, "kernels_per_step": launches_per_step, "loss": float(loss),
+            "clocks": clk.summary(t0, t1),
+            "roofline": {"bound": "fp32-simt", "achieved": value / world * flops / 1e12, "unit": "TFLOP/s",
+                         "algorithmic_gflop_per_patch": flops / 1e9,
+                         "note": "fp32 FMA peak of a B200 is ~72 TF/s (148 SMs x 128 lanes x 2 x 1.9 GHz); the trainable part runs "
+                                 "on plain fp32 SIMT kernels (gradient parity first), not on tensor cores"},
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference_cuda(a):
     """the same oracle port run by PyTorch eager on the B200 in the reference's GPU precision
     regime (outer fp16 autocast, inner bf16 ViT, fp32 MSDA) — what a user gets from the reference code on this GPU
@@ -260,6 +337,8 @@ def main():
         return run_reference(a)
     if a.impl == "reference-cuda":
         return run_reference_cuda(a)
+    if a.mode == "train":
+        return run_train(a)
     import torch
     import torch.distributed as dist
     os.environ.setdefault("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "1")

@@ -22,40 +22,57 @@ __device__ __forceinline__ float f32_act(float v, int act) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM / conv3x3
-// acc[m, n] = sum_k A(m, k) * W[n, k];  A(m, k): plain rows (with an optional batch row remap) or the 3x3 / pad 1 window
-// of an NHWC image.  Epilogue identical in meaning to b2u_epilogue (bias, act1, scale/shift, act2, residual, row remap,
-// pixel shuffle).  64 x 64 tile, BK 16, 256 threads, 4 x 4 outputs per thread, k ascending (one fmaf chain per output).
-constexpr int FT = 64, FK = 16;
+// acc[m, n] = sum_k A(m, k) * W'(n, k).  A(m, k): plain rows (optional batch row remap), transposed rows, or the 3x3 / pad 1
+// window of an NHWC image; W'(n, k): plain [N, K] rows, transposed, the flipped 3x3 weights of the conv data gradient, or
+// the 3x3 window of an image (conv weight gradient: k = output pixel).  Epilogue identical in meaning to b2u_epilogue.
+// 128 x 128 tile, BK 8, 256 threads, 8 x 8 outputs per thread (two 4-wide groups 64 apart), k ascending (one fmaf chain
+// per output: the accumulation order within a K slice does not depend on the tiling).
+constexpr int FT = 128, FK = 8;
+
+struct F32RowAddr {      // per-thread loader state for one row of the A / W' operand
+  long long row;         // plain row index (after remap) or -1 when out of range
+  int cb, cy, cx;        // conv: batch, output y, output x of the pixel this row / column stands for
+};
+
+__device__ __forceinline__ float f32_conv_window(const float* img, int Hin, int Win, int Cc, int stride, int cb, int cy, int cx, int tap,
+                                                 int c) {
+  const int dy = tap / 3, dx = tap - dy * 3;
+  const int iy = cy * stride + dy - 1, ix = cx * stride + dx - 1;
+  if (c < Cc && iy >= 0 && iy < Hin && ix >= 0 && ix < Win) return img[((static_cast<long long>(cb) * Hin + iy) * Win + ix) * Cc + c];
+  return 0.f;
+}
 
 __global__ void __launch_bounds__(256) f32_gemm_kernel(const b2u_f32_gemm_params p) {
-  __shared__ float sA[FK][FT + 1];
-  __shared__ float sW[FK][FT + 1];
+  __shared__ __align__(16) float sA[FK][FT + 4];
+  __shared__ __align__(16) float sW[FK][FT + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const long long m0 = static_cast<long long>(blockIdx.y) * FT;
-  const int n0 = blockIdx.x * FT;
+  const long long m0 = static_cast<long long>(blockIdx.x) * FT;   // rows on grid.x (up to 2^31 tiles: 64 x 512^2 pixels)
+  const int n0 = blockIdx.y * FT;
   const float* A = p.A;
   const float* W = p.W;
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // loader: thread -> (row lr = tid / 4 (0..63), 4 consecutive k's lk = (tid & 3) * 4)
-  const int lr = tid >> 2, lk = (tid & 3) * 4;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  // loader: thread -> (tile row lr = tid / 2 (0..127), 4 consecutive k's lk = (tid & 1) * 4) of both operands
+  const int lr = tid >> 1, lk = (tid & 1) * 4;
   const long long am = m0 + lr;
-  // conv addressing of this thread's A row
-  int cb = 0, cy = 0, cx = 0;
+  const int wn = n0 + lr;
   const int stride = p.conv == B2U_CONV3X3_S2 ? 2 : 1;
   const int Ho = p.conv ? p.Hin / stride : 0, Wo = p.conv ? p.Win / stride : 0;
-  if (p.conv && am < p.M) {
-    cb = static_cast<int>(am / (static_cast<long long>(Ho) * Wo));
-    const int r = static_cast<int>(am - static_cast<long long>(cb) * Ho * Wo);
-    cy = r / Wo;
-    cx = r - cy * Wo;
+  int acb = 0, acy = 0, acx = 0;
+  if (p.conv && p.w_mode != 3 && am < p.M) {                     // A side = conv window (forward / data gradient)
+    acb = static_cast<int>(am / (static_cast<long long>(Ho) * Wo));
+    const int r = static_cast<int>(am - static_cast<long long>(acb) * Ho * Wo);
+    acy = r / Wo;
+    acx = r - acy * Wo;
   }
   long long arow = am;
   if (!p.conv && p.a_rows_in > 0 && am < p.M) arow = (am / p.a_rows_in) * p.a_rows_out + p.a_row_off + am % p.a_rows_in;
+  // w_mode 3: W'(n, k) = window(pixel k, tap = n / Cpad, c = n % Cpad)
+  const int wtap = p.w_mode == 3 ? wn / p.Cpad : 0, wc = p.w_mode == 3 ? wn - wtap * p.Cpad : 0;
   // split-K (backward weight gradients: K = number of rows / pixels): slice blockIdx.z of the K range, atomic epilogue
   int k_lo = 0, k_hi = p.K;
   if (p.ksplit > 1) {
@@ -63,58 +80,74 @@ __global__ void __launch_bounds__(256) f32_gemm_kernel(const b2u_f32_gemm_params
     k_lo = blockIdx.z * per;
     k_hi = min(p.K, k_lo + per);
   }
+  const bool a_vec = !p.conv && !p.a_trans && (p.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool w_vec = p.w_mode == 0 && (p.ldw & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   for (int k0 = k_lo; k0 < k_hi; k0 += FK) {
+    float a4[4] = {0.f, 0.f, 0.f, 0.f}, w4[4] = {0.f, 0.f, 0.f, 0.f};
+    const int kb = k0 + lk;
+    if (am < p.M) {
+      if (a_vec && kb + 3 < k_hi) {
+        const float4 t = *reinterpret_cast<const float4*>(A + arow * p.lda + kb);
+        a4[0] = t.x; a4[1] = t.y; a4[2] = t.z; a4[3] = t.w;
+      } else {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int k = k0 + lk + e;
-      float a = 0.f, w = 0.f;
-      if (k < k_hi) {
-        if (am < p.M) {
-          if (p.a_trans) {
-            a = A[static_cast<long long>(k) * p.lda + am];            // A'(m, k) = A[k][m]
-          } else if (!p.conv) {
-            a = A[arow * p.lda + k];
-          } else {
+        for (int e = 0; e < 4; ++e) {
+          const int k = kb + e;
+          if (k >= k_hi) break;
+          if (p.a_trans) a4[e] = A[static_cast<long long>(k) * p.lda + am];            // A'(m, k) = A[k][m]
+          else if (!p.conv || p.w_mode == 3) a4[e] = A[arow * p.lda + k];
+          else {
             const int tap = k / p.Cpad, c = k - tap * p.Cpad;
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const int iy = cy * stride + dy - 1, ix = cx * stride + dx - 1;
-            if (c < p.C && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
-              a = A[((static_cast<long long>(cb) * p.Hin + iy) * p.Win + ix) * p.C + c];
-          }
-        }
-        if (n0 + lr < p.N) {
-          if (p.w_mode == 0) {
-            w = W[static_cast<long long>(n0 + lr) * p.ldw + k];
-          } else if (p.w_mode == 1) {
-            w = W[static_cast<long long>(k) * p.ldw + n0 + lr];          // W'(n, k) = W[k][n]
-          } else {
-            // 3x3 data gradient: this call convolves dY (C = Cout channels) with W'(c, (tap', n)) = W[n][(8 - tap')*wc + c]
-            const int tap = k / p.Cpad, nn = k - tap * p.Cpad;
-            if (nn < p.C) w = W[static_cast<long long>(nn) * p.ldw + (8 - tap) * p.w_cpad + n0 + lr];
+            a4[e] = f32_conv_window(A, p.Hin, p.Win, p.C, stride, acb, acy, acx, tap, c);
           }
         }
       }
-      sA[lk + e][lr] = a;
-      sW[lk + e][lr] = w;
     }
+    if (wn < p.N) {
+      if (w_vec && kb + 3 < k_hi) {
+        const float4 t = *reinterpret_cast<const float4*>(W + static_cast<long long>(wn) * p.ldw + kb);
+        w4[0] = t.x; w4[1] = t.y; w4[2] = t.z; w4[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = kb + e;
+          if (k >= k_hi) break;
+          if (p.w_mode == 0) w4[e] = W[static_cast<long long>(wn) * p.ldw + k];
+          else if (p.w_mode == 1) w4[e] = W[static_cast<long long>(k) * p.ldw + wn];   // W'(n, k) = W[k][n]
+          else if (p.w_mode == 2) {
+            // 3x3 data gradient: this call convolves dY (C = Cout channels) with W'(c, (tap', n)) = W[n][(8 - tap')*w_cpad + c]
+            const int tap = k / p.Cpad, nn = k - tap * p.Cpad;
+            if (nn < p.C) w4[e] = W[static_cast<long long>(nn) * p.ldw + (8 - tap) * p.w_cpad + wn];
+          } else {
+            // 3x3 weight gradient: k = output pixel of the image W (the layer input), window element (wtap, wc)
+            const int cb = k / (Ho * Wo), r = k - cb * (Ho * Wo);
+            const int cy = r / Wo, cx = r - cy * Wo;
+            w4[e] = f32_conv_window(W, p.Hin, p.Win, p.C, stride, cb, cy, cx, wtap, wc);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { sA[lk + e][lr] = a4[e]; sW[lk + e][lr] = w4[e]; }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < FK; ++k) {
-      float a[4], w[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sW[k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[k][ty * 4 + i];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = sW[k][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (m >= p.M) continue;
     long long orow = m;
     if (p.ps_cout > 0) {
@@ -127,8 +160,8 @@ __global__ void __launch_bounds__(256) f32_gemm_kernel(const b2u_f32_gemm_params
       orow = (m / p.rows_in) * p.rows_out + p.row_off + m % p.rows_in;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
       if (n >= p.N) continue;
       long long r = orow;
       int oc = n;
@@ -155,10 +188,11 @@ extern "C" int b2u_f32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream_) 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!p || !p->A || !p->W || !p->out) return set_error(-1, "b2u_f32_gemm: null pointer");
   if (p->M <= 0 || p->N <= 0 || p->K <= 0) return set_error(-1, "b2u_f32_gemm: bad shape");
-  if (p->conv && (p->Cpad < p->C || p->K != 9 * p->Cpad)) return set_error(-1, "b2u_f32_gemm: conv needs K = 9 * Cpad");
+  if (p->conv && p->w_mode != 3 && (p->Cpad < p->C || p->K != 9 * p->Cpad)) return set_error(-1, "b2u_f32_gemm: conv needs K = 9 * Cpad");
+  if (p->w_mode == 3 && (!p->conv || p->N != 9 * p->Cpad)) return set_error(-1, "b2u_f32_gemm: conv weight gradient needs N = 9 * Cpad");
   if (p->ksplit > 1 && (p->bias || p->scale || p->shift || p->act1 || p->act2 || p->residual))
     return set_error(-1, "b2u_f32_gemm: split-K accumulates raw products only");
-  dim3 grid((p->N + FT - 1) / FT, static_cast<unsigned>((p->M + FT - 1) / FT), p->ksplit > 1 ? p->ksplit : 1);
+  dim3 grid(static_cast<unsigned>((p->M + FT - 1) / FT), (p->N + FT - 1) / FT, p->ksplit > 1 ? p->ksplit : 1);
   f32_gemm_kernel<<<grid, 256, 0, stream>>>(*p);
   return check_launch("f32_gemm");
 }
@@ -456,54 +490,69 @@ extern "C" int b2u_f32_msda(const float* value, const float* offaw, float* out, 
 }
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm / SE / FiLM
-// per-(n, c) mean and biased variance over HW rows (fp64 accumulation, two-pass), then y = (x-mean)*rstd*w + b (+ LeakyReLU).
-// grid (C / 32, B), block (32 channels x 8 row groups).
-__global__ void __launch_bounds__(256) f32_instnorm_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out,
-                                                           long long ld_out, const float* __restrict__ w,
-                                                           const float* __restrict__ bb, long long HW, int Cc, float eps,
-                                                           int lrelu) {
+// per-(n, c) mean and biased variance over HW rows (fp64 accumulation, two passes: mean first, then centred squares), then
+// y = (x-mean)*rstd*w + b (+ LeakyReLU).  The rows of one image are split over gridDim.z blocks (a 512^2 image with 32
+// channels would otherwise be ONE block): partial sums meet in fp64 atomics on work[2][B][C]; stats[B][C][2] = (mean, rstd)
+// is also what the backward needs.
+__global__ void __launch_bounds__(256) f32_in_sum_kernel(const float* __restrict__ x, long long ld, long long HW, int Cc, int pass,
+                                                         double* __restrict__ work, int B) {
   __shared__ double red[8][33];
-  __shared__ float s_mean[32], s_rstd[32];
   const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const long long b = blockIdx.y;
-  const float* x = in + b * HW * ld_in;
+  const long long per = (HW + gridDim.z - 1) / gridDim.z;
+  const long long lo = blockIdx.z * per, hi = lo + per < HW ? lo + per : HW;
+  const float* xb = x + b * HW * ld;
   double s = 0.0;
-  if (c < Cc)
-    for (long long r = rg; r < HW; r += 8) s += x[r * ld_in + c];
+  if (c < Cc) {
+    if (pass == 0) {
+      for (long long r = lo + rg; r < hi; r += 8) s += xb[r * ld + c];
+    } else {
+      const double mean = work[b * Cc + c] / static_cast<double>(HW);
+      for (long long r = lo + rg; r < hi; r += 8) { const double d = static_cast<double>(xb[r * ld + c]) - mean; s += d * d; }
+    }
+  }
   red[rg][cx] = s;
   __syncthreads();
-  if (rg == 0) {
+  if (rg == 0 && c < Cc) {
     double t = 0.0;
     for (int k = 0; k < 8; ++k) t += red[k][cx];
-    s_mean[cx] = static_cast<float>(t / HW);
-  }
-  __syncthreads();
-  const float mean = s_mean[cx];
-  double q = 0.0;
-  if (c < Cc)
-    for (long long r = rg; r < HW; r += 8) { const double d = static_cast<double>(x[r * ld_in + c]) - mean; q += d * d; }
-  red[rg][cx] = q;
-  __syncthreads();
-  if (rg == 0) {
-    double t = 0.0;
-    for (int k = 0; k < 8; ++k) t += red[k][cx];
-    s_rstd[cx] = 1.0f / sqrtf(static_cast<float>(t / HW) + eps);
-  }
-  __syncthreads();
-  if (c >= Cc) return;
-  const float rstd = s_rstd[cx], g = w[c], be = bb[c];
-  float* y = out + b * HW * ld_out;
-  for (long long r = rg; r < HW; r += 8) {
-    float v = (x[r * ld_in + c] - mean) * rstd * g + be;
-    if (lrelu) v = v > 0.f ? v : 0.01f * v;
-    y[r * ld_out + c] = v;
+    atomicAdd(&work[(static_cast<long long>(pass) * B + b) * Cc + c], t);
   }
 }
+__global__ void f32_in_finish_kernel(const double* __restrict__ work, float* __restrict__ stats, int B, int Cc, long long HW, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Cc) return;
+  stats[2 * i] = static_cast<float>(work[i] / static_cast<double>(HW));
+  stats[2 * i + 1] = 1.0f / sqrtf(static_cast<float>(work[static_cast<long long>(B) * Cc + i] / static_cast<double>(HW)) + eps);
+}
+__global__ void f32_in_apply_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ out, long long ldo,
+                                    const float* __restrict__ stats, const float* __restrict__ w, const float* __restrict__ bb, int B,
+                                    long long HW, int Cc, int lrelu) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= B * HW * Cc) return;
+  const int c = static_cast<int>(i % Cc);
+  const long long r = i / Cc, b = r / HW;
+  const float mean = stats[2 * (b * Cc + c)], rstd = stats[2 * (b * Cc + c) + 1];
+  float v = (x[r * ldx + c] - mean) * rstd * w[c] + bb[c];
+  if (lrelu) v = v > 0.f ? v : 0.01f * v;
+  out[r * ldo + c] = v;
+}
+static int in_splits(long long HW) { return static_cast<int>(HW >= 65536 ? 32 : (HW >= 4096 ? 8 : 1)); }
+
 extern "C" int b2u_f32_instnorm(const float* in, int64_t ld_in, float* out, int64_t ld_out, const float* w, const float* b,
-                                int32_t B, int64_t HW, int32_t Cc, float eps, int32_t lrelu, b2u_stream_t stream_) {
-  dim3 grid((Cc + 31) / 32, B);
-  f32_instnorm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(in, ld_in, out, ld_out, w, b, HW, Cc, eps, lrelu);
+                                double* work, float* stats, int32_t B, int64_t HW, int32_t Cc, float eps, int32_t lrelu,
+                                b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || !w || !b || !work || !stats) return set_error(-1, "b2u_f32_instnorm: null pointer");
+  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2 * B * Cc, stream);
+  if (e != cudaSuccess) return set_error(-2, "b2u_f32_instnorm: memset: %s", cudaGetErrorString(e));
+  dim3 grid((Cc + 31) / 32, B, in_splits(HW));
+  f32_in_sum_kernel<<<grid, 256, 0, stream>>>(in, ld_in, HW, Cc, 0, work, B);
+  f32_in_sum_kernel<<<grid, 256, 0, stream>>>(in, ld_in, HW, Cc, 1, work, B);
+  f32_in_finish_kernel<<<(B * Cc + 255) / 256, 256, 0, stream>>>(work, stats, B, Cc, HW, eps);
+  const long long total = static_cast<long long>(B) * HW * Cc;
+  f32_in_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, ld_in, out, ld_out, stats, w, b, B, HW, Cc, lrelu);
   return check_launch("f32_instnorm");
 }
 

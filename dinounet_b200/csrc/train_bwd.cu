@@ -145,70 +145,76 @@ extern "C" int b2u_f32_layernorm_bwd(const float* x, const float* w, const float
 }
 
 // ---------------------------------------------------------------------------------------- InstanceNorm (+LeakyReLU) backward
-// y = lrelu(xhat * w + b), xhat = (x - mean) * rstd over HW per (n, c).  grid (C/32, B), block 32 channels x 8 row groups.
-__global__ void __launch_bounds__(256) f32_instnorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy,
-                                                               long long lddy, const float* __restrict__ w, const float* __restrict__ bb,
-                                                               float* __restrict__ dx, long long lddx, float* __restrict__ dw,
-                                                               float* __restrict__ db, long long HW, int Cc, float eps, int lrelu) {
-  __shared__ double red[8][33];
-  __shared__ double red2[8][33];
-  __shared__ float s_a[32], s_b[32];
+// y = lrelu(xhat * w + b), xhat = (x - mean) * rstd over HW per (n, c); (mean, rstd) = stats[B][C][2] saved by the forward.
+// pass 1 (rows split over gridDim.z, fp64 atomics): T1 = sum dy', T2 = sum dy' xhat per (n, c)  (dy' = dy * lrelu'(y));
+//         db += T1, dw += T2;   pass 2 (elementwise): dx = rstd * w * (dy' - T1/HW - xhat * T2/HW).
+__global__ void __launch_bounds__(256) f32_in_bwd_sum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy,
+                                                             long long lddy, const float* __restrict__ stats, const float* __restrict__ w,
+                                                             const float* __restrict__ bb, double* __restrict__ work, long long HW, int Cc,
+                                                             int B, int lrelu) {
+  __shared__ double red[8][33], red2[8][33];
   const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const long long b = blockIdx.y;
-  const bool ok = c < Cc;
-  const float* xb = x + b * HW * ldx;
-  const float* gb = dy + b * HW * lddy;
-  double s = 0.0;
-  if (ok) for (long long r = rg; r < HW; r += 8) s += xb[r * ldx + c];
-  red[rg][cx] = s;
-  __syncthreads();
-  if (rg == 0) { double t = 0.0; for (int k = 0; k < 8; ++k) t += red[k][cx]; s_a[cx] = static_cast<float>(t / HW); }
-  __syncthreads();
-  const float mean = s_a[cx];
-  double q = 0.0;
-  if (ok) for (long long r = rg; r < HW; r += 8) { const double d = static_cast<double>(xb[r * ldx + c]) - mean; q += d * d; }
-  __syncthreads();
-  red[rg][cx] = q;
-  __syncthreads();
-  if (rg == 0) { double t = 0.0; for (int k = 0; k < 8; ++k) t += red[k][cx]; s_b[cx] = 1.0f / sqrtf(static_cast<float>(t / HW) + eps); }
-  __syncthreads();
-  const float rstd = s_b[cx];
-  const float g = ok ? w[c] : 0.f, be = ok ? bb[c] : 0.f;
-  double t1 = 0.0, t2 = 0.0;                       // sum dy', sum dy' * xhat
-  if (ok)
-    for (long long r = rg; r < HW; r += 8) {
+  const long long per = (HW + gridDim.z - 1) / gridDim.z;
+  const long long lo = blockIdx.z * per, hi = lo + per < HW ? lo + per : HW;
+  double t1 = 0.0, t2 = 0.0;
+  if (c < Cc) {
+    const float mean = stats[2 * (b * Cc + c)], rstd = stats[2 * (b * Cc + c) + 1], g = w[c], be = bb[c];
+    const float* xb = x + b * HW * ldx;
+    const float* gb = dy + b * HW * lddy;
+    for (long long r = lo + rg; r < hi; r += 8) {
       const float xh = (xb[r * ldx + c] - mean) * rstd;
       float d = gb[r * lddy + c];
       if (lrelu && xh * g + be <= 0.f) d *= 0.01f;
       t1 += d;
       t2 += static_cast<double>(d) * xh;
     }
-  __syncthreads();
+  }
   red[rg][cx] = t1; red2[rg][cx] = t2;
   __syncthreads();
-  if (rg == 0) {
+  if (rg == 0 && c < Cc) {
     double a = 0.0, b2 = 0.0;
     for (int k = 0; k < 8; ++k) { a += red[k][cx]; b2 += red2[k][cx]; }
-    s_a[cx] = static_cast<float>(a); s_b[cx] = static_cast<float>(b2);
-    if (ok) { atomicAdd(&db[c], static_cast<float>(a)); atomicAdd(&dw[c], static_cast<float>(b2)); }
-  }
-  __syncthreads();
-  if (!ok) return;
-  const float T1 = s_a[cx], T2 = s_b[cx];
-  const float inv = 1.0f / static_cast<float>(HW);
-  float* ob = dx + b * HW * lddx;
-  for (long long r = rg; r < HW; r += 8) {
-    const float xh = (xb[r * ldx + c] - mean) * rstd;
-    float d = gb[r * lddy + c];
-    if (lrelu && xh * g + be <= 0.f) d *= 0.01f;
-    ob[r * lddx + c] = rstd * g * (d - inv * T1 - xh * inv * T2);
+    atomicAdd(&work[b * Cc + c], a);
+    atomicAdd(&work[(static_cast<long long>(B) + b) * Cc + c], b2);
   }
 }
+__global__ void f32_in_bwd_params_kernel(const double* __restrict__ work, float* __restrict__ dw, float* __restrict__ db, int B, int Cc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cc) return;
+  double a = 0.0, b2 = 0.0;
+  for (int b = 0; b < B; ++b) { a += work[static_cast<long long>(b) * Cc + c]; b2 += work[(static_cast<long long>(B) + b) * Cc + c]; }
+  db[c] += static_cast<float>(a);
+  dw[c] += static_cast<float>(b2);
+}
+__global__ void f32_in_bwd_dx_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long lddy,
+                                     const float* __restrict__ stats, const float* __restrict__ w, const float* __restrict__ bb,
+                                     const double* __restrict__ work, float* __restrict__ dx, long long lddx, int B, long long HW, int Cc,
+                                     int lrelu) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= B * HW * Cc) return;
+  const int c = static_cast<int>(i % Cc);
+  const long long r = i / Cc, b = r / HW;
+  const float mean = stats[2 * (b * Cc + c)], rstd = stats[2 * (b * Cc + c) + 1], g = w[c], be = bb[c];
+  const float inv = 1.0f / static_cast<float>(HW);
+  const float T1 = static_cast<float>(work[b * Cc + c]), T2 = static_cast<float>(work[(static_cast<long long>(B) + b) * Cc + c]);
+  const float xh = (x[r * ldx + c] - mean) * rstd;
+  float d = dy[r * lddy + c];
+  if (lrelu && xh * g + be <= 0.f) d *= 0.01f;
+  dx[r * lddx + c] = rstd * g * (d - inv * T1 - xh * inv * T2);
+}
 extern "C" int b2u_f32_instnorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, const float* w, const float* b,
-                                    float* dx, int64_t lddx, float* dw, float* db, int32_t B, int64_t HW, int32_t Cc, float eps,
-                                    int32_t lrelu, b2u_stream_t s) {
-  f32_instnorm_bwd_kernel<<<dim3((Cc + 31) / 32, B), 256, 0, static_cast<cudaStream_t>(s)>>>(x, ldx, dy, lddy, w, b, dx, lddx, dw, db, HW, Cc, eps, lrelu);
+                                    const float* stats, double* work, float* dx, int64_t lddx, float* dw, float* db, int32_t B,
+                                    int64_t HW, int32_t Cc, int32_t lrelu, b2u_stream_t s_) {
+  cudaStream_t s = static_cast<cudaStream_t>(s_);
+  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2 * B * Cc, s);
+  if (e != cudaSuccess) return set_error(-2, "b2u_f32_instnorm_bwd: memset: %s", cudaGetErrorString(e));
+  const int splits = static_cast<int>(HW >= 65536 ? 32 : (HW >= 4096 ? 8 : 1));
+  f32_in_bwd_sum_kernel<<<dim3((Cc + 31) / 32, B, splits), 256, 0, s>>>(x, ldx, dy, lddy, stats, w, b, work, HW, Cc, B, lrelu);
+  f32_in_bwd_params_kernel<<<(Cc + 255) / 256, 256, 0, s>>>(work, dw, db, B, Cc);
+  const long long total = static_cast<long long>(B) * HW * Cc;
+  f32_in_bwd_dx_kernel<<<blocks_for(total), 256, 0, s>>>(x, ldx, dy, lddy, stats, w, b, work, dx, lddx, B, HW, Cc, lrelu);
   return check_launch("f32_instnorm_bwd");
 }
 

@@ -181,6 +181,8 @@ def build_plan_fp32(eng, B: int, S: int):
     Yf = buf("Yf", (px0 * 32,))
     U1 = buf("U1", (px0 * 4 * 32,))
     pooled = buf("pooled", (B, 256))
+    in_work = buf("in_work", (2 * B * 256,), torch.float64)
+    in_stats = buf("in_stats", (B * 256 * 2,))
     feats = eng.features
     cat = [buf("cat0", (B * S4 * S4, 2 * feats[2])), buf("cat1", (B * S2 * S2, 2 * feats[1])), buf("cat2", (B * S * S, 2 * feats[0]))]
     skip3 = buf("skip3", (B * S8 * S8, feats[3]))
@@ -194,13 +196,13 @@ def build_plan_fp32(eng, B: int, S: int):
         gemm(pre + "film_gen", ZZ, px, R, 2 * R, w[pre + "film"], 2 * R, GB, 2 * R, bias=w[pre + "filmb"])
         plan.add(pre + "film", lib.b2u_f32_film, _ptr(GB), _ptr(ZZ), _ptr(Z), px, R)
         gemm(pre + "reduce_sc", Z, px, R, R, w[pre + "w3"], n3_, RS, n3_, bias=w[pre + "b3"])
-        plan.add(pre + "in1", lib.b2u_f32_instnorm, _ptr(RS), n3_, _ptr(T1), oc, _ptr(w[pre + "in1w"]), _ptr(w[pre + "in1b"]), B,
-                 r * r, oc, cfg.IN_EPS, 1)
+        plan.add(pre + "in1", lib.b2u_f32_instnorm, _ptr(RS), n3_, _ptr(T1), oc, _ptr(w[pre + "in1w"]), _ptr(w[pre + "in1b"]), _ptr(in_work),
+                 _ptr(in_stats), B, r * r, oc, cfg.IN_EPS, 1)
         plan.add(pre + "dw", lib.b2u_f32_dwconv3x3, _ptr(T1), _ptr(T2), _ptr(w[pre + "dw"]), _ptr(w[pre + "dwb"]), B, r, r, oc, 1,
                  L.ACT_NONE)
         gemm(pre + "pw", T2, px, oc, oc, w[pre + "pw"], oc, T1, oc, bias=w[pre + "pwb"])
-        plan.add(pre + "in2", lib.b2u_f32_instnorm, _ptr(T1), oc, _ptr(T2), oc, _ptr(w[pre + "in2w"]), _ptr(w[pre + "in2b"]), B,
-                 r * r, oc, cfg.IN_EPS, 1)
+        plan.add(pre + "in2", lib.b2u_f32_instnorm, _ptr(T1), oc, _ptr(T2), oc, _ptr(w[pre + "in2w"]), _ptr(w[pre + "in2b"]), _ptr(in_work),
+                 _ptr(in_stats), B, r * r, oc, cfg.IN_EPS, 1)
         gemm(pre + "refine", T2, px, oc, oc, w[pre + "ref"], oc, T1, oc, bias=w[pre + "refb"])
         if has_sc:
             sc_ptr, ldsc = RS.data_ptr() + oc * 4, n3_
@@ -234,7 +236,7 @@ def build_plan_fp32(eng, B: int, S: int):
             gemm(f"d{s}.conv{j}", src, B * r_hi * r_hi, W.shape[1], cin, W, skip, CO, skip, bias=w[f"d{s}.c{j}b"],
                  conv=L.CONV3X3_S1, img=(r_hi, r_hi, cin))
             plan.add(f"d{s}.in{j}", lib.b2u_f32_instnorm, _ptr(CO), skip, _ptr(CA), skip, _ptr(w[f"d{s}.n{j}w"]),
-                     _ptr(w[f"d{s}.n{j}b"]), B, r_hi * r_hi, skip, cfg.IN_EPS, 1)
+                     _ptr(w[f"d{s}.n{j}b"]), _ptr(in_work), _ptr(in_stats), B, r_hi * r_hi, skip, cfg.IN_EPS, 1)
             src, cin = CA, skip
         lres, below = CA, skip
     gemm("seg", CA, B * S * S, feats[0], feats[0], w["seg.w"], eng.ncls, lin, eng.ncls, bias=w["seg.b"])

@@ -115,7 +115,7 @@ SIGNATURES = {
     "b2u_f32_dwconv3x3": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "b2u_f32_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp],
     "b2u_f32_msda": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
-    "b2u_f32_instnorm": [vp, i64, vp, i64, vp, vp, i32, i64, i32, f32, i32, vp],
+    "b2u_f32_instnorm": [vp, i64, vp, i64, vp, vp, vp, vp, i32, i64, i32, f32, i32, vp],
     "b2u_f32_se": [vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp],
     "b2u_f32_film": [vp, vp, vp, i64, i32, vp],
     "b2u_f32_tail": [vp, i64, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
@@ -124,7 +124,7 @@ SIGNATURES = {
     "b2u_f32_act_bwd": [vp, vp, vp, i64, i32, vp],
     "b2u_f32_colsum": [vp, i64, i64, i32, vp, vp],
     "b2u_f32_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp],
-    "b2u_f32_instnorm_bwd": [vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, i32, i64, i32, f32, i32, vp],
+    "b2u_f32_instnorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, i64, i32, i32, vp],
     "b2u_f32_bn_act": [vp, vp, vp, vp, vp, vp, f32, i64, i32, i32, vp],
     "b2u_f32_bn_act_bwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, i64, i32, i32, vp],
     "b2u_f32_dwconv_wgrad": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],

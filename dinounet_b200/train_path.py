@@ -131,8 +131,11 @@ class Conv3x3F(Function):
             else:
                 _call("b2u_f32_conv3x3_dgrad", dy, Wp, dx, B, H, Wd, Cc, Cc, N, stride)
         if ctx.needs_input_grad[1]:
+            # dWp[n, (tap, c)] = sum_pix dy[pix, n] * window(x)[pix, tap, c]: the GEMM with A' = dy^T and the window on the W side
             dWp = torch.zeros_like(Wp)
-            _call("b2u_f32_conv3x3_wgrad", x, dy, dWp, B, H, Wd, Cc, Cc, N, stride)
+            npix = B * Ho * Wo
+            _gemm(dy, x, dWp, N, 9 * Cc, npix, a_trans=1, lda=N, w_mode=3, conv=L.CONV3X3_S2 if stride == 2 else L.CONV3X3_S1,
+                  img=(H, Wd, Cc), cpad=Cc, ksplit=max(1, min(256, npix // 4096)))
             dW = dWp.view(N, 3, 3, Cc).permute(0, 3, 1, 2).contiguous()
         if ctx.has_b and ctx.needs_input_grad[2]:
             db = _colsum(dy, N)
@@ -203,19 +206,22 @@ class InstNormLReLUF(Function):
         x = x.contiguous()
         Cc = x.shape[1]
         y = torch.empty_like(x)
-        _call("b2u_f32_instnorm", x, Cc, y, Cc, g, b, B, HW, Cc, cfg.IN_EPS, 1)
-        ctx.save_for_backward(x, g, b)
+        work = torch.empty(2 * B * Cc, dtype=torch.float64, device=x.device)
+        stats = torch.empty(2 * B * Cc, dtype=torch.float32, device=x.device)
+        _call("b2u_f32_instnorm", x, Cc, y, Cc, g, b, work, stats, B, HW, Cc, cfg.IN_EPS, 1)
+        ctx.save_for_backward(x, g, b, stats)
         ctx.geo = (B, HW, Cc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, g, b = ctx.saved_tensors
+        x, g, b, stats = ctx.saved_tensors
         B, HW, Cc = ctx.geo
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         dg, db = torch.zeros_like(g), torch.zeros_like(b)
-        _call("b2u_f32_instnorm_bwd", x, Cc, dy, Cc, g, b, dx, Cc, dg, db, B, HW, Cc, cfg.IN_EPS, 1)
+        work = torch.empty(2 * B * Cc, dtype=torch.float64, device=x.device)
+        _call("b2u_f32_instnorm_bwd", x, Cc, dy, Cc, g, b, stats, work, dx, Cc, dg, db, B, HW, Cc, 1)
         return dx, dg, db, None, None
 
 
@@ -532,17 +538,50 @@ class AddF(Function):
 
 
 # ------------------------------------------------------------------------------------------------------------ optimizer
+def all_reduce_gradients(params, group=None, average: bool = True):
+    """Data-parallel gradient exchange (what DDP does for the reference, nnUNetTrainer.py:216-218): the gradients of the
+    ~13-20 M trainable parameters are packed into ONE flat fp32 buffer and summed with a single all-reduce (NCCL over
+    NVLink / NVSwitch on GPUs, gloo in the CPU tests), then unpacked in place.  52-80 MB per step: far below the compute
+    time of a step, so one bucket is enough; parameters without a gradient contribute zeros so every rank packs the same
+    layout."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    ps = [p for p in params if p.requires_grad]
+    if not ps:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in ps:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+
+
 class FusedSGD:
     """torch.optim.SGD(lr, weight_decay, momentum 0.99, nesterov=True) + clip_grad_norm_(12) (nnUNetTrainer.py:486-489,
     922-923) on the hand-written kernels: one squared-norm reduction per tensor into a device scalar, then one fused update
-    per tensor that reads the clip coefficient from device memory (no host synchronisation)."""
+    per tensor that reads the clip coefficient from device memory (no host synchronisation).  `param_groups[0]["lr"]` is
+    what the reference's PolyLRScheduler writes (training/lr_scheduler/polylr.py)."""
 
     def __init__(self, params, lr: float, weight_decay: float = 3e-5, momentum: float = 0.99, max_norm: float = 12.0):
         self.params = [p for p in params if p.requires_grad]
-        self.lr, self.wd, self.mom, self.max_norm = lr, weight_decay, momentum, max_norm
+        self.param_groups = [{"params": self.params, "lr": lr, "weight_decay": weight_decay, "momentum": momentum, "nesterov": True}]
+        self.max_norm = max_norm
         self.bufs = [torch.zeros_like(p) for p in self.params]
         self.first = True
         self._sq = None
+
+    lr = property(lambda self: self.param_groups[0]["lr"])
+    wd = property(lambda self: self.param_groups[0]["weight_decay"])
+    mom = property(lambda self: self.param_groups[0]["momentum"])
 
     @torch.no_grad()
     def step(self):
@@ -568,6 +607,18 @@ class FusedSGD:
     def grad_norm(self) -> float:
         return float(self._sq.sqrt().item())
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
             p.grad = None
+
+
+def train_step(net, loss_fn, optimizer: FusedSGD, data: torch.Tensor, target: torch.Tensor, group=None) -> torch.Tensor:
+    """One optimisation step with the semantics of `nnUNetTrainer.train_step` (nnUNetTrainer.py:899-929): zero grads,
+    forward, Dice+CE, backward, (data-parallel: one gradient all-reduce), clip 12, SGD-nesterov.  fp32 end to end outside the
+    frozen ViT (no GradScaler: there is no fp16 gradient to scale).  Returns the detached loss."""
+    optimizer.zero_grad()
+    loss = loss_fn(net(data), target)
+    loss.backward()
+    all_reduce_gradients(optimizer.params, group)
+    optimizer.step()
+    return loss.detach()

@@ -65,6 +65,30 @@ class DinoUNetTrainer(_Base):
                                "ddp": self.is_ddp}, {}, weight_ce=1, weight_dice=1,
                               ignore_label=self.label_manager.ignore_label)
 
+    # ---- training step on the B200 path (nnUNetTrainer.py:486-489, 899-929)
+    def configure_optimizers(self):
+        """SGD(momentum 0.99, nesterov, weight decay) + the reference's PolyLRScheduler (it only writes param_groups[0]['lr'])
+        on the fused kernels; gradient clipping (12) is part of the fused step."""
+        from .train_path import FusedSGD
+        optimizer = FusedSGD(self.network.parameters(), self.initial_lr, weight_decay=self.weight_decay, momentum=0.99, max_norm=12.0)
+        try:
+            from dinounet.training.lr_scheduler.polylr import PolyLRScheduler
+            lr_scheduler = PolyLRScheduler(optimizer, self.initial_lr, self.num_epochs)
+        except Exception:  # pragma: no cover - reference stack absent
+            lr_scheduler = None
+        return optimizer, lr_scheduler
+
+    def train_step(self, batch: dict) -> dict:
+        from .train_path import train_step
+        data = batch["data"].to(self.device, non_blocking=True)
+        target = batch["target"]
+        if isinstance(target, list):
+            target = target[0]
+        target = target.to(self.device, non_blocking=True)
+        net = self.network.module if hasattr(self.network, "module") else self.network
+        loss = train_step(net, self.loss, self.optimizer, data, target)
+        return {"loss": loss.cpu().numpy()}
+
     def validation_step(self, batch: dict) -> dict:
         """One online-validation batch: B200 forward, then loss + hard tp/fp/fn in one fused pass over the logits."""
         data = batch["data"].to(self.device, non_blocking=True)

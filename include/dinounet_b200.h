@@ -304,6 +304,7 @@ typedef struct b2u_f32_gemm_params {
   int64_t ldres;
   /* backward-pass addressing (csrc/train_bwd.cu callers): a_trans: A'(m, k) = A[k][m]; w_mode 1: W'(n, k) = W[k][n];
    * w_mode 2 (with conv != 0): 3x3 data gradient, W'(c, (tap', n)) = W[n][(8 - tap') * w_cpad + c];
+   * w_mode 3 (with conv != 0, a_trans): 3x3 weight gradient, W is the layer's NHWC input, W'((tap, c), pixel) = its window;
    * ksplit > 1: the K range is split over gridDim.z and the raw products are atomically ADDED to out (zero it first);
    * accumulate: out += instead of out =. */
   int32_t a_trans, w_mode, w_cpad, ksplit, accumulate;
@@ -323,8 +324,9 @@ int b2u_f32_attention(const float* qkv, const float* rope_sin, const float* rope
                       int32_t heads, int32_t head_dim, int32_t prefix, float scale, b2u_stream_t stream);
 int b2u_f32_msda(const float* value, const float* offaw, float* out, int32_t B, int32_t Hv, int32_t Wv, int32_t heads,
                  int32_t dh, b2u_stream_t stream);                                                 /* ms_deform_attn.py:158-216 */
-int b2u_f32_instnorm(const float* in, int64_t ld_in, float* out, int64_t ld_out, const float* w, const float* b, int32_t B,
-                     int64_t HW, int32_t C, float eps, int32_t lrelu, b2u_stream_t stream);
+/* InstanceNorm2d(affine) (+ LeakyReLU 0.01): work = 2*B*C doubles (scratch), stats = [B][C][2] floats (mean, rstd) out */
+int b2u_f32_instnorm(const float* in, int64_t ld_in, float* out, int64_t ld_out, const float* w, const float* b, double* work,
+                     float* stats, int32_t B, int64_t HW, int32_t C, float eps, int32_t lrelu, b2u_stream_t stream);
 int b2u_f32_se(const float* t, const float* shortcut, int64_t ld_shortcut, float* pooled_work, const float* w1, const float* b1,
                const float* w2, const float* b2, float* out, int32_t B, int64_t HW, int32_t C, int32_t hidden, b2u_stream_t stream);
 int b2u_f32_film(const float* gamma_beta, const float* zs_zp, float* z, int64_t px, int32_t R, b2u_stream_t stream);
@@ -342,9 +344,9 @@ int b2u_f32_act_bwd(const float* x_pre, const float* dy, float* dx, int64_t n, i
 int b2u_f32_colsum(const float* in, int64_t ld, int64_t rows, int32_t C, float* out_accum, b2u_stream_t stream);
 int b2u_f32_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int64_t rows,
                           int32_t D, float eps, b2u_stream_t stream);
-int b2u_f32_instnorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, const float* w, const float* b, float* dx,
-                         int64_t lddx, float* dw, float* db, int32_t B, int64_t HW, int32_t C, float eps, int32_t lrelu,
-                         b2u_stream_t stream);
+int b2u_f32_instnorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, const float* w, const float* b,
+                         const float* stats, double* work, float* dx, int64_t lddx, float* dw, float* db, int32_t B, int64_t HW,
+                         int32_t C, int32_t lrelu, b2u_stream_t stream);
 /* eval-mode (Sync)BatchNorm + optional ReLU, forward and backward (the gradient oracle's semantics) */
 int b2u_f32_bn_act(const float* x, float* y, const float* gamma, const float* beta, const float* running_mean,
                    const float* running_var, float eps, int64_t rows, int32_t C, int32_t act, b2u_stream_t stream);

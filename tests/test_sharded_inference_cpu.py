@@ -98,3 +98,42 @@ def test_two_rank_gloo_slice_sharded_sliding_window(n_slices):
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
     assert all(shape == (2, n_slices, 6, 5) and dt == "torch.float16" for _, _, shape, dt in res)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dinounet_b200.train_path import all_reduce_gradients
+        g = torch.Generator().manual_seed(5)
+        ps = [torch.randn(7, 3, generator=g).requires_grad_(), torch.randn(11, generator=g).requires_grad_(),
+              torch.randn(2, 2, generator=g).requires_grad_(), torch.randn(4, generator=g)]       # last one: frozen
+        grads = [[torch.full_like(p, float(r + 1) * (i + 1)) for i, p in enumerate(ps)] for r in range(world)]
+        ps[0].grad, ps[1].grad = grads[rank][0].clone(), grads[rank][1].clone()
+        if rank == 0:
+            ps[2].grad = grads[rank][2].clone()          # rank 1 has no gradient for this tensor: contributes zeros
+        all_reduce_gradients(ps)
+        ok = torch.allclose(ps[0].grad, sum(grads[r][0] for r in range(world)) / world)
+        ok = ok and torch.allclose(ps[1].grad, sum(grads[r][1] for r in range(world)) / world)
+        ok = ok and torch.allclose(ps[2].grad, grads[0][2] / world) and ps[3].grad is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_all_reduce():
+    """Data-parallel training exchange (train_path.all_reduce_gradients): one flat all-reduce, mean over ranks, ranks
+    without a gradient for some tensor contribute zeros, frozen parameters are left alone."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
