@@ -26,3 +26,15 @@ except Exception as e:
     print("${M} N=${N}: FAILED", e)
 PY
 done
+if [ -n "$TRAIN" ]; then
+  PORT=$((PORT+1))
+  if [ "$N" -eq 1 ]; then
+    timeout 900 python bench.py --mode train --model dinounet_b --batch 64 --steps 3 --warmup 3 > gpurun_out/${TAG}_train_b_n${N}.json 2> gpurun_out/${TAG}_train_b_n${N}.err
+  else
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT bench.py --mode train --gpus $N --model dinounet_b --batch 64 --steps 3 --warmup 3 > gpurun_out/${TAG}_train_b_n${N}.json 2> gpurun_out/${TAG}_train_b_n${N}.err
+  fi
+  tail -c 400 gpurun_out/${TAG}_train_b_n${N}.json | head -c 400; echo
+  python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_train_b_n${N}.json').read().strip().splitlines()[-1]); print('train dinounet_b N=${N}:', round(d['value'],1), 'patches/s', round(d['ms_per_step'],1), 'ms/step')" || tail -3 gpurun_out/${TAG}_train_b_n${N}.err
+fi
