@@ -302,6 +302,54 @@ def run_train(a):
         dist.destroy_process_group()
 
 
+def run_reference_cuda_train(a):
+    """The reference's training step as torch eager + autograd on the B200 (library kernels, the reference's autocast regime,
+    its differentiable pure-PyTorch deformable-attention core instead of the CUDA extension): forward, Dice+CE, backward, clip,
+    SGD-nesterov.  Informational arm beside `--mode train`."""
+    import torch
+    from oracle import dinounet_oracle as O
+    from oracle import grad_oracle as G
+    from oracle import loss_oracle as LO
+    dev = torch.device("cuda", 0)
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(a.model, 2, seed=0).items()}
+    keys = G.trainable_keys(a.model, 2)
+    P = dict(sd)
+    leaves = {k: P[k].clone().requires_grad_(True) for k in keys}
+    for k, v in O.expand_aliases(leaves).items():
+        P[k] = v
+    opt = torch.optim.SGD(list(leaves.values()), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    v = O.VARIANTS[a.model]
+    B, S = a.batch, a.size
+    xs = [O.make_input(B, S, 100 + i).to(dev) for i in range(2)]
+    ts = [torch.randint(0, 2, (B, 1, S, S), generator=torch.Generator().manual_seed(i)).float().to(dev) for i in range(2)]
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            logits = O.decoder_forward(P, O.encoder_forward(P, v, xs[i % 2], True, None), None)
+            loss, _, _ = LO.dc_and_ce_loss(logits.float(), ts[i % 2], batch_dice=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(leaves.values()), 12)
+        opt.step()
+        return loss
+
+    for i in range(max(2, a.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    print(json.dumps({"impl": "reference-cuda", "mode": "train", "metric": "2D patches/sec (512x512) fwd+bwd (Dice+CE) + SGD step",
+                      "value": B / ms * 1e3, "unit": "patches/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+                      "higher_is_better": True, "dtype": "fp16/bf16 autocast (torch eager + autograd, library kernels)", "data": "synthetic",
+                      "config": {"workload": f"{a.model} train step, {S}x{S}x3, batch {B}"}, "loss": float(loss),
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+
+
 def run_reference_cuda(a):
     """the same oracle port run by PyTorch eager on the B200 in the reference's GPU precision
     regime (outer fp16 autocast, inner bf16 ViT, fp32 MSDA) — what a user gets from the reference code on this GPU
@@ -336,7 +384,7 @@ def main():
     if a.impl == "reference":
         return run_reference(a)
     if a.impl == "reference-cuda":
-        return run_reference_cuda(a)
+        return run_reference_cuda_train(a) if a.mode == "train" else run_reference_cuda(a)
     if a.mode == "train":
         return run_train(a)
     import torch

@@ -1,4 +1,4 @@
-"""A/B timing of the tcgen05 attention kernels at the bench shape (dinounet_l, B=32: 512 (batch, head) pairs x 1029 tokens)
+"""Timing of the tcgen05 attention kernel (and its single-pass softmax variant, option 4 = 4) at the bench shape (dinounet_l, B=32: 512 (batch, head) pairs x 1029 tokens)
 and at the cfg-5 sweep points (head_dim 64 / 128, N 261 / 1029, several batches): CUDA events on the launch stream,
 inputs rotated so that no launch starts on a warm L2 copy of its own K/V.
     python tools/bench_attn.py [out.json]
@@ -61,12 +61,12 @@ def time_case(B, H, N, hd, opt, reps=12):
     us = e0.elapsed_time(e1) / reps * 1e3
     tf = 4.0 * N * N * hd * B * H / (us * 1e-6) / 1e12
     lib.b2u_set_option(4, 0)
-    return {"B": B, "heads": H, "N": N, "head_dim": hd, "kernel": {0: "gen3", 2: "gen2", 4: "gen3-onepass", 5: "gen4"}[opt], "us": round(us, 1),
+    return {"B": B, "heads": H, "N": N, "head_dim": hd, "kernel": {0: "gen3", 4: "gen3-onepass"}[opt], "us": round(us, 1),
             "tflops": round(tf, 1), "frac_of_sustained_bf16_peak": round(tf / peak, 3), "rel_err_vs_sdpa": err}
 
 
 rows = []
-for opt in (0, 4, 5):
+for opt in (0, 4):
     rows.append(time_case(32, 16, 1029, 64, opt))
     print(rows[-1], flush=True)
 if "--sweep" in sys.argv:
