@@ -64,9 +64,11 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
     a.Wo = p->Win / stride;
     a.cb = (p->C + BK - 1) / BK;
     a.num_kb = 9 * a.cb;
-    a.TW = a.Wo >= 128 ? 128 : a.Wo;
-    if (a.TW & (a.TW - 1)) return set_error(-1, "b2u_gemm(conv): output width must be a power of two (<128) or >=128");
-    if (a.Wo % a.TW) return set_error(-1, "b2u_gemm(conv): output width must be a multiple of the tile width");
+    // tile = TH x TW = 128 output pixels; TW = the largest power of two (<= 128) that divides the output width, so any
+    // width that is a multiple of 4 tiles exactly in x (rows past the image are masked in the epilogue, OOB = zero fill)
+    a.TW = 128;
+    while (a.TW > 1 && (a.Wo % a.TW)) a.TW >>= 1;
+    if (a.TW < 4) return set_error(-1, "b2u_gemm(conv): output width must be a multiple of 4");
     a.TH = BM / a.TW;
     a.tiles_x = a.Wo / a.TW;
     a.tiles_y = (a.Ho + a.TH - 1) / a.TH;

@@ -273,10 +273,12 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ plan
     def build_plan(self, B: int, S: int) -> Tuple[Plan, dict]:
-        if S < 128 or (S & (S - 1)):
-            # the conv tiles want power-of-two row widths below 128 px and 128-multiples above, on every pyramid level
-            # (S/2 ... S/32), and the three-plane depthwise conv needs S/16 % 8 == 0; the reference's plans force 512
-            raise ValueError("input size must be a power of two >= 128 (the reference's plan forces 512x512)")
+        if S < 128 or S % 128:
+            # every pyramid level (S/2 ... S/32) must tile: conv row widths multiples of 4, the halo-mode convs multiples of 8,
+            # the three-plane depthwise conv S/16 % 8 == 0 -> multiples of 128 (128, 256, 384, 512, 640, ...); the reference's
+            # plans force 512
+            raise ValueError("input size must be a multiple of 128 (the reference's plan forces 512x512); the fp32 tier takes "
+                             "multiples of 32")
         v, w, lib = self.v, self.w, self.lib
         vt, rt, tv, tr = self.vt, self.rt, self.tv, self.tr
         D, Hh = v.embed_dim, v.num_heads

@@ -149,8 +149,8 @@ def test_engine_rejects_unsupported_patch_sizes_with_a_clear_error():
     from oracle import dinounet_oracle as O
     sd = {k: v for k, v in O.make_state_dict("dinounet_s", 2, seed=0).items() if not k.startswith("decoder.encoder.")}
     eng = ForwardEngine.__new__(ForwardEngine)          # build_plan's size check comes before any device work
-    for S in (96, 160, 384, 500):
-        with pytest.raises(ValueError, match="power of two"):
+    for S in (96, 160, 320, 500):
+        with pytest.raises(ValueError, match="multiple of 128"):
             ForwardEngine.build_plan(eng, 1, S)
 
 

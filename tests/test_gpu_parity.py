@@ -308,3 +308,19 @@ def test_frozen_vit_feature_caching_is_bit_identical():
     assert torch.equal(y2, y) and torch.equal(y3, y) and not torch.equal(other, y)
     plan, _ = net._engine.get_plan(2, 256)
     assert n_rest == len(plan.calls) - plan.vit_end and plan.vit_end > 0.3 * len(plan.calls)
+
+
+@pytest.mark.parametrize("S", [384, 640])
+def test_forward_non_power_of_two_sizes(S):
+    """Sizes that are multiples of 128 but not powers of two (h = 24 / 40 patch rows, N = 581 / 1605 tokens, 48- / 80-px conv
+    rows): against the oracle run live on the host (no golden: the oracle is pinned to the reference by the other cases)."""
+    model = "dinounet_s"
+    sd = O.make_state_dict(model, 2, seed=0)
+    x = O.make_input(1, S, 11)
+    net = _net(model, sd)
+    with torch.no_grad():
+        y = net(x.cuda()).float().cpu()
+        yg, lab = net._engine.forward(x.cuda(), use_graph=True)
+    ref = O.forward(sd, model, x)
+    _compare(y, ref, None, f"{model} {S}x{S} vs oracle")
+    assert torch.equal(yg.float().cpu(), y) and torch.equal(lab.long().cpu(), y.argmax(1))
