@@ -38,6 +38,7 @@ def parse():
                     help="adapter query stream storage: fp32 = the reference's dtype (default), 16 = opt-in reduced storage")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--gemm-pair", default="on", choices=["on", "off"], help="CTA-pair (cta_group::2) GEMM tiles (A/B switch)")
+    ap.add_argument("--pdl", default="off", choices=["on", "off"], help="programmatic dependent launch across the plan (A/B switch; measured slower, default off)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="patches in the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--eager-steps", type=int, default=10, help="timed steps of the torch-eager CUDA arm at N=1 (0 = skip)")
     ap.add_argument("--ops-out", default="", help="write the per-kernel timing breakdown (JSON) here")
@@ -406,6 +407,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib.load().b2u_set_option(3, 1 if a.gemm_pair == "off" else 0)
+    lib.load().b2u_set_option(5, 1 if a.pdl == "on" else 0)
 
     B, S, K, W = a.batch, a.size, a.steps, max(3, a.warmup)
     if a.model == "dinounet_7b":
@@ -567,7 +569,7 @@ def main():
             "config": {"workload": f"{a.model} forward, {S}x{S}x3, per-GPU batch {B}, random-init weights" + (" (generated on device)" if a.model == "dinounet_7b" else " (seed 0)"),
                        "global_batch": B * world, "parallelism": f"batch-sharded dp{world} + 1 NCCL all-gather of fp16 logits per step (side stream, double-buffered)" if world > 1 else "single GPU",
                        "l2": "3 resident input batches rotated (3x%.0f MB) and a per-step activation working set >> 126 MB L2" % (B * 3 * S * S * 4 / 1e6),
-                       "cuda_graph": use_graph},
+                       "cuda_graph": use_graph, "programmatic_dependent_launch": a.pdl == "on"},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                     "d2h_bytes_per_step": B * 2 * S * S * 4},
             "gpu_launches": K * n_kernels, "kernels_per_step": n_kernels,

@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                              // prologue done: wait for the QKV kernel's q / k / v^T
   const int J = args.nchunks;
   const int tail_valid = args.ntok - (J - 1) * 128;          // valid keys of the last chunk, 1..128
   const int tail_n = (tail_valid + 15) & ~15;                // MMA width of the last chunk (N of S, K of PV)
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
       pair_sync();                                   // the partner has read my staged chunks: P smem may be rewritten
     }
   }
+  pdl_launch_dependents();   // this CTA's items are done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -504,7 +506,7 @@ static int launch_attn_tc3(const AttnMaps& maps, const AttnArgs& a, cudaStream_t
   }
   const int sms = num_sms();
   const int grid = static_cast<int>(a.items < sms ? a.items : sms);
-  kern<<<grid, CF::kThreads, CF::kSmem, stream>>>(maps, a);
+  launch_pdl(kern, grid, CF::kThreads, CF::kSmem, stream, maps, a);
   return check_launch("attention_tc3");
 }
 

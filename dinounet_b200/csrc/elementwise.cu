@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int rows, int D, float eps, int rows_in, int rows_out,
                                                         int row_off) {
+  pdl_begin();
   using In = LnIn<T, IN16>;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -100,6 +101,7 @@ template <typename T, bool OUT32, bool IN16, int NV>
 __global__ void __launch_bounds__(256) layernorm_reg_kernel(const void* __restrict__ in, void* __restrict__ out,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int rows, float eps, int rows_in, int rows_out, int row_off) {
+  pdl_begin();
   using In = LnIn<T, IN16>;
   constexpr int D = 128 * NV;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -145,14 +147,14 @@ static void layernorm_launch(const void* in, void* out, const float* gamma, cons
   const int grid = blocks_for(rows, 8);
 #define B2U_LN_REG(NV_)                                                                                                 \
   case 128 * NV_:                                                                                                       \
-    layernorm_reg_kernel<T, OUT32, IN16, NV_><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, eps, rows_in, rows_out, row_off); \
+    launch_pdl(layernorm_reg_kernel<T, OUT32, IN16, NV_>, grid, 256, 0, stream, in, out, gamma, beta, rows, eps, rows_in, rows_out, row_off); \
     return;
   switch (D) {
     B2U_LN_REG(3) B2U_LN_REG(6) B2U_LN_REG(8)      // 384 / 768 / 1024 (ViT-S/B/L and their adapters)
     default: break;
   }
 #undef B2U_LN_REG
-  layernorm_kernel<T, OUT32, IN16><<<grid, 256, 0, stream>>>(in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
+  launch_pdl(layernorm_kernel<T, OUT32, IN16>, grid, 256, 0, stream, in, out, gamma, beta, rows, D, eps, rows_in, rows_out, row_off);
 }
 
 static int layernorm_impl(const void* in, bool in16, void* out, const float* gamma, const float* beta, int32_t rows,
@@ -189,6 +191,7 @@ extern "C" int b2u_layernorm16(const void* in, void* out, const float* gamma, co
 template <typename T>
 __global__ void cast_rows_kernel(const float* __restrict__ in, T* __restrict__ out, long long total8, int D8,
                                  int rows_in, int rows_out, int row_off) {
+  pdl_begin();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const long long r = i / D8;
@@ -208,7 +211,7 @@ extern "C" int b2u_cast_rows(const float* in, void* out, int32_t rows, int32_t D
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (D % 8) return set_error(-1, "b2u_cast_rows: D %% 8 != 0");
   const long long total8 = static_cast<long long>(rows) * (D / 8);
-  B2U_DISPATCH_T(dtype, (cast_rows_kernel<T><<<blocks_for(total8, 256), 256, 0, stream>>>(
+  B2U_DISPATCH_T(dtype, (launch_pdl(cast_rows_kernel<T>, blocks_for(total8, 256), 256, 0, stream, 
                              in, static_cast<T*>(out), total8, D / 8, rows_in, rows_out, row_off)));
   return check_launch("cast_rows");
 }
@@ -216,6 +219,7 @@ extern "C" int b2u_cast_rows(const float* in, void* out, int32_t rows, int32_t D
 // 16-bit row gather (same row selection as b2u_cast_rows): 16 bytes per thread
 __global__ void copy_rows16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total8, int D8,
                                    int rows_in, int rows_out, int row_off) {
+  pdl_begin();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const long long r = i / D8;
@@ -230,7 +234,7 @@ extern "C" int b2u_copy_rows16(const void* in, void* out, int32_t rows, int32_t 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (D % 8) return set_error(-1, "b2u_copy_rows16: D %% 8 != 0");
   const long long total8 = static_cast<long long>(rows) * (D / 8);
-  copy_rows16_kernel<<<blocks_for(total8, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out),
+  launch_pdl(copy_rows16_kernel, blocks_for(total8, 256), 256, 0, stream, static_cast<const uint4*>(in), static_cast<uint4*>(out),
                                                                  total8, D / 8, rows_in, rows_out, row_off);
   return check_launch("copy_rows16");
 }
@@ -238,6 +242,7 @@ extern "C" int b2u_copy_rows16(const void* in, void* out, int32_t rows, int32_t 
 // ------------------------------------------------------------------------------------------------ patchify
 template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int S) {
+  pdl_begin();
   // one thread per (patch, c, ky, half) -> 8 consecutive kx
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int w = S / 16;
@@ -261,12 +266,13 @@ extern "C" int b2u_patchify(const float* x, void* out, int32_t B, int32_t S, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (S % 16) return set_error(-1, "b2u_patchify: S %% 16 != 0");
   const long long total = static_cast<long long>(B) * (S / 16) * (S / 16) * 96;
-  B2U_DISPATCH_T(dtype, (patchify_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(x, static_cast<T*>(out), B, S)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(patchify_kernel<T>, blocks_for(total, 256), 256, 0, stream, x, static_cast<T*>(out), B, S)));
   return check_launch("patchify");
 }
 
 __global__ void write_prefix_kernel(float* __restrict__ X, const float* __restrict__ prefix, int B, int ntok,
                                     int n_prefix, int D) {
+  pdl_begin();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = B * n_prefix * D;
   if (i >= total) return;
@@ -277,7 +283,7 @@ __global__ void write_prefix_kernel(float* __restrict__ X, const float* __restri
 extern "C" int b2u_write_prefix(float* X, const float* prefix, int32_t B, int32_t ntok, int32_t n_prefix, int32_t D,
                                 b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  write_prefix_kernel<<<blocks_for(static_cast<long long>(B) * n_prefix * D, 256), 256, 0, stream>>>(X, prefix, B, ntok, n_prefix, D);
+  launch_pdl(write_prefix_kernel, blocks_for(static_cast<long long>(B) * n_prefix * D, 256), 256, 0, stream, X, prefix, B, ntok, n_prefix, D);
   return check_launch("write_prefix");
 }
 
@@ -288,6 +294,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) stem_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          T* __restrict__ out, int B, int S) {
+  pdl_begin();
   __shared__ float sw[27 * 64];
   __shared__ float ssc[64], ssh[64];
   for (int i = threadIdx.x; i < 27 * 64; i += 256) {
@@ -354,13 +361,14 @@ extern "C" int b2u_stem_conv0(const float* x, const float* w, const float* scale
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (S % 8) return set_error(-1, "b2u_stem_conv0: S %% 8 != 0");
   const long long total = static_cast<long long>(B) * (S / 2) * (S / 8) * 8;
-  B2U_DISPATCH_T(dtype, (stem_conv0_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(x, w, scale, shift, static_cast<T*>(out), B, S)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(stem_conv0_kernel<T>, blocks_for(total, 256), 256, 0, stream, x, w, scale, shift, static_cast<T*>(out), B, S)));
   return check_launch("stem_conv0");
 }
 
 // ------------------------------------------------------------------------------------------------ maxpool 3x3 s2 p1
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C8) {
+  pdl_begin();
   const int Ho = H / 2, Wo = W / 2;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * Ho * Wo * C8;
@@ -395,7 +403,7 @@ extern "C" int b2u_maxpool3x3s2(const void* in, void* out, int32_t B, int32_t H,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (C % 8) return set_error(-1, "b2u_maxpool3x3s2: C %% 8 != 0");
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-  B2U_DISPATCH_T(dtype, (maxpool_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(in), static_cast<T*>(out), B, H, W, C / 8)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(maxpool_kernel<T>, blocks_for(total, 256), 256, 0, stream, static_cast<const T*>(in), static_cast<T*>(out), B, H, W, C / 8)));
   return check_launch("maxpool3x3s2");
 }
 
@@ -406,6 +414,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                      const float* __restrict__ w9, const float* __restrict__ bias, int B,
                                                      int H, int W, int C8, int planes, int act) {
+  pdl_begin();
   // 4-pixel groups per image: planes==3 -> (2H x 2W) + (H x W) + (H/2 x W/2) planes, every plane width is a multiple of 4
   const long long rows_per_img = planes == 3 ? (static_cast<long long>(H) * W * 21) / 4 : static_cast<long long>(H) * W;
   const long long groups_per_img = rows_per_img / 4;
@@ -488,7 +497,7 @@ extern "C" int b2u_dwconv3x3(const void* in, void* out, const float* w, const fl
   if ((planes == 3 && (W % 8 || H % 2)) || (planes == 1 && W % 4)) return set_error(-1, "b2u_dwconv3x3: plane widths must be multiples of 4");
   const long long rows = planes == 3 ? (static_cast<long long>(H) * W * 21) / 4 : static_cast<long long>(H) * W;
   const long long total = static_cast<long long>(B) * (rows / 4) * (C / 8);
-  B2U_DISPATCH_T(dtype, (dwconv_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(in), static_cast<T*>(out), w, bias, B, H, W, C / 8, planes, act)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(dwconv_kernel<T>, blocks_for(total, 256), 256, 0, stream, static_cast<const T*>(in), static_cast<T*>(out), w, bias, B, H, W, C / 8, planes, act)));
   return check_launch("dwconv3x3");
 }
 
@@ -497,6 +506,7 @@ template <typename T>
 __global__ void tail_fuse_kernel(const void* __restrict__ base, int base_fp32, long long base_bstride,
                                  const float* __restrict__ tap, T* __restrict__ out, const float* __restrict__ scale,
                                  const float* __restrict__ shift, int B, int H, int W, int Ht, int Wt, int D8) {
+  pdl_begin();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * H * W * D8;
   if (i >= total) return;
@@ -550,6 +560,7 @@ template <typename T, int S>
 __global__ void tail_fuse_up_kernel(const void* __restrict__ base, int base_fp32, long long base_bstride,
                                     const float* __restrict__ tap, T* __restrict__ out, const float* __restrict__ scale,
                                     const float* __restrict__ shift, int B, int Ht, int Wt, int D8) {
+  pdl_begin();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int CW = Wt + 1, CH = Ht + 1;
   const long long total = static_cast<long long>(B) * CH * CW * D8;
@@ -617,14 +628,14 @@ extern "C" int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_b
   if ((H == 4 * Ht && W == 4 * Wt) || (H == 2 * Ht && W == 2 * Wt)) {
     const long long cells = static_cast<long long>(B) * (Ht + 1) * (Wt + 1) * (D / 8);
     if (H == 4 * Ht) {
-      B2U_DISPATCH_T(dtype, (tail_fuse_up_kernel<T, 4><<<blocks_for(cells, 256), 256, 0, stream>>>(base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, Ht, Wt, D / 8)));
+      B2U_DISPATCH_T(dtype, (launch_pdl(tail_fuse_up_kernel<T, 4>, blocks_for(cells, 256), 256, 0, stream, base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, Ht, Wt, D / 8)));
     } else {
-      B2U_DISPATCH_T(dtype, (tail_fuse_up_kernel<T, 2><<<blocks_for(cells, 256), 256, 0, stream>>>(base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, Ht, Wt, D / 8)));
+      B2U_DISPATCH_T(dtype, (launch_pdl(tail_fuse_up_kernel<T, 2>, blocks_for(cells, 256), 256, 0, stream, base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, Ht, Wt, D / 8)));
     }
     return check_launch("tail_fuse(up)");
   }
   const long long total = static_cast<long long>(B) * H * W * (D / 8);
-  B2U_DISPATCH_T(dtype, (tail_fuse_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, H, W, Ht, Wt, D / 8)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(tail_fuse_kernel<T>, blocks_for(total, 256), 256, 0, stream, base, base_fp32, base_batch_stride, tap, static_cast<T*>(out), scale, shift, B, H, W, Ht, Wt, D / 8)));
   return check_launch("tail_fuse");
 }
 
@@ -637,6 +648,7 @@ static inline int in_stats_chunk(int rows) { return rows >= 8192 ? 2048 : (rows 
 template <typename T>
 __global__ void __launch_bounds__(256) in_stats_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ sums,
                                                        float* __restrict__ work, int rows, int C8, int chunk) {
+  pdl_begin();
   extern __shared__ float red[];  // [rows_par][C8*16]
   __shared__ int s_last;
   const int b = blockIdx.y, nchunks = gridDim.x, B = gridDim.y;
@@ -695,7 +707,7 @@ extern "C" int b2u_in_stats(const void* x, int64_t ldx, float* sums, float* work
   const int chunk = in_stats_chunk(rows);
   dim3 grid((rows + chunk - 1) / chunk, B);
   const size_t smem = static_cast<size_t>(256 / C8) * C8 * 16 * sizeof(float);
-  B2U_DISPATCH_T(dtype, (in_stats_kernel<T><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), ldx, sums, work, rows, C8, chunk)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(in_stats_kernel<T>, grid, 256, smem, stream, static_cast<const T*>(x), ldx, sums, work, rows, C8, chunk)));
   return check_launch("in_stats");
 }
 
@@ -707,6 +719,7 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const T* __restrict__ x, 
                                                        long long ldy, const float* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int rows, int C8, float eps, int chunk) {
+  pdl_begin();
   const int b = blockIdx.y;
   const int cg = threadIdx.x % C8, rl = threadIdx.x / C8;
   const int rows_par = 256 / C8;
@@ -760,7 +773,7 @@ extern "C" int b2u_in_apply(const void* x, int64_t ldx, void* y, int64_t ldy, co
     per_thread >>= 1;
   const int chunk = rows_par * per_thread;
   dim3 grid((rows + chunk - 1) / chunk, B);
-  B2U_DISPATCH_T(dtype, (in_apply_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), ldx, static_cast<T*>(y), ldy, sums, gamma, beta, rows, C8, eps, chunk)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(in_apply_kernel<T>, grid, 256, 0, stream, static_cast<const T*>(x), ldx, static_cast<T*>(y), ldy, sums, gamma, beta, rows, C8, eps, chunk)));
   return check_launch("in_apply");
 }
 
@@ -768,6 +781,7 @@ extern "C" int b2u_in_apply(const void* x, int64_t ldx, void* y, int64_t ldy, co
 template <typename T>
 __global__ void film_kernel(const T* __restrict__ gb, const T* __restrict__ zz, long long ldzz, int zoff,
                             T* __restrict__ z, long long rows, int R8) {
+  pdl_begin();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * R8) return;
   const int c8 = static_cast<int>(i % R8);
@@ -791,7 +805,7 @@ extern "C" int b2u_film(const void* gb, const void* zz, int64_t ldzz, int32_t zo
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (R % 8) return set_error(-1, "b2u_film: R %% 8 != 0");
   const long long total = static_cast<long long>(rows) * (R / 8);
-  B2U_DISPATCH_T(dtype, (film_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(gb), static_cast<const T*>(zz), ldzz, zoff, static_cast<T*>(z), rows, R / 8)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(film_kernel<T>, blocks_for(total, 256), 256, 0, stream, static_cast<const T*>(gb), static_cast<const T*>(zz), ldzz, zoff, static_cast<T*>(z), rows, R / 8)));
   return check_launch("film");
 }
 
@@ -799,6 +813,7 @@ extern "C" int b2u_film(const void* gb, const void* zz, int64_t ldzz, int32_t zo
 __global__ void se_gate_kernel(const float* __restrict__ sums, const float* __restrict__ w1, const float* __restrict__ b1,
                                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gate,
                                int C, int Cr, int rows) {
+  pdl_begin();
   extern __shared__ float sm[];  // pooled[C] + hidden[Cr]
   float* pooled = sm;
   float* hidden = sm + C;
@@ -821,13 +836,14 @@ __global__ void se_gate_kernel(const float* __restrict__ sums, const float* __re
 extern "C" int b2u_se_gate(const float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
                            float* gate, int32_t B, int32_t C, int32_t Cr, int32_t rows, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  se_gate_kernel<<<B, 256, (C + Cr) * sizeof(float), stream>>>(sums, w1, b1, w2, b2, gate, C, Cr, rows);
+  launch_pdl(se_gate_kernel, B, 256, (C + Cr) * sizeof(float), stream, sums, w1, b1, w2, b2, gate, C, Cr, rows);
   return check_launch("se_gate");
 }
 
 template <typename T>
 __global__ void se_apply_kernel(const T* __restrict__ t, const T* __restrict__ sc, long long ldsc,
                                 const float* __restrict__ gate, T* __restrict__ out, int B, int rows, int C8) {
+  pdl_begin();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * rows * C8;
   if (i >= total) return;
@@ -852,7 +868,7 @@ extern "C" int b2u_se_apply(const void* t, const void* sc, int64_t ldsc, const f
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (C % 8) return set_error(-1, "b2u_se_apply: C %% 8 != 0");
   const long long total = static_cast<long long>(B) * rows * (C / 8);
-  B2U_DISPATCH_T(dtype, (se_apply_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(static_cast<const T*>(t), static_cast<const T*>(sc), ldsc, gate, static_cast<T*>(out), B, rows, C / 8)));
+  B2U_DISPATCH_T(dtype, (launch_pdl(se_apply_kernel<T>, blocks_for(total, 256), 256, 0, stream, static_cast<const T*>(t), static_cast<const T*>(sc), ldsc, gate, static_cast<T*>(out), B, rows, C / 8)));
   return check_launch("se_apply");
 }
 
@@ -866,6 +882,7 @@ __global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, 
                                                        float eps, const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ logits, uint8_t* __restrict__ labels,
                                                        int rows, int ncls) {
+  pdl_begin();
   __shared__ float s_a[C], s_b[C];       // per-image affine: y = x*a + b
   __shared__ float s_w[kSegMaxClasses * C], s_bias[kSegMaxClasses];
   const int b = blockIdx.y;
@@ -926,6 +943,7 @@ __global__ void __launch_bounds__(256) seg_head_kernel8(const T* __restrict__ x,
                                                        float eps, const float* __restrict__ w, const float* __restrict__ bias,
                                                        float* __restrict__ logits, uint8_t* __restrict__ labels,
                                                        int rows, int ncls) {
+  pdl_begin();
   __shared__ float s_a[C], s_b[C];       // per-image affine: y = x*a + b
   __shared__ float s_w[8 * C], s_bias[8];
   const int b = blockIdx.y;
@@ -981,9 +999,9 @@ extern "C" int b2u_seg_head(const void* x, const float* sums, const float* gamma
   if (ncls < 1 || ncls > kSegMaxClasses) return set_error(-1, "b2u_seg_head: 1 <= ncls <= %d", kSegMaxClasses);
   dim3 grid((rows + 255) / 256, B);
   if (ncls <= 8) {
-    B2U_DISPATCH_T(dtype, (seg_head_kernel8<T, 32><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
+    B2U_DISPATCH_T(dtype, (launch_pdl(seg_head_kernel8<T, 32>, grid, 256, 0, stream, static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
   } else {
-    B2U_DISPATCH_T(dtype, (seg_head_kernel<T, 32><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
+    B2U_DISPATCH_T(dtype, (launch_pdl(seg_head_kernel<T, 32>, grid, 256, 0, stream, static_cast<const T*>(x), sums, gamma, beta, eps, w, b, logits, labels, rows, ncls)));
   }
   return check_launch("seg_head");
 }

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                              // barriers, TMEM and tensor maps are set up: now wait for the producer kernel's data
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       }
     }
   }
+  pdl_launch_dependents();   // this CTA's tiles are done: once every CTA is here the next kernel may start its prologue
   tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();   // nobody leaves while the peer can still touch its smem / barriers / TMEM
@@ -741,13 +743,15 @@ static int launch_pair2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t
   cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = get_option(5) == 1 ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, args);
   if (e != cudaSuccess) return set_error(-2, "gemm_tc2 pair launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc2_pair");
@@ -772,7 +776,7 @@ static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStrea
   const long long tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
   const int sms = num_sms();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  kern<<<grid, 320, args.conv == 3 ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem, stream>>>(maps, args);
+  launch_pdl(kern, grid, 320, args.conv == 3 ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem, stream, maps, args);
   return check_launch("gemm_tc2");
 }
 

@@ -19,6 +19,7 @@ namespace b2u {
 template <typename T, int HALF>  // HALF = channels per lane (dh / 2), even
 __global__ void __launch_bounds__(256) msda_fwd_kernel(const T* __restrict__ value, const float* __restrict__ offaw,
                                                        T* __restrict__ out, int B, int Hv, int Wv, int heads) {
+  pdl_begin();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HW = Hv * Wv;
   const int Lq = (HW * 21) / 4;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const T* __restrict__ val
 template <typename T, int DH, int HPC, int PITCH = HPC * DH>
 __global__ void __launch_bounds__(256) msda_smem_kernel(const T* __restrict__ value, const float* __restrict__ offaw,
                                                         T* __restrict__ out, int Hv, int Wv, int heads, int qsplit) {
+  pdl_begin();
   extern __shared__ __align__(16) uint8_t sm_raw[];
   T* slab = reinterpret_cast<T*>(sm_raw);                 // [HW][PITCH]
   const int HW = Hv * Wv;
@@ -204,7 +206,7 @@ static int launch_msda_smem(const void* value, const float* offaw, void* out, in
   int qsplit = ((per_sm > 1 ? 6 : 2) * per_sm * num_sms() + B * groups - 1) / (B * groups);
   if (qsplit < 1) qsplit = 1;
   dim3 grid(qsplit, groups, B);
-  kern<<<grid, 256, smem, stream>>>(static_cast<const T*>(value), offaw, static_cast<T*>(out), Hv, Wv, heads, qsplit);
+  launch_pdl(kern, grid, 256, smem, stream, static_cast<const T*>(value), offaw, static_cast<T*>(out), Hv, Wv, heads, qsplit);
   return check_launch("msda_forward(smem)");
 }
 
@@ -230,10 +232,10 @@ extern "C" int b2u_msda_forward(const void* value, const float* offaw, void* out
 #define B2U_MSDA(HALF_)                                                                                               \
   case 2 * HALF_:                                                                                                     \
     if (dtype == B2U_BF16)                                                                                            \
-      msda_fwd_kernel<__nv_bfloat16, HALF_><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(value), offaw,  \
+      launch_pdl(msda_fwd_kernel<__nv_bfloat16, HALF_>, grid, 256, 0, stream, static_cast<const __nv_bfloat16*>(value), offaw,  \
                                                                       static_cast<__nv_bfloat16*>(out), B, Hv, Wv, heads); \
     else                                                                                                              \
-      msda_fwd_kernel<__half, HALF_><<<grid, 256, 0, stream>>>(static_cast<const __half*>(value), offaw,               \
+      launch_pdl(msda_fwd_kernel<__half, HALF_>, grid, 256, 0, stream, static_cast<const __half*>(value), offaw,               \
                                                                static_cast<__half*>(out), B, Hv, Wv, heads);          \
     break;
   switch (dh) {
@@ -249,6 +251,7 @@ __global__ void msda_f32_kernel(const float* __restrict__ value, const int64_t* 
                                 const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                                 const float* __restrict__ attw, float* __restrict__ out, int B, int S, int Lq, int M,
                                 int D, int L, int P) {
+  pdl_begin();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * Lq * M * D;
   if (i >= total) return;
@@ -288,7 +291,7 @@ extern "C" int b2u_msda_forward_f32(const float* value, const int64_t* spatial_s
   if (!value || !spatial_shapes || !level_start_index || !loc || !attw || !out)
     return set_error(-1, "b2u_msda_forward_f32: null pointer");
   const long long total = static_cast<long long>(B) * Lq * heads * dh;
-  msda_f32_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(value, spatial_shapes, level_start_index, loc,
+  launch_pdl(msda_f32_kernel, static_cast<int>((total + 255) / 256), 256, 0, stream, value, spatial_shapes, level_start_index, loc,
                                                                             attw, out, B, S, Lq, heads, dh, levels, points);
   return check_launch("msda_forward_f32");
 }
@@ -301,6 +304,7 @@ __global__ void msda_bwd_f32_kernel(const float* __restrict__ value, const int64
                                     const float* __restrict__ attw, const float* __restrict__ gout,
                                     float* __restrict__ gvalue, float* __restrict__ gloc, float* __restrict__ gattw,
                                     int B, int S, int Lq, int M, int D, int L, int P) {
+  pdl_begin();
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(B) * Lq * M;
@@ -371,7 +375,7 @@ extern "C" int b2u_msda_backward_f32(const float* value, const int64_t* spatial_
   cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * static_cast<size_t>(B) * S * heads * dh, stream);
   if (e != cudaSuccess) return set_error(-2, "b2u_msda_backward_f32: memset: %s", cudaGetErrorString(e));
   const long long warps = static_cast<long long>(B) * Lq * heads;
-  msda_bwd_f32_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+  launch_pdl(msda_bwd_f32_kernel, static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream, 
       value, spatial_shapes, level_start_index, loc, attw, grad_out, grad_value, grad_loc, grad_attw, B, S, Lq, heads,
       dh, levels, points);
   return check_launch("msda_backward_f32");
