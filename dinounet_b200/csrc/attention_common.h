@@ -41,6 +41,6 @@ __device__ __forceinline__ float ex2(float x) {
   return r;
 }
 
-int attention_tc3_dispatch(const AttnMaps& maps, const AttnArgs& a, int head_dim, int dtype, bool one_pass, cudaStream_t stream);
+int attention_tc3_dispatch(const AttnMaps& maps, const AttnArgs& a, int head_dim, int dtype, int variant, cudaStream_t stream);
 
 }  // namespace b2u

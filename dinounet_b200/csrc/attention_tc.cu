@@ -213,7 +213,7 @@ static int attention_tc_impl(const void* q, const void* k, const void* vt, void*
   if ((rc = make_map_3d(&maps.q, q, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, 128))) return rc;
   if ((rc = make_map_3d(&maps.k, k, dtype, hd, ntok, BH, hd, static_cast<uint64_t>(ntok) * hd, 64, kc))) return rc;
   if ((rc = make_map_3d(&maps.vt, vt, dtype, npad, hd, BH, npad, static_cast<uint64_t>(npad) * hd, 64, static_cast<uint32_t>(head_dim)))) return rc;
-  return attention_tc3_dispatch(maps, a, head_dim, dtype, get_option(4) == 4, stream);
+  return attention_tc3_dispatch(maps, a, head_dim, dtype, get_option(4), stream);
 }
 
 extern "C" int b2u_attention_tc(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t heads,

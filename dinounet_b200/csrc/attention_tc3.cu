@@ -108,7 +108,21 @@ __device__ __forceinline__ float row_max(const uint32_t (&v)[32], int lim, float
 // One 32-column group: P = exp2(s*scale - m) -> 16-bit -> swizzled smem (A operand of the PV MMA); returns the fp32 row
 // sum of the un-rounded probabilities (as flash-attention).  gc = index of the group inside the 128-key chunk:
 // K-block gc>>1, 16-byte chunks (gc&1)*4 .. +3 of this row.  Two compiled bodies: only the last key chunk zeroes columns.
-template <typename TT, bool kTail>
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel err 7.5e-5 - far below the 16-bit
+// rounding of P): x = n + f, f in [-0.5, 0.5]; 2^f ~ c0 + f (c1 + f (c2 + f c3)); 2^n by adding n to the exponent field.
+// Used for every POLY-th probability so that the MUFU pipe (16 exp2 / clk / SM: the roofline of head_dim-64 attention) is
+// relieved by a quarter / half of its work (flash-attention 4 does the same).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float xf = x + 12582912.0f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (xf - 12582912.0f);
+  float p = fmaf(0.05517165f, f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+
+template <typename TT, bool kTail, int POLY>
 __device__ __forceinline__ float exp_store(const uint32_t (&v)[32], int lim, float sl2, float m_new, int gc,
                                            uint32_t sP_row, int row) {
   float rs4[4] = {0.f, 0.f, 0.f, 0.f};    // independent partial sums (no 32-deep dependent FADD chain)
@@ -119,8 +133,10 @@ __device__ __forceinline__ float exp_store(const uint32_t (&v)[32], int lim, flo
 #pragma unroll
     for (int c = 0; c < 8; c += 2) {
       const int cc = c4 * 8 + c;
-      float a = ex2(fmaf(__uint_as_float(v[cc]), sl2, -m_new));
-      float b = ex2(fmaf(__uint_as_float(v[cc + 1]), sl2, -m_new));
+      const float xa = fmaf(__uint_as_float(v[cc]), sl2, -m_new);
+      const float xb = fmaf(__uint_as_float(v[cc + 1]), sl2, -m_new);
+      float a = (POLY > 0 && (cc % POLY) == POLY - 1) ? ex2_poly(xa) : ex2(xa);
+      float b = (POLY > 0 && ((cc + 1) % POLY) == POLY - 1) ? ex2_poly(xb) : ex2(xb);
       if constexpr (kTail) {
         if (cc >= lim) a = 0.f;
         if (cc + 1 >= lim) b = 0.f;
@@ -148,7 +164,7 @@ struct SmCtx {
 //           exp(group 1), re-read group 0, release S, exp(group 0).  Every tcgen05.ld is unconditional: an asm output
 //           array defined under a branch is materialised in local memory by the compiler.
 //    kTail: the last chunk owns ngrp in {0,1,2} groups and lim valid columns: per-group blocks with their own arrays.
-template <typename TT, int HD, bool kTail, bool kOne>
+template <typename TT, int HD, bool kTail, bool kOne, int POLY>
 __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, int lim, float& m, float& l,
                                               uint32_t& sfull_cnt, uint32_t& ofull_cnt) {
   constexpr int OW = HD / 2;
@@ -199,9 +215,9 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
     tc_fence_after();
   }
   if constexpr (!kTail) {
-    rs = exp_store<TT, false>(v, 32, cx.sl2, m_new, cx.part * 2 + 1, cx.sP_row, cx.row);
+    rs = exp_store<TT, false, POLY>(v, 32, cx.sl2, m_new, cx.part * 2 + 1, cx.sP_row, cx.row);
     if constexpr (kOne) {
-      rs += exp_store<TT, false>(w, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row);
+      rs += exp_store<TT, false, POLY>(w, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row);
     } else {
       tmem_ld32(cx.tS, v);
       tmem_ld_wait();
@@ -213,7 +229,7 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
         uint32_t t[32];
         tmem_ld32(cx.tS + pc * 32, t);
         tmem_ld_wait();
-        rs += exp_store<TT, true>(t, lim - pc * 32, cx.sl2, m_new, cx.part * 2 + pc, cx.sP_row, cx.row);
+        rs += exp_store<TT, true, POLY>(t, lim - pc * 32, cx.sl2, m_new, cx.part * 2 + pc, cx.sP_row, cx.row);
       }
     }
   }
@@ -221,7 +237,7 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
     tc_fence_before();
     __syncwarp();
     if (cx.lane == 0) mbar_arrive(cx.s_free);                // all reads of S(j) done: S(j+1) may be produced
-    if constexpr (!kTail) rs += exp_store<TT, false>(v, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row);
+    if constexpr (!kTail) rs += exp_store<TT, false, POLY>(v, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row);
   }
   // ---- rare: the reference maximum moved -> rescale this warp's slice of O in TMEM (no PV MMA is in flight: PV(j-1) has
   // retired and PV(j) waits for this warp's p_full arrival)
@@ -245,7 +261,7 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
   if (cx.lane == 0) mbar_arrive(cx.p_full);
 }
 
-template <typename T, int HD, bool kOne>
+template <typename T, int HD, bool kOne, int POLY>
 __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
   using TT = T16<T>;
   using CF = At3Cfg<HD>;
@@ -430,11 +446,11 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
       cx.tS = tS; cx.tO = tO; cx.sP_row = sP_row; cx.row = row; cx.part = part; cx.lane = lane; cx.xm = xm; cx.sl2 = sl2;
       cx.s_full = &s_full[g]; cx.s_free = &s_free[g]; cx.p_full = &p_full[g]; cx.o_full = &o_full[g];
       cx.bar_id = 1 + g * 4 + q4;
-      for (int j = 0; j + 1 < J; ++j) softmax_chunk<TT, HD, false, kOne>(cx, j, 2, 64, m, l, sfull_cnt, ofull_cnt);
+      for (int j = 0; j + 1 < J; ++j) softmax_chunk<TT, HD, false, kOne, POLY>(cx, j, 2, 64, m, l, sfull_cnt, ofull_cnt);
       {
         int ngrp = (tail_n - part * CW + 31) >> 5;             // 32-column groups this warp owns in the last chunk
         ngrp = ngrp < 0 ? 0 : (ngrp > CW / 32 ? CW / 32 : ngrp);
-        softmax_chunk<TT, HD, true, kOne>(cx, J - 1, ngrp, tail_valid - part * CW, m, l, sfull_cnt, ofull_cnt);
+        softmax_chunk<TT, HD, true, kOne, POLY>(cx, J - 1, ngrp, tail_valid - part * CW, m, l, sfull_cnt, ofull_cnt);
       }
       // ---- last PV retired: read this warp's O slice, release the accumulator for the next item
       mbar_wait(&o_full[g], ofull_cnt & 1);
@@ -492,9 +508,9 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
   }
 }
 
-template <typename T, int HD, bool kOne>
+template <typename T, int HD, bool kOne, int POLY>
 static int launch_attn_tc3(const AttnMaps& maps, const AttnArgs& a, cudaStream_t stream) {
-  auto kern = attn_tc3_kernel<T, HD, kOne>;
+  auto kern = attn_tc3_kernel<T, HD, kOne, POLY>;
   using CF = At3Cfg<HD>;
   static_assert(CF::kSmem <= 227 * 1024, "attention smem budget");
   static bool configured_dev[64] = {};
@@ -510,14 +526,19 @@ static int launch_attn_tc3(const AttnMaps& maps, const AttnArgs& a, cudaStream_t
   return check_launch("attention_tc3");
 }
 
-int attention_tc3_dispatch(const AttnMaps& maps, const AttnArgs& a, int head_dim, int dtype, bool one_pass, cudaStream_t stream) {
+int attention_tc3_dispatch(const AttnMaps& maps, const AttnArgs& a, int head_dim, int dtype, int variant, cudaStream_t stream) {
+  // variant (b2u_set_option(4, .)): 0 = default, 4 = single-pass softmax, 6 = every exp2 on the MUFU pipe, 7 / 8 = every 3rd / 6th on the FMA pipe (default: every 4th)
+  const bool bf = dtype == B2U_BF16;
   if (head_dim == 64) {
-    if (one_pass)
-      return dtype == B2U_BF16 ? launch_attn_tc3<__nv_bfloat16, 64, true>(maps, a, stream) : launch_attn_tc3<__half, 64, true>(maps, a, stream);
-    return dtype == B2U_BF16 ? launch_attn_tc3<__nv_bfloat16, 64, false>(maps, a, stream) : launch_attn_tc3<__half, 64, false>(maps, a, stream);
+    if (variant == 4) return bf ? launch_attn_tc3<__nv_bfloat16, 64, true, 0>(maps, a, stream) : launch_attn_tc3<__half, 64, true, 0>(maps, a, stream);
+    if (variant == 6) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 0>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 0>(maps, a, stream);
+    if (variant == 7) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 3>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 3>(maps, a, stream);
+    if (variant == 8) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 6>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 6>(maps, a, stream);
+    return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 4>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 4>(maps, a, stream);
   }
-  // head_dim 128: 320 threads compile to 168 registers -> the single-pass softmax fits without spills
-  return dtype == B2U_BF16 ? launch_attn_tc3<__nv_bfloat16, 128, true>(maps, a, stream) : launch_attn_tc3<__half, 128, true>(maps, a, stream);
+  // head_dim 128: 320 threads compile to 168 registers -> the single-pass softmax fits without spills; exp2 is half as
+  // dense per flop there, MUFU is not the limiter
+  return bf ? launch_attn_tc3<__nv_bfloat16, 128, true, 0>(maps, a, stream) : launch_attn_tc3<__half, 128, true, 0>(maps, a, stream);
 }
 
 }  // namespace b2u
