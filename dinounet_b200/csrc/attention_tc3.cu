@@ -110,8 +110,8 @@ __device__ __forceinline__ float row_max(const uint32_t (&v)[32], int lim, float
 // K-block gc>>1, 16-byte chunks (gc&1)*4 .. +3 of this row.  Two compiled bodies: only the last key chunk zeroes columns.
 // exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel err 7.5e-5 - far below the 16-bit
 // rounding of P): x = n + f, f in [-0.5, 0.5]; 2^f ~ c0 + f (c1 + f (c2 + f c3)); 2^n by adding n to the exponent field.
-// Used for every POLY-th probability so that the MUFU pipe (16 exp2 / clk / SM: the roofline of head_dim-64 attention) is
-// relieved by a quarter / half of its work (flash-attention 4 does the same).
+// Used for every POLY-th probability (default: every 3rd) so that the MUFU pipe (16 exp2 / clk / SM: the roofline of
+// head_dim-64 attention) is relieved of a third of its work (flash-attention 4 does the same).
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -125.0f);
   const float xf = x + 12582912.0f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
@@ -122,10 +122,40 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
 
+// packed fp32 pair arithmetic (sm_100 FFMA2 / FADD2): one issue slot for two lanes of the scale-and-shift and the row sums
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 template <typename TT, bool kTail, int POLY>
 __device__ __forceinline__ float exp_store(const uint32_t (&v)[32], int lim, float sl2, float m_new, int gc,
                                            uint32_t sP_row, int row) {
-  float rs4[4] = {0.f, 0.f, 0.f, 0.f};    // independent partial sums (no 32-deep dependent FADD chain)
+  float2 rs2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};    // independent packed partial sums
+  const float2 sl2v = make_float2(sl2, sl2), mnv = make_float2(-m_new, -m_new);
   const uint32_t base = sP_row + (gc >> 1) * (128 * 128);
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {       // 8 probabilities -> one 16-byte store
@@ -133,21 +163,21 @@ __device__ __forceinline__ float exp_store(const uint32_t (&v)[32], int lim, flo
 #pragma unroll
     for (int c = 0; c < 8; c += 2) {
       const int cc = c4 * 8 + c;
-      const float xa = fmaf(__uint_as_float(v[cc]), sl2, -m_new);
-      const float xb = fmaf(__uint_as_float(v[cc + 1]), sl2, -m_new);
-      float a = (POLY > 0 && (cc % POLY) == POLY - 1) ? ex2_poly(xa) : ex2(xa);
-      float b = (POLY > 0 && ((cc + 1) % POLY) == POLY - 1) ? ex2_poly(xb) : ex2(xb);
+      const float2 xx = fma2(make_float2(__uint_as_float(v[cc]), __uint_as_float(v[cc + 1])), sl2v, mnv);
+      float a = (POLY > 0 && (cc % POLY) == POLY - 1) ? ex2_poly(xx.x) : ex2(xx.x);
+      float b = (POLY > 0 && ((cc + 1) % POLY) == POLY - 1) ? ex2_poly(xx.y) : ex2(xx.y);
       if constexpr (kTail) {
         if (cc >= lim) a = 0.f;
         if (cc + 1 >= lim) b = 0.f;
       }
-      rs4[c >> 1] += a + b;
+      rs2[c >> 1] = add2(rs2[c >> 1], make_float2(a, b));
       pk[c >> 1] = TT::pack2(a, b);
     }
     const int chunk = (gc & 1) * 4 + c4;
     sts128a(base + ((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
   }
-  return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+  const float2 t = add2(add2(rs2[0], rs2[1]), add2(rs2[2], rs2[3]));
+  return t.x + t.y;
 }
 
 struct SmCtx {
@@ -527,14 +557,13 @@ static int launch_attn_tc3(const AttnMaps& maps, const AttnArgs& a, cudaStream_t
 }
 
 int attention_tc3_dispatch(const AttnMaps& maps, const AttnArgs& a, int head_dim, int dtype, int variant, cudaStream_t stream) {
-  // variant (b2u_set_option(4, .)): 0 = default, 4 = single-pass softmax, 6 = every exp2 on the MUFU pipe, 7 / 8 = every 3rd / 6th on the FMA pipe (default: every 4th)
+  // variant (b2u_set_option(4, .)): 0 = default, 4 = single-pass softmax, 6 = every exp2 on the MUFU pipe, 7 = every 4th exp2 on the FMA pipe (default: every 3rd; measured: 1/2 and packed-pair polynomials lose)
   const bool bf = dtype == B2U_BF16;
   if (head_dim == 64) {
     if (variant == 4) return bf ? launch_attn_tc3<__nv_bfloat16, 64, true, 0>(maps, a, stream) : launch_attn_tc3<__half, 64, true, 0>(maps, a, stream);
     if (variant == 6) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 0>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 0>(maps, a, stream);
-    if (variant == 7) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 3>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 3>(maps, a, stream);
-    if (variant == 8) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 6>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 6>(maps, a, stream);
-    return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 4>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 4>(maps, a, stream);
+    if (variant == 7) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 4>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 4>(maps, a, stream);
+    return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 3>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 3>(maps, a, stream);
   }
   // head_dim 128: 320 threads compile to 168 registers -> the single-pass softmax fits without spills; exp2 is half as
   // dense per flop there, MUFU is not the limiter
