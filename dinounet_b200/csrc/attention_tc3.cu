@@ -122,35 +122,6 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
 
-// packed fp32 pair arithmetic (sm_100 FFMA2 / FADD2): one issue slot for two lanes of the scale-and-shift and the row sums
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n"
-      ".reg .b64 ra, rb, rc, rd;\n"
-      "mov.b64 ra, {%2, %3};\n"
-      "mov.b64 rb, {%4, %5};\n"
-      "mov.b64 rc, {%6, %7};\n"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n"
-      "mov.b64 {%0, %1}, rd;\n"
-      "}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("{\n"
-      ".reg .b64 ra, rb, rd;\n"
-      "mov.b64 ra, {%2, %3};\n"
-      "mov.b64 rb, {%4, %5};\n"
-      "add.rn.f32x2 rd, ra, rb;\n"
-      "mov.b64 {%0, %1}, rd;\n"
-      "}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-
 template <typename TT, bool kTail, int POLY>
 __device__ __forceinline__ float exp_store(const uint32_t (&v)[32], int lim, float sl2, float m_new, int gc,
                                            uint32_t sP_row, int row) {

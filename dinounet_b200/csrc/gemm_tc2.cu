@@ -96,12 +96,33 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(h, copysignf(er, x), h);
 }
 
+// the same for two values in packed f32x2 instructions (7 FFMA2/FMUL2 + 4 MUFU + 4 sign ops per PAIR instead of 13 + 2 per value)
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 u = fma2(make_float2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f), ax, make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_approx(u.x), rcp_approx(u.y));
+  float2 p = fma2(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = fma2(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = fma2(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = fma2(p, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 q = mul2(mul2(x, x), make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+  const float2 pt = mul2(p, t);
+  const float2 er = fma2(make_float2(-pt.x, -pt.y), e, make_float2(1.0f, 1.0f));       // erf(|x|/sqrt2)
+  const float2 h = mul2(x, make_float2(0.5f, 0.5f));
+  return fma2(h, make_float2(copysignf(er.x, x.x), copysignf(er.y, x.y)), h);
+}
+
 template <int ACT, int NV>
 __device__ __forceinline__ void act_vec(float (&f)[NV]) {
   constexpr int act = ACT;
   if (act == B2U_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) f[j] = gelu_fast(f[j]);
+    for (int j = 0; j < NV; j += 2) {
+      const float2 r = gelu_fast2(make_float2(f[j], f[j + 1]));
+      f[j] = r.x;
+      f[j + 1] = r.y;
+    }
   } else if (act == B2U_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -413,11 +434,13 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
           const int head = (n - which * args.D) / HDm;
           float x[64];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {   // Linear output rounded to 16 bits (packed converts: F2FP, not the slow F2F)
-            const float2 lo = TT::unpack2(TT::pack2(__uint_as_float(v0[j]) + s_bias[hcol + lo_off + j],
-                                                    __uint_as_float(v0[j + 1]) + s_bias[hcol + lo_off + j + 1]));
-            const float2 hi = TT::unpack2(TT::pack2(__uint_as_float(v1r[j]) + s_bias[hcol + hi_off + j],
-                                                    __uint_as_float(v1r[j + 1]) + s_bias[hcol + hi_off + j + 1]));
+          for (int j = 0; j < 32; j += 2) {   // Linear output rounded to 16 bits (packed add: FADD2; packed converts: F2FP)
+            const float2 blo = *reinterpret_cast<const float2*>(&s_bias[hcol + lo_off + j]);
+            const float2 bhi = *reinterpret_cast<const float2*>(&s_bias[hcol + hi_off + j]);
+            const float2 alo = add2(make_float2(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])), blo);
+            const float2 ahi = add2(make_float2(__uint_as_float(v1r[j]), __uint_as_float(v1r[j + 1])), bhi);
+            const float2 lo = TT::unpack2(TT::pack2(alo.x, alo.y));
+            const float2 hi = TT::unpack2(TT::pack2(ahi.x, ahi.y));
             x[j] = lo.x; x[j + 1] = lo.y;
             x[32 + j] = hi.x; x[33 + j] = hi.y;
           }
@@ -446,10 +469,19 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
               const int A = lo_off + j;                // angle index in [0, head_dim/2)
               const uint32_t rbase_ = (A < hq ? ry : rx) + (A & (hq - 1)) * 4;
               const float4 sn = lds128f(rbase_), cs = lds128f(rbase_ + hq * 4);
-              packed[j / 2] = TT::pack2(x[j] * cs.x - x[j + 32] * sn.x, x[j + 1] * cs.y - x[j + 33] * sn.y);
-              packed[j / 2 + 1] = TT::pack2(x[j + 2] * cs.z - x[j + 34] * sn.z, x[j + 3] * cs.w - x[j + 35] * sn.w);
-              packed[16 + j / 2] = TT::pack2(x[j + 32] * cs.x + x[j] * sn.x, x[j + 33] * cs.y + x[j + 1] * sn.y);
-              packed[16 + j / 2 + 1] = TT::pack2(x[j + 34] * cs.z + x[j + 2] * sn.z, x[j + 35] * cs.w + x[j + 3] * sn.w);
+              // rotation in packed f32x2: lo' = lo*cos - hi*sin, hi' = hi*cos + lo*sin (two angles per instruction)
+              const float2 c01 = make_float2(cs.x, cs.y), c23 = make_float2(cs.z, cs.w);
+              const float2 s01 = make_float2(sn.x, sn.y), s23 = make_float2(sn.z, sn.w);
+              const float2 l01 = make_float2(x[j], x[j + 1]), l23 = make_float2(x[j + 2], x[j + 3]);
+              const float2 h01 = make_float2(x[j + 32], x[j + 33]), h23 = make_float2(x[j + 34], x[j + 35]);
+              const float2 a01 = fma2(l01, c01, mul2(h01, make_float2(-s01.x, -s01.y)));
+              const float2 a23 = fma2(l23, c23, mul2(h23, make_float2(-s23.x, -s23.y)));
+              const float2 b01 = fma2(h01, c01, mul2(l01, s01));
+              const float2 b23 = fma2(h23, c23, mul2(l23, s23));
+              packed[j / 2] = TT::pack2(a01.x, a01.y);
+              packed[j / 2 + 1] = TT::pack2(a23.x, a23.y);
+              packed[16 + j / 2] = TT::pack2(b01.x, b01.y);
+              packed[16 + j / 2 + 1] = TT::pack2(b23.x, b23.y);
             }
           } else if (which < 2 && rot) {
 #pragma unroll
@@ -642,7 +674,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3);
               const float4 a4 = lds128f(patch_u32 + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-              float f[4] = {a4.x + bi[0], a4.y + bi[1], a4.z + bi[2], a4.w + bi[3]};
+              const float2 p01 = add2(make_float2(a4.x, a4.y), make_float2(bi[0], bi[1]));
+              const float2 p23 = add2(make_float2(a4.z, a4.w), make_float2(bi[2], bi[3]));
+              float f[4] = {p01.x, p01.y, p23.x, p23.y};
               if (e.round16) {
 #pragma unroll
                 for (int j = 0; j < 4; j += 2) {
@@ -654,10 +688,17 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
               act_vec<ACT1, 4>(f);
               if (affine) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+                for (int j = 0; j < 4; j += 2) {
+                  const float2 t = fma2(make_float2(f[j], f[j + 1]), make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1]));
+                  f[j] = t.x; f[j + 1] = t.y;
+                }
               }
               act_vec<ACT2, 4>(f);
-              if (e.residual) { f[0] += res[i].x; f[1] += res[i].y; f[2] += res[i].z; f[3] += res[i].w; }
+              if (e.residual) {
+                const float2 r01 = add2(make_float2(f[0], f[1]), make_float2(res[i].x, res[i].y));
+                const float2 r23 = add2(make_float2(f[2], f[3]), make_float2(res[i].z, res[i].w));
+                f[0] = r01.x; f[1] = r01.y; f[2] = r23.x; f[3] = r23.y;
+              }
               if (e.add16) {
                 const uint4 pr = add[i >> 1];
                 const float2 t0 = TT::unpack2((i & 1) ? pr.z : pr.x), t1 = TT::unpack2((i & 1) ? pr.w : pr.y);
