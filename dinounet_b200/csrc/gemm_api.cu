@@ -54,6 +54,7 @@ extern "C" int b2u_gemm(const b2u_gemm_params* p, b2u_stream_t stream_) {
     m_tiles = (static_cast<long long>(p->M) + BM - 1) / BM;
     // CTA pairs (cta_group::2) for the 256-wide tiles of plain GEMMs (option 3 = 1 disables, for A/B runs)
     a.pair = (v2 && bn == 256 && m_tiles >= 2 && get_option(3) != 1) ? 1 : 0;
+    a.res_prefetch = (get_option(7) != 1 && a.num_kb <= 8) ? 1 : 0;   // short K only: measured +3 % there, nothing (or worse) at K >= 1024
     if ((rc = make_map_2d(&maps.a[0], p->A, p->M, p->K, p->lda, BM, p->dtype))) return rc;
     if ((rc = make_map_2d(&maps.b, p->Wp, p->N, p->K, p->ldw, a.pair ? bn / 2 : bn, p->dtype))) return rc;
   } else {
@@ -136,7 +137,7 @@ extern "C" int b2u_qkv_rope(const b2u_qkv_params* p, b2u_stream_t stream_) {
   if (p->rope_w > 0 && v2) {
     a.rope_w = p->rope_w;
     a.rope_h = (p->ntok - p->prefix) / p->rope_w;
-    if (a.rope_h * a.rope_w != p->ntok - p->prefix || a.rope_h + a.rope_w > 128)
+    if (a.rope_h * a.rope_w != p->ntok - p->prefix || (a.rope_h + a.rope_w) * (head_dim * 2 + 16) > 128 * 32 * 2 * 4)
       return set_error(-1, "b2u_qkv_rope: rope grid %d x %d does not match ntok/prefix or is too large", a.rope_h, a.rope_w);
   }
   if (a.npad && (a.npad % 8 || a.npad < p->ntok)) return set_error(-1, "b2u_qkv_rope: bad npad");

@@ -36,6 +36,7 @@ struct GemmArgs {
   int rope_h, rope_w;  // > 0: separable rope tables staged in smem
   int halo_stages;  // conv == 3 (halo-reuse 3x3 mode)
   int pair;         // 1: CTA-pair (tcgen05 cta_group::2) kernel, W map box holds BLOCK_N / 2 rows
+  int res_prefetch; // 1: the epilogue pulls the NEXT tile's residual rows into L2 while it drains the current tile
 };
 
 int num_sms();

@@ -33,7 +33,7 @@ constexpr int kHaloBytes = kHaloH * kHaloW * 128;      // one TMA box: 18 rows x
 constexpr int kHaloStageBytes = 23 * 1024;             // box rounded up to the 1024 B swizzle period
 constexpr int kHaloPrefetch = 8;                       // L2 prefetch distance of the halo boxes, in tiles of one CTA
 
-constexpr int kRopeBytes = 128 * 32 * 2 * 4;   // (rope_h + rope_w <= 128) rows x <=32 angles x {sin, cos} fp32
+constexpr int kRopeBytes = 128 * 32 * 2 * 4;   // (rope_h + rope_w) rows x (<=32 angles x {sin, cos} fp32 + 16 B pad): host-checked
 
 // PAIR: two CTAs of a cluster form one tcgen05 cta_group::2 unit: a 256 x BN output tile, each CTA stages its own 128
 // rows of A and HALF of the W tile (BN/2 rows), so a stage is A 16 KB + W 16 KB (BN 256) instead of 16 + 32 KB: 1.5x less
@@ -45,7 +45,9 @@ template <int BN, int EPI = 0, bool PAIR = false> struct Cfg2 {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 8 * 4096;        // 8 epilogue warps x (32 rows x 128 B)
+  static constexpr int kEpiWarps = (EPI == 4 || (EPI == 2 && BN == 256)) ? 16 : 8;   // latency-bound GELU / RoPE epilogues: four warps per TMEM lane quarter
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;  // producer warp + MMA warp + epilogue warps
+  static constexpr int kStagingBytes = 8 * 4096;        // 8 epilogue warps x (32 rows x 128 B) / 16 x (32 rows x 64 B)
   static constexpr int kBiasBytes = BN * 4;
   static constexpr int kRope = EPI == 2 ? kRopeBytes : 0;   // (EPI 3 reuses s_bias only)
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBiasBytes + kRope + 1024 /*align*/ + 256 /*barriers*/;
@@ -54,7 +56,8 @@ template <int BN, int EPI = 0, bool PAIR = false> struct Cfg2 {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int kEpiThreads = 256>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -113,6 +116,10 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x) {
   return fma2(h, make_float2(copysignf(er.x, x.x), copysignf(er.y, x.y)), h);
 }
 
+// a pair of fp32 values rounded to the 16-bit type and back (what the reference's autocast Linear hands the next op)
+template <typename TT>
+__device__ __forceinline__ float2 round16v(float2 a) { return TT::unpack2(TT::pack2(a.x, a.y)); }
+
 template <int ACT, int NV>
 __device__ __forceinline__ void act_vec(float (&f)[NV]) {
   constexpr int act = ACT;
@@ -132,10 +139,11 @@ __device__ __forceinline__ void act_vec(float (&f)[NV]) {
   }
 }
 
-// EPI: 0 = generic 16-bit out, 1 = generic fp32 out, 2 = QKV(+RoPE, head split), 3 = SwiGLU (silu(x1)*x2).  ACT1 / ACT2: compile-time activations
+// EPI: 0 = generic 16-bit out, 1 = generic fp32 out, 2 = QKV(+RoPE, head split), 3 = SwiGLU (silu(x1)*x2), 4 = lean 16-bit out
+// (bias -> 16-bit rounding -> ACT1 only, 16 epilogue warps; CTA pairs).  ACT1 / ACT2: compile-time activations
 // after the bias / after the affine (B2U_ACT_*), so the fully unrolled epilogue stays small enough for the I-cache.
 template <int BN, int EPI, int ACT1, int ACT2, typename T, bool PAIR = false>
-__global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
+__global__ void __launch_bounds__((Cfg2<BN, EPI, PAIR>::kThreads), 1) gemm_tc2_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
   using C = Cfg2<BN, EPI, PAIR>;
   using TT = T16<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
   uint8_t* s_wtaps = smem + nstages * stage_bytes;                       // halo mode only: 9 x [BN x 128 B]
   uint8_t* staging = s_wtaps + (halo ? 9 * C::kBBytes : 0);
   float* s_bias = reinterpret_cast<float*>(staging + C::kStagingBytes);
-  float* s_rope = reinterpret_cast<float*>(staging + C::kStagingBytes + C::kBiasBytes);   // [h+w][32] = (sin16 | cos16)
+  float* s_rope = reinterpret_cast<float*>(staging + C::kStagingBytes + C::kBiasBytes);   // [h+w][2*hq + 4] = (sin | cos | pad)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes + C::kBiasBytes + C::kRope);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* tfull_bar = empty_bar + 8;
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
     mbar_init(w_bar, 1);
     // BN <= 32: a tile is one 32-column chunk, drained by ONE warp per TMEM lane quarter; the two warp sets alternate
     // tiles (set = accumulator buffer), so two epilogues are in flight instead of one set idling
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 16 : (BN <= 32 ? 4 : 8)); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 2 * C::kEpiWarps : (BN <= 32 ? 4 : C::kEpiWarps)); }
     fence_mbar_init();
   }
   if constexpr (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / multicast commit
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         const int a = c - (is_cos ? hq : 0);
         const long long src = r < args.rope_h ? static_cast<long long>(r) * args.rope_w * HDm + a
                                               : static_cast<long long>(r - args.rope_h) * HDm + hq + a;
-        s_rope[i] = is_cos ? __ldg(args.rope_cos + src) : __ldg(args.rope_sin + src);
+        s_rope[r * (2 * hq + 4) + c] = is_cos ? __ldg(args.rope_cos + src) : __ldg(args.rope_sin + src);   // rows padded by 16 B (below)
       }
     }
   }
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
+    // ===================== epilogue warps (2..9; EPI 4: 2..17) =====================
     const int q4 = warp & 3;
     const int ew = warp - 2;                         // staging patch index
     const int half = ew >> 2;                        // which half of the tile's columns this warp drains
@@ -386,7 +394,139 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
         return (y < args.Ho) && (x < args.Wo);
       };
 
-      if constexpr (EPI == 2) {
+      if constexpr (EPI == 2 && C::kEpiWarps == 16) {
+        // ---- QKV epilogue on sixteen warps (four per TMEM lane quarter): warp = one 64-column unit (32 low + 32 matching
+        // high rope columns of a head), drained as two passes of 16 + 16 columns so that it fits 96 registers and a 64 B
+        // staging row.  No barrier among the warps (bias through L1 as warp-uniform loads).
+        const int HDm = args.head_dim;                 // 64 or 128
+        const int hq = HDm >> 2;                       // angles per axis (rope_position_encoding.py: D_head / 4)
+        long long m1;
+        const bool v1 = row_of(q4 * 32 + lane, m1);   // phase-1 owner row
+        const unsigned ntok_u = static_cast<unsigned>(args.ntok);   // token rows fit 32 bits (host-checked): 32-bit divides
+        const int b1 = static_cast<int>(static_cast<unsigned>(m1) / ntok_u);
+        const int t1 = static_cast<int>(static_cast<unsigned>(m1) - static_cast<unsigned>(b1) * ntok_u);
+        const bool rot = v1 && t1 >= args.prefix;
+        long long dst_off[4];                          // phase-2 rows of this lane: rr = i*8 + lane/4 (4 lanes x 16 B per row)
+        bool dst_ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          long long m2;
+          dst_ok[i] = row_of(q4 * 32 + i * 8 + (lane >> 2), m2);
+          const int b2 = static_cast<int>(static_cast<unsigned>(m2) / ntok_u);
+          const int t2 = static_cast<int>(static_cast<unsigned>(m2) - static_cast<unsigned>(b2) * ntok_u);
+          dst_off[i] = (static_cast<long long>(b2) * args.heads * args.ntok + t2) * HDm;
+        }
+        const uint32_t patch4_u32 = smem_u32(staging + ew * 2048);
+        const int u = half;                            // = ew >> 2 in 0..3: the unit of this warp
+        const int hcol = HDm == 64 ? u * 64 : (u >> 1) * 128;          // first accumulator column of the head
+        const int pss = HDm == 64 ? 0 : (u & 1);
+        const int n = n0 + hcol;
+        const bool live = n < args.N;                  // warp-uniform
+        const int which = n / args.D;
+        const int head = (n - which * args.D) / HDm;
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll 1
+        for (int ps = 0; ps < 2; ++ps) {
+          const int lo_off = pss * 32 + ps * 16, hi_off = (HDm >> 1) + pss * 32 + ps * 16;    // element offsets inside the head
+          uint32_t v0[16], v1r[16];
+          tmem_ld16(taddr + hcol + lo_off, v0);
+          tmem_ld16(taddr + hcol + hi_off, v1r);
+          tmem_ld_wait();
+          if (ps == 1) {                               // the accumulator is in registers: hand the buffer back before the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(tempty0 + buf * 8);
+              else mbar_arrive(&tempty_bar[buf]);
+            }
+          }
+          if (!live) continue;
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {   // Linear output rounded to 16 bits (packed add: FADD2; packed converts: F2FP)
+            const float4 blo = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n + lo_off + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 bhi = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n + hi_off + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float2 l01 = round16v<TT>((add2(make_float2(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])), make_float2(blo.x, blo.y))));
+            const float2 l23 = round16v<TT>((add2(make_float2(__uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3])), make_float2(blo.z, blo.w))));
+            const float2 h01 = round16v<TT>((add2(make_float2(__uint_as_float(v1r[j]), __uint_as_float(v1r[j + 1])), make_float2(bhi.x, bhi.y))));
+            const float2 h23 = round16v<TT>((add2(make_float2(__uint_as_float(v1r[j + 2]), __uint_as_float(v1r[j + 3])), make_float2(bhi.z, bhi.w))));
+            x[j] = l01.x; x[j + 1] = l01.y; x[j + 2] = l23.x; x[j + 3] = l23.y;
+            x[16 + j] = h01.x; x[17 + j] = h01.y; x[18 + j] = h23.x; x[19 + j] = h23.y;
+          }
+          if (which == 2 && args.npad > 0) {
+            // V^T [B, heads, head_dim, npad]: lane = token, loop over d -> each store instruction writes 32 consecutive keys
+            if (v1) {
+              T* dst = reinterpret_cast<T*>(args.v) + (static_cast<long long>(b1) * args.heads + head) * HDm * args.npad + t1;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                dst[static_cast<long long>(lo_off + j) * args.npad] = TT::from_f(x[j]);
+                dst[static_cast<long long>(hi_off + j) * args.npad] = TT::from_f(x[16 + j]);
+              }
+            }
+            continue;   // warp-uniform
+          }
+          uint32_t packed[16];
+          if (which < 2 && rot && args.rope_w > 0) {
+            // separable tables from smem ([h + w] rows of (sin[hq] | cos[hq] | pad)): angle A < hq comes from the patch row's
+            // table, A >= hq from the patch column's; cos/sin[A + head_dim/2] == cos/sin[A]
+            const int pidx = t1 - args.prefix;
+            const int py = pidx / args.rope_w, px = pidx - py * args.rope_w;
+            const uint32_t rstride = hq * 8 + 16;      // padded rows: the 32 lanes' column-table rows hit distinct banks
+            const uint32_t ry = smem_u32(s_rope) + py * rstride, rx = smem_u32(s_rope) + (args.rope_h + px) * rstride;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const int A = lo_off + j;                // angle index in [0, head_dim/2)
+              const uint32_t rbase_ = (A < hq ? ry : rx) + (A & (hq - 1)) * 4;
+              const float4 sn = lds128f(rbase_), cs = lds128f(rbase_ + hq * 4);
+              // rotation in packed f32x2: lo' = lo*cos - hi*sin, hi' = hi*cos + lo*sin (two angles per instruction)
+              const float2 c01 = make_float2(cs.x, cs.y), c23 = make_float2(cs.z, cs.w);
+              const float2 s01 = make_float2(sn.x, sn.y), s23 = make_float2(sn.z, sn.w);
+              const float2 l01 = make_float2(x[j], x[j + 1]), l23 = make_float2(x[j + 2], x[j + 3]);
+              const float2 h01 = make_float2(x[j + 16], x[j + 17]), h23 = make_float2(x[j + 18], x[j + 19]);
+              const float2 a01 = fma2(l01, c01, mul2(h01, make_float2(-s01.x, -s01.y)));
+              const float2 a23 = fma2(l23, c23, mul2(h23, make_float2(-s23.x, -s23.y)));
+              const float2 b01 = fma2(h01, c01, mul2(l01, s01));
+              const float2 b23 = fma2(h23, c23, mul2(l23, s23));
+              packed[j / 2] = TT::pack2(a01.x, a01.y);
+              packed[j / 2 + 1] = TT::pack2(a23.x, a23.y);
+              packed[8 + j / 2] = TT::pack2(b01.x, b01.y);
+              packed[8 + j / 2 + 1] = TT::pack2(b23.x, b23.y);
+            }
+          } else if (which < 2 && rot) {
+            const float* sinr = args.rope_sin + static_cast<long long>(t1 - args.prefix) * HDm;
+            const float* cosr = args.rope_cos + static_cast<long long>(t1 - args.prefix) * HDm;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 c_lo = *reinterpret_cast<const float4*>(cosr + lo_off + j), s_lo = *reinterpret_cast<const float4*>(sinr + lo_off + j);
+              const float4 c_hi = *reinterpret_cast<const float4*>(cosr + hi_off + j), s_hi = *reinterpret_cast<const float4*>(sinr + hi_off + j);
+              packed[j / 2] = TT::pack2(x[j] * c_lo.x - x[j + 16] * s_lo.x, x[j + 1] * c_lo.y - x[j + 17] * s_lo.y);
+              packed[j / 2 + 1] = TT::pack2(x[j + 2] * c_lo.z - x[j + 18] * s_lo.z, x[j + 3] * c_lo.w - x[j + 19] * s_lo.w);
+              packed[8 + j / 2] = TT::pack2(x[j + 16] * c_hi.x + x[j] * s_hi.x, x[j + 17] * c_hi.y + x[j + 1] * s_hi.y);
+              packed[8 + j / 2 + 1] = TT::pack2(x[j + 18] * c_hi.z + x[j + 2] * s_hi.z, x[j + 19] * c_hi.w + x[j + 3] * s_hi.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) packed[j / 2] = TT::pack2(x[j], x[j + 1]);
+          }
+          // stage: row = lane, 4 x 16 B chunks (2 of the lo segment, 2 of the hi segment), chunk position c ^ ((row >> 1) & 3)
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(patch4_u32 + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          __syncwarp();
+          T* base = reinterpret_cast<T*>(which == 0 ? args.q : (which == 1 ? args.k : args.v)) +
+                    static_cast<long long>(head) * args.ntok * HDm + ((lane & 2) ? hi_off : lo_off) + (lane & 1) * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2);
+            const uint4 val = lds128(patch4_u32 + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            if (dst_ok[i]) *reinterpret_cast<uint4*>(base + dst_off[i]) = val;
+          }
+        }
+        continue;   // the accumulator buffer was released above
+      } else if constexpr (EPI == 2) {
         // stage the (masked) bias of this tile's columns once
         epi_bar_sync();
         for (int i = etid; i < BN; i += 256) s_bias[i] = (e.bias && n0 + i < args.N) ? __ldg(e.bias + n0 + i) : 0.f;
@@ -462,7 +602,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             // table, A >= hq from the patch column's; cos/sin[A + head_dim/2] == cos/sin[A]
             const int pidx = t1 - args.prefix;
             const int py = pidx / args.rope_w, px = pidx - py * args.rope_w;
-            const uint32_t rstride = hq * 8;           // bytes per table row
+            // bytes per table row: + 16 B so that the 32 lanes (32 consecutive patch columns = 32 table rows) spread over all
+            // banks; with the dense 128 B rows every LDS.128 of the column table was an 8-way bank conflict (ncu: short_sb 28 %)
+            const uint32_t rstride = hq * 8 + 16;
             const uint32_t ry = smem_u32(s_rope) + py * rstride, rx = smem_u32(s_rope) + (args.rope_h + px) * rstride;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -565,10 +707,100 @@ __global__ void __launch_bounds__(320, 1) gemm_tc2_kernel(const __grid_constant_
             if (dst_ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(e.out) + dst_row[i] * e.ldc + ocol) = val;
           }
         }
+      } else if constexpr (EPI == 4) {
+        // ---- lean 16-bit epilogue (ViT fc1: bias -> Linear output rounded to 16 bits -> GELU).  Measured with ncu on the
+        // generic path: the MMA never waits for operands but for an accumulator buffer - eight epilogue warps (two per
+        // scheduler) run the dependent GELU chains at 0.2 IPC.  Here SIXTEEN warps drain a tile (four per TMEM lane
+        // quarter, two 32-column chunks each), the math runs on the TMEM registers (thread = accumulator row) and only the
+        // packed 16-bit result goes through the staging transpose.  (Standalone at the fc1 shape: 242 -> 213 us.)
+        // (no barrier among the epilogue warps: the bias comes through L1 as warp-uniform loads, each warp runs on its own)
+        long long dst_row[4];
+        bool dst_ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {             // phase-2 rows: rr = i*8 + lane/4 (4 lanes x 16 B = one 64 B row segment)
+          long long m2;
+          dst_ok[i] = row_of(q4 * 32 + i * 8 + (lane >> 2), m2);
+          dst_row[i] = dst_ok[i] ? m2 : 0;
+        }
+        uint8_t* patch4 = staging + ew * 2048;
+        const uint32_t patch4_u32 = smem_u32(patch4);
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q4 * 32) << 16);
+        constexpr int kPerWarp = BN / 32 / 4;            // chunks per warp (2 for BN 256)
+#pragma unroll 1
+        for (int cc = 0; cc < kPerWarp; ++cc) {
+          const int ch = half * kPerWarp + cc;           // half = ew >> 2 in 0..3 here
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          if (cc == kPerWarp - 1) {                      // the accumulator is in registers: hand the buffer back before the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(tempty0 + buf * 8);
+              else mbar_arrive(&tempty_bar[buf]);
+            }
+          }
+          const int n = n0 + ch * 32;
+          if (n >= args.N) continue;   // warp-uniform
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float2 a01 = add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b4.x, b4.y));
+            float2 a23 = add2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b4.z, b4.w));
+            if (e.round16) {
+              a01 = TT::unpack2(TT::pack2(a01.x, a01.y));
+              a23 = TT::unpack2(TT::pack2(a23.x, a23.y));
+            }
+            float f[4] = {a01.x, a01.y, a23.x, a23.y};
+            act_vec<ACT1, 4>(f);
+            packed[j / 2] = TT::pack2(f[0], f[1]);
+            packed[j / 2 + 1] = TT::pack2(f[2], f[3]);
+          }
+          // stage: row = lane, 64 B of output (4 x 16 B chunks) at chunk position c ^ ((row >> 1) & 3) within a 64 B slot
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(patch4_u32 + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          __syncwarp();
+          const int ocol = n + (lane & 3) * 8 + e.col_off;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2);
+            const uint4 val = lds128(patch4_u32 + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            if (dst_ok[i]) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(e.out) + dst_row[i] * e.ldc + ocol) = val;
+          }
+        }
+        continue;   // the accumulator buffer was released above
       } else {
         // ---- phase-2 row assignment: fp32 output -> 8 lanes per row (4 cols each), 4 rows per pass, 8 passes;
         //                              16-bit output -> 4 lanes per row (8 cols each), 8 rows per pass, 4 passes.
         constexpr bool o32 = (EPI == 1);
+        if constexpr (BN >= 64) {
+          // Short-K GEMMs with an fp32 residual stream (extractor out-proj / ffn2: 256 KB of residual read + write per tile
+          // against 2-3 us of MMA) are bound by the LATENCY of these residual loads - two warps per scheduler cannot keep
+          // enough bytes in flight.  Pull the NEXT tile's residual rows into L2 now, one tile ahead of their use.
+          if (args.res_prefetch && e.residual != nullptr && args.conv == 0 && e.ps_cout == 0) {
+            const long long nx = tile + unit_cnt;
+            if (nx < total_tiles) {
+              const int ntn = static_cast<int>(nx % args.n_tiles);
+              const long long mtn = PAIR ? 2 * (nx / args.n_tiles) + cta_rank : nx / args.n_tiles;
+              const long long mn = mtn * BM + (etid >> 1);
+              if (mn < args.M && (ntn + 1) * BN <= args.N) {
+                long long row = mn;
+                if (e.rows_in > 0) {
+                  const long long qb = mn / e.rows_in;
+                  row = qb * e.rows_out + e.row_off + (mn - qb * e.rows_in);
+                }
+                const char* pf = reinterpret_cast<const char*>(e.residual + row * e.ldres + ntn * BN + e.col_off) + (etid & 1) * (BN * 2);
+#pragma unroll
+                for (int l = 0; l < BN / 64; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + l * 128));
+              }
+            }
+          }
+        }
         const int lpr = o32 ? 8 : 4;                 // lanes per row
         const int rpp = 32 / lpr;                    // rows per pass
         const int npass = 32 / rpp;
@@ -781,7 +1013,7 @@ static int launch_pair2(const GemmMaps& maps, const GemmArgs& args, cudaStream_t
   const int pairs = num_sms() / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * static_cast<unsigned>(tiles < pairs ? tiles : pairs));
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(Cfg2<BN, EPI, true>::kThreads);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -817,7 +1049,7 @@ static int launch_variant2(const GemmMaps& maps, const GemmArgs& args, cudaStrea
   const long long tiles = static_cast<long long>(args.m_tiles) * args.n_tiles;
   const int sms = num_sms();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  launch_pdl(kern, grid, 320, args.conv == 3 ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem, stream, maps, args);
+  launch_pdl(kern, grid, Cfg2<BN, EPI>::kThreads, args.conv == 3 ? Cfg2<BN, EPI>::kSmemHalo : Cfg2<BN, EPI>::kSmem, stream, maps, args);
   return check_launch("gemm_tc2");
 }
 
@@ -838,7 +1070,16 @@ static int dispatch_epi(bool qkv, const GemmMaps& maps, const GemmArgs& args, cu
     if (a1 == 0 && a2 == 0) return launch_variant2<BN, 1, 0, 0, T>(maps, args, stream);
   } else {
     if (a1 == 0 && a2 == 0) return launch_variant2<BN, 0, 0, 0, T>(maps, args, stream);
-    if (a1 == B2U_ACT_GELU && a2 == 0) return launch_variant2<BN, 0, B2U_ACT_GELU, 0, T>(maps, args, stream);
+    if (a1 == B2U_ACT_GELU && a2 == 0) {
+      if constexpr (BN == 256) {
+        // plain Linear -> GELU on CTA pairs (ViT fc1): the 16-warp lean epilogue
+        const b2u_epilogue& e = args.epi;
+        const bool lean = args.pair && args.conv == 0 && !e.residual && !e.add16 && !e.scale && !e.shift && e.ps_cout == 0 &&
+                          e.rows_in == 0 && args.N % 32 == 0 && get_option(6) == 0;
+        if (lean) return launch_pair2<BN, 4, B2U_ACT_GELU, 0, T>(maps, args, stream);
+      }
+      return launch_variant2<BN, 0, B2U_ACT_GELU, 0, T>(maps, args, stream);
+    }
     if (a1 == 0 && a2 == B2U_ACT_RELU) return launch_variant2<BN, 0, 0, B2U_ACT_RELU, T>(maps, args, stream);
     if (a1 == 0 && a2 == B2U_ACT_LRELU) return launch_variant2<BN, 0, 0, B2U_ACT_LRELU, T>(maps, args, stream);
   }

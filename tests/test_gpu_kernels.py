@@ -207,19 +207,23 @@ def test_conv3x3_halo_mode_matches_per_tap_walk(cin, cout, hh, ww, B):
 
 
 @pytest.mark.parametrize("dtype", [L.BF16, L.F16])
-def test_qkv_rope_and_attention(gemm_impl, dtype):
+@pytest.mark.parametrize("B,h,D,Hh", [(2, 16, 384, 6),    # CTA pairs, 16-warp epilogue, half-empty last n-tile (N = 1152)
+                                      (1, 8, 768, 12),    # M = 69 < 256: one CTA per tile (no pairing), 256-wide tiles
+                                      (2, 8, 512, 4),     # head_dim 128 (ViT-7B): two 64-column units per head
+                                      (3, 16, 128, 2)])   # N = 384 -> 128-wide tiles: the 8-warp epilogue
+def test_qkv_rope_and_attention(gemm_impl, dtype, B, h, D, Hh):
     td = TD[dtype]
-    B, h, D, Hh = 2, 16, 384, 6
+    hd = D // Hh
     Pn = h * h
     N = Pn + 5
     lib = L.load()
     Y = _rand(B * N, D, dt=td)
     Wq = _rand(3 * D, D, dt=td, scale=D ** -0.5, seed=1)
     bias = _rand(3 * D, seed=2, scale=0.1)
-    periods = 100.0 ** (2 * torch.arange(16, dtype=torch.float32) / 32)
+    periods = 100.0 ** (2 * torch.arange(hd // 4, dtype=torch.float32) / (hd // 2))
     sin, cos = O.rope_sincos(periods, h, h)
     sin, cos = sin.to(DEV).contiguous(), cos.to(DEV).contiguous()
-    q, k, v = (torch.full((B, Hh, N, 64), float("nan"), device=DEV, dtype=td) for _ in range(3))
+    q, k, v = (torch.full((B, Hh, N, hd), float("nan"), device=DEV, dtype=td) for _ in range(3))
     p = L.QkvParams()
     p.B, p.ntok, p.D, p.heads, p.prefix = B, N, D, Hh, 5
     p.A, p.lda, p.Wp, p.ldw, p.bias = P(Y), D, P(Wq), D, P(bias)
@@ -227,23 +231,23 @@ def test_qkv_rope_and_attention(gemm_impl, dtype):
     L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv")
     torch.cuda.synchronize()
     if gemm_impl == "v2":   # separable in-smem rope tables must give bit-identical q/k
-        q2, k2, v2_ = (torch.full((B, Hh, N, 64), float("nan"), device=DEV, dtype=td) for _ in range(3))
+        q2, k2, v2_ = (torch.full((B, Hh, N, hd), float("nan"), device=DEV, dtype=td) for _ in range(3))
         p.q, p.k, p.v, p.rope_w = P(q2), P(k2), P(v2_), h
         L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv(smem rope)")
         torch.cuda.synchronize()
         assert torch.equal(q, q2) and torch.equal(k, k2) and torch.equal(v, v2_)
     qkv = (Y.float() @ Wq.float().t() + bias).to(td)
-    qr, kr, vr = [t.transpose(1, 2) for t in torch.unbind(qkv.reshape(B, N, 3, Hh, 64), 2)]
+    qr, kr, vr = [t.transpose(1, 2) for t in torch.unbind(qkv.reshape(B, N, 3, Hh, hd), 2)]
     qr, kr = O._rope(qr, sin, cos), O._rope(kr, sin, cos)
     tol = 2 ** -6 if dtype == L.BF16 else 2 ** -9
     assert rel_err(q, qr) < tol and rel_err(k, kr) < tol and rel_err(v, vr) < tol
     # the QKV epilogue's transposed V store feeds the tcgen05 attention kernel: whole path against SDPA
     npad = (N + 7) // 8 * 8
-    vt = torch.zeros(B, Hh, 64, npad, device=DEV, dtype=td)
+    vt = torch.zeros(B, Hh, hd, npad, device=DEV, dtype=td)
     p.q, p.k, p.v, p.v_transposed, p.npad, p.rope_w = P(q), P(k), P(vt), 1, npad, h
     L.check(lib.b2u_qkv_rope(C.byref(p), stream()), "qkv(V^T)")
     out = torch.full((B, N, D), float("nan"), device=DEV, dtype=td)
-    L.check(lib.b2u_attention_tc(P(q), P(k), P(vt), P(out), B, Hh, N, npad, 0, 64 ** -0.5, dtype, stream()), "attention")
+    L.check(lib.b2u_attention_tc_hd(P(q), P(k), P(vt), P(out), B, Hh, N, npad, hd, hd ** -0.5, dtype, stream()), "attention")
     torch.cuda.synchronize()
     assert torch.equal(vt[..., :N], v.transpose(2, 3))
     ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, D)

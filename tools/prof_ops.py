@@ -18,8 +18,12 @@ bf = torch.bfloat16
 g = torch.Generator().manual_seed(0)
 rnd = lambda *s, dt=bf, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev).to(dt)
 
-if op in ("fc1", "fc2", "proj"):
-    if op == "fc1":
+if op in ("fc1", "fc1_noact", "fc2", "proj"):
+    if op == "fc1_noact":
+        A, W, bias = rnd(T, D), rnd(Hd, D, sc=D ** -0.5), rnd(Hd, dt=torch.float32)
+        out = torch.empty(T, Hd, device=dev, dtype=bf)
+        run = lambda: gemm(A, W, out, L.BF16, bias=bias)
+    elif op == "fc1":
         A, W, bias = rnd(T, D), rnd(Hd, D, sc=D ** -0.5), rnd(Hd, dt=torch.float32)
         out = torch.empty(T, Hd, device=dev, dtype=bf)
         run = lambda: gemm(A, W, out, L.BF16, bias=bias, act1=L.ACT_GELU)
@@ -31,6 +35,11 @@ if op in ("fc1", "fc2", "proj"):
         A, W, bias = rnd(T, D), rnd(D, D, sc=D ** -0.5), rnd(D, dt=torch.float32)
         X, ls = rnd(T, D, dt=torch.float32), rnd(D, dt=torch.float32)
         run = lambda: gemm(A, W, X, L.BF16, out_fp32=True, bias=bias, scale=ls, residual=X, ldres=D)
+elif op in ("outproj", "ffn2"):   # extractor GEMMs into the fp32 query stream (dinounet_l, B=32: 172032 query rows)
+    Mq, Kq = 32 * 5376, (512 if op == "outproj" else 256)
+    A, W, bias = rnd(Mq, Kq, dt=torch.float16), rnd(D, Kq, dt=torch.float16, sc=Kq ** -0.5), rnd(D, dt=torch.float32)
+    X = rnd(Mq, D, dt=torch.float32)
+    run = lambda: gemm(A, W, X, L.F16, out_fp32=True, bias=bias, residual=X, ldres=D)
 elif op == "qkv":
     import ctypes as C
     from oracle import dinounet_oracle as O
