@@ -5,7 +5,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["gemm_api.cu", ("gemm_tc2.cu", "gemm_tc2_bf16.o", ["-DB2U_GEMM2_TYPE=1"]), ("gemm_tc2.cu", "gemm_tc2_f16.o", ["-DB2U_GEMM2_TYPE=0"]), "attention_tc.cu", "attention_tc3.cu", "elementwise.cu", "fp32_tier.cu", "train_bwd.cu", "msda.cu", "sliding_window.cu", "loss.cu", "host_util.cu"]
-OUT = os.path.join(os.path.dirname(HERE), "libdinounet_b200.so")
+# A/B builds: B2U_EXTRA_FLAGS="-DFOO=1" B2U_OUT_SUFFIX=_foo python build.py -> libdinounet_b200_foo.so (objects under build_foo/);
+# run with DINOUNET_B200_LIB=<that file>.  The default build takes neither.
+SUFFIX = os.environ.get("B2U_OUT_SUFFIX", "")
+EXTRA = os.environ.get("B2U_EXTRA_FLAGS", "").split()
+OUT = os.path.join(os.path.dirname(HERE), f"libdinounet_b200{SUFFIX}.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math=false"]
@@ -22,7 +26,7 @@ def _stale(obj, src):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + SUFFIX)
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
     for s in SOURCES:
@@ -35,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, oname)
         objs.append(obj)
         if force or _stale(obj, src):
-            cmd = [NVCC, *FLAGS, *extra, "-c", src, "-o", obj]
+            cmd = [NVCC, *FLAGS, *EXTRA, *extra, "-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             procs.append((oname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

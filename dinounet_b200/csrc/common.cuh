@@ -60,18 +60,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// (B2U_MBAR_HINT_NS: try_wait with a suspend-time hint.  Measured with 20 us: GEMMs unchanged, attention 240.7 -> 265.5 us
+// per layer - the wake-up is slower than the default poll - so the default build does not define it.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
+#ifdef B2U_MBAR_HINT_NS
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(addr),
       "r"(parity)
+#ifdef B2U_MBAR_HINT_NS
+      , "r"(static_cast<uint32_t>(B2U_MBAR_HINT_NS))
+#endif
       : "memory");
 }
 

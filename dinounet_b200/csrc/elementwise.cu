@@ -641,8 +641,9 @@ extern "C" int b2u_tail_fuse(const void* base, int32_t base_fp32, int64_t base_b
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm
 // stats: block = (row chunk, image b); thread = (row lane, 8-channel group); smem tree over row lanes; the block's
-// partial (sum, sumsq) per channel goes to a workspace slot, and the LAST block of each image (ticket counter) adds the
-// slots in fixed chunk order -> bitwise deterministic, no float atomics, no zero-fill of `sums` needed.
+// partial (shifted sum, shifted sumsq) per channel goes to a workspace slot, and the LAST block of each image (ticket counter)
+// adds the slots in fixed chunk order -> bitwise deterministic, no float atomics, no zero-fill of `sums` needed.
+// Output per (image, channel): (sum x, sum (x - mean)^2).
 static inline int in_stats_chunk(int rows) { return rows >= 8192 ? 2048 : (rows >= 1024 ? 256 : 64); }
 
 template <typename T>
@@ -656,6 +657,14 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const T* __restrict__ x, 
   const int rows_par = 256 / C8;
   const int r0 = blockIdx.x * chunk;
   const int r1 = min(rows, r0 + chunk);
+  // Shifted sums: every block of image b accumulates sum(x - x0) and sum((x - x0)^2) with x0 = the image's first pixel of the
+  // channel, so the variance below never subtracts two large nearly equal numbers when |mean| >> std
+  float sh[8];
+  {
+    Vec8<T> v0;
+    v0.load(x + static_cast<long long>(b) * rows * ldx + cg * 8);
+    v0.to_float(sh);
+  }
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int r = r0 + rl; r < r1; r += rows_par) {
     Vec8<T> v;
@@ -663,7 +672,7 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const T* __restrict__ x, 
     float f[8];
     v.to_float(f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    for (int j = 0; j < 8; ++j) { const float d = f[j] - sh[j]; s[j] += d; q[j] = fmaf(d, d, q[j]); }
   }
   float* my = red + (rl * C8 + cg) * 16;
 #pragma unroll
@@ -684,11 +693,17 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const T* __restrict__ x, 
   if (!s_last) return;
   __threadfence();
   const float* pb = work + B + static_cast<long long>(b) * nchunks * nout;
-  for (int o = threadIdx.x; o < nout; o += 256) {
-    float t = 0.f;
-    for (int c = 0; c < nchunks; ++c) t += __ldcg(pb + static_cast<long long>(c) * nout + o);
-    const int g = o / 16, j = o % 16;
-    sums[(static_cast<long long>(b) * C8 * 8 + g * 8 + (j & 7)) * 2 + (j >> 3)] = t;
+  for (int o = threadIdx.x; o < C8 * 8; o += 256) {       // one thread per channel: fixed chunk order -> deterministic
+    const int g = o >> 3, j = o & 7;
+    float ts = 0.f, tq = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      ts += __ldcg(pb + static_cast<long long>(c) * nout + g * 16 + j);
+      tq += __ldcg(pb + static_cast<long long>(c) * nout + g * 16 + 8 + j);
+    }
+    const float x0 = T16<T>::to_f(x[static_cast<long long>(b) * rows * ldx + o]);
+    float* dst = sums + (static_cast<long long>(b) * C8 * 8 + o) * 2;
+    dst[0] = fmaf(static_cast<float>(rows), x0, ts);                  // sum x
+    dst[1] = fmaxf(tq - ts * ts / static_cast<float>(rows), 0.f);     // sum (x - mean)^2
   }
   if (threadIdx.x == 0) counters[b] = 0;  // self-resetting ticket
 }
@@ -731,7 +746,7 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const T* __restrict__ x, 
     const int c = cg * 8 + j;
     const float2 sq = *reinterpret_cast<const float2*>(sums + (static_cast<long long>(b) * C8 * 8 + c) * 2);
     const float mean = sq.x * inv;
-    const float var = fmaxf(sq.y * inv - mean * mean, 0.f);
+    const float var = sq.y * inv;                     // centred second moment (b2u_in_stats)
     // same operation order as before: (x - mean) * rstd * gamma + beta
     sa[j] = rsqrtf(var + eps);
     sb[j] = mean;
@@ -888,7 +903,7 @@ __global__ void __launch_bounds__(256) seg_head_kernel(const T* __restrict__ x, 
   const int b = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += 256) {
     const float mean = sums[(static_cast<long long>(b) * C + c) * 2] / rows;
-    const float var = fmaxf(sums[(static_cast<long long>(b) * C + c) * 2 + 1] / rows - mean * mean, 0.f);
+    const float var = sums[(static_cast<long long>(b) * C + c) * 2 + 1] / rows;   // centred second moment (b2u_in_stats)
     const float a = rsqrtf(var + eps) * gamma[c];
     s_a[c] = a;
     s_b[c] = beta[c] - mean * a;
@@ -949,7 +964,7 @@ __global__ void __launch_bounds__(256) seg_head_kernel8(const T* __restrict__ x,
   const int b = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += 256) {
     const float mean = sums[(static_cast<long long>(b) * C + c) * 2] / rows;
-    const float var = fmaxf(sums[(static_cast<long long>(b) * C + c) * 2 + 1] / rows - mean * mean, 0.f);
+    const float var = sums[(static_cast<long long>(b) * C + c) * 2 + 1] / rows;   // centred second moment (b2u_in_stats)
     const float a = rsqrtf(var + eps) * gamma[c];
     s_a[c] = a;
     s_b[c] = beta[c] - mean * a;

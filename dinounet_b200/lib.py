@@ -14,7 +14,8 @@ F16, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LRELU, ACT_SWIGLU = 0, 1, 2, 3, 4
 CONV_NONE, CONV3X3_S1, CONV3X3_S2 = 0, 1, 2
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdinounet_b200.so")
+# DINOUNET_B200_LIB: load another build of the same C-ABI (A/B measurements of kernel variants; csrc/build.py)
+_LIB_PATH = os.environ.get("DINOUNET_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdinounet_b200.so")
 
 
 class NativeLibraryError(RuntimeError):

@@ -561,6 +561,29 @@ def test_msda_backward_engine_shape_and_autograd_function():
         ops.ms_deform_attn_forward(value.transpose(1, 2), shapes, lsi, loc, aw, 64)
 
 
+def test_instancenorm_large_mean_small_std():
+    """|mean| >> std: E[x^2] - mean^2 in fp32 loses the variance (x^2 ~ 1e4, var ~ 0.07); the statistics kernel accumulates
+    shifted sums instead, so the normalised output still matches torch's (Welford) instance_norm."""
+    lib = L.load()
+    B, rows, Cc = 2, 16384, 32
+    off = torch.linspace(-150.0, 150.0, Cc, device=DEV)
+    x = (_rand(B * rows, Cc, seed=5) * 0.25 + off).to(torch.float16)
+    sums = torch.full((B, Cc, 2), float("nan"), device=DEV)
+    work = torch.zeros(int(lib.b2u_in_stats_work_floats(B, rows, Cc)), device=DEV)
+    L.check(lib.b2u_in_stats(P(x), Cc, P(sums), P(work), B, rows, Cc, L.F16, stream()), "stats")
+    g, b = _rand(Cc, seed=1), _rand(Cc, seed=2)
+    y = torch.empty(B * rows, Cc, device=DEV, dtype=torch.float16)
+    L.check(lib.b2u_in_apply(P(x), Cc, P(y), Cc, P(sums), P(g), P(b), B, rows, Cc, 1e-5, L.F16, stream()), "apply")
+    torch.cuda.synchronize()
+    xd = x.double().view(B, rows, Cc)
+    assert rel_err(sums[..., 0], xd.sum(1).float()) < 1e-6
+    var = xd.var(1, unbiased=False)
+    assert ((sums[..., 1].double() / rows - var).abs() / var).max().item() < 1e-4
+    xin = x.float().view(B, rows, Cc).transpose(1, 2).reshape(B, Cc, 128, 128)
+    ref = F.leaky_relu(F.instance_norm(xin, None, None, g, b, True, 0.1, 1e-5), 0.01)
+    assert rel_err(y.view(B, rows, Cc).transpose(1, 2).reshape(B, Cc, 128, 128), ref) < 3e-3
+
+
 def test_instancenorm_film_se_seg():
     lib = L.load()
     B, rows, Cc = 2, 4096, 32
