@@ -519,12 +519,14 @@ def main():
             t_gemm = sum(fam.get(k, 0) for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2"))
             pk = peaks()
             traffic, traffic_src = None, None
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+            tj = None
             if os.path.exists(tpath) and (a.model, B, S, a.vit_dtype) == ("dinounet_l", 32, 512, "bf16"):
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of
-                # the four ViT GEMM shapes at exactly this workload (tools/prof_ops.py), averaged over the family
-                traffic = json.load(open(tpath))["vit_gemm_family_avg_per_launch"]
-                traffic_src = "profiles/r01_traffic.json (ncu --set full, fc1/fc2/proj/qkv shapes)"
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu pass over one step of exactly
+                # this workload (tools/one_step.py + tools/ncu_table.py), averaged over the four ViT GEMM shapes
+                tj = json.load(open(tpath))
+                traffic = tj["vit_gemm_family_avg_per_launch"]
+                traffic_src = "profiles/r02_traffic.json (ncu per-launch dram bytes, qkv/proj/fc1/fc2 of one step)"
             ach = flops / (t_gemm * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel<256,EPI,ACT,%s> = persistent tcgen05 GEMM (ViT qkv/proj/fc1/fc2, %d launches/step)" % (a.vit_dtype, 4 * v.depth),
                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src,
@@ -541,7 +543,8 @@ def main():
                 ach_h = hb / (t_conv * 1e-3) / 1e9
                 roof_hbm = {"bound": "hbm", "kernel": "gemm_tc2_kernel<32,...> conv3x3 halo mode (decoder stage 2 conv 0, %d->%d ch @ %dx%d)" % (2 * f0, f0, S, S),
                             "achieved": ach_h, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_h / pk["hbm_gbs"],
-                            "algorithmic_bytes_per_launch": hb, "us": t_conv * 1e3, "traffic": None, "peak_source": pk["src"]}
+                            "algorithmic_bytes_per_launch": hb, "us": t_conv * 1e3,
+                            "traffic": (tj or {}).get("per_launch_dram_bytes", {}).get("d2.conv0"), "peak_source": pk["src"]}
             if a.ops_out:
                 os.makedirs(os.path.dirname(a.ops_out) or ".", exist_ok=True)
                 json.dump({"per_family_ms": breakdown, "per_op_ms": [(n, s_.elapsed_time(e_)) for n, s_, e_ in evs]},

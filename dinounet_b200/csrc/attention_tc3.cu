@@ -22,7 +22,7 @@
 //   * items are ordered long-first: all full tile pairs, then the single-tile leftovers, so the persistent round-robin
 //     ends on the short items.
 // Every MMA operand is K-major SW128; V is consumed as V^T [B,H,HD,npad] (written transposed by the QKV epilogue).
-// TMEM columns per group: S [0,128) | O [128, 128+HD).
+// TMEM columns per group: S [0,128) | O [128, 128+HD) | P [128+HD, 128+HD+64) (16-bit probabilities, A operand of the PV MMA).
 #include <type_traits>
 
 #include "common.cuh"
@@ -46,7 +46,7 @@ template <int HD> struct At3Cfg {
   // 20 warps compile to 96 registers per thread (registers are allocated per 4-warp granule: 65536 / 640)
   static constexpr int kThreads = kCtrlWarps * 32 + kGroups * 128 * kSplit;
   static constexpr int kXchgBytes = 2 * 128 * 4 * 4;        // [2 groups][128 rows][4] fp32 exchange slots
-  static constexpr int kGroupCols = 128 + HD;               // S | O
+  static constexpr int kGroupCols = 128 + HD + 64;          // S | O | P (128 keys x 16 bit = 64 columns)
   static constexpr int kSmem = kGroups * (kQBytes + kPBytes) + kStages * (kKBytes + kVBytes) + 1024 + 256 + kXchgBytes;
 };
 
@@ -60,6 +60,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -122,9 +125,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
 
-template <typename TT, bool kTail, int POLY>
+template <typename TT, bool kTail, int POLY, bool PT>
 __device__ __forceinline__ float exp_store(const uint32_t (&v)[32], int lim, float sl2, float m_new, int gc,
-                                           uint32_t sP_row, int row) {
+                                           uint32_t sP_row, int row, uint32_t tP) {
   float2 rs2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};    // independent packed partial sums
   const float2 sl2v = make_float2(sl2, sl2), mnv = make_float2(-m_new, -m_new);
   const uint32_t base = sP_row + (gc >> 1) * (128 * 128);
@@ -144,15 +147,19 @@ __device__ __forceinline__ float exp_store(const uint32_t (&v)[32], int lim, flo
       rs2[c >> 1] = add2(rs2[c >> 1], make_float2(a, b));
       pk[c >> 1] = TT::pack2(a, b);
     }
-    const int chunk = (gc & 1) * 4 + c4;
-    sts128a(base + ((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    if constexpr (PT) {
+      tmem_st4(tP + gc * 16 + c4 * 4, pk[0], pk[1], pk[2], pk[3]);   // keys gc*32 + c4*8 .. +7 of this thread's row
+    } else {
+      const int chunk = (gc & 1) * 4 + c4;
+      sts128a(base + ((chunk ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    }
   }
   const float2 t = add2(add2(rs2[0], rs2[1]), add2(rs2[2], rs2[3]));
   return t.x + t.y;
 }
 
 struct SmCtx {
-  uint32_t tS, tO, sP_row;
+  uint32_t tS, tO, tP, sP_row;
   int row, part, lane, bar_id;
   float* xm;
   float sl2;
@@ -165,7 +172,7 @@ struct SmCtx {
 //           exp(group 1), re-read group 0, release S, exp(group 0).  Every tcgen05.ld is unconditional: an asm output
 //           array defined under a branch is materialised in local memory by the compiler.
 //    kTail: the last chunk owns ngrp in {0,1,2} groups and lim valid columns: per-group blocks with their own arrays.
-template <typename TT, int HD, bool kTail, bool kOne, int POLY>
+template <typename TT, int HD, bool kTail, bool kOne, int POLY, bool PT>
 __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, int lim, float& m, float& l,
                                               uint32_t& sfull_cnt, uint32_t& ofull_cnt) {
   constexpr int OW = HD / 2;
@@ -216,9 +223,9 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
     tc_fence_after();
   }
   if constexpr (!kTail) {
-    rs = exp_store<TT, false, POLY>(v, 32, cx.sl2, m_new, cx.part * 2 + 1, cx.sP_row, cx.row);
+    rs = exp_store<TT, false, POLY, PT>(v, 32, cx.sl2, m_new, cx.part * 2 + 1, cx.sP_row, cx.row, cx.tP);
     if constexpr (kOne) {
-      rs += exp_store<TT, false, POLY>(w, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row);
+      rs += exp_store<TT, false, POLY, PT>(w, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row, cx.tP);
     } else {
       tmem_ld32(cx.tS, v);
       tmem_ld_wait();
@@ -230,7 +237,7 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
         uint32_t t[32];
         tmem_ld32(cx.tS + pc * 32, t);
         tmem_ld_wait();
-        rs += exp_store<TT, true, POLY>(t, lim - pc * 32, cx.sl2, m_new, cx.part * 2 + pc, cx.sP_row, cx.row);
+        rs += exp_store<TT, true, POLY, PT>(t, lim - pc * 32, cx.sl2, m_new, cx.part * 2 + pc, cx.sP_row, cx.row, cx.tP);
       }
     }
   }
@@ -238,7 +245,7 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
     tc_fence_before();
     __syncwarp();
     if (cx.lane == 0) mbar_arrive(cx.s_free);                // all reads of S(j) done: S(j+1) may be produced
-    if constexpr (!kTail) rs += exp_store<TT, false, POLY>(v, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row);
+    if constexpr (!kTail) rs += exp_store<TT, false, POLY, PT>(v, 32, cx.sl2, m_new, cx.part * 2, cx.sP_row, cx.row, cx.tP);
   }
   // ---- rare: the reference maximum moved -> rescale this warp's slice of O in TMEM (no PV MMA is in flight: PV(j-1) has
   // retired and PV(j) waits for this warp's p_full arrival)
@@ -256,13 +263,14 @@ __device__ __forceinline__ void softmax_chunk(const SmCtx& cx, int j, int ngrp, 
   }
   l = l * corr + rs;
   m = m_new;
-  fence_proxy_async();                       // make the generic-proxy P writes visible to the MMA (async proxy)
+  if constexpr (PT) tmem_st_wait();          // P (and a rescaled O) are in tensor memory before the MMA is told so
+  else fence_proxy_async();                  // make the generic-proxy P writes visible to the MMA (async proxy)
   tc_fence_before();
   __syncwarp();
   if (cx.lane == 0) mbar_arrive(cx.p_full);
 }
 
-template <typename T, int HD, bool kOne, int POLY>
+template <typename T, int HD, bool kOne, int POLY, bool PT>
 __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs args) {
   using TT = T16<T>;
   using CF = At3Cfg<HD>;
@@ -394,9 +402,15 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
           const int nk = (j + 1 == J) ? (tail_n >> 4) : 8;    // K = 16 steps of this chunk
           for (int t = 0; t < nk; ++t) {
             const int kb = t >> 2, k = t & 3;
-            const uint64_t da = make_desc_k128(smem_u32(sP + g * CF::kPBytes + kb * 128 * 128));
             const uint64_t db = make_desc_k128(smem_u32(sV + st_p * CF::kVBytes + kb * HD * 128));
-            tc_mma_f16(tS + 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_o, (j | t) != 0 ? 1u : 0u);
+            if constexpr (PT) {
+              // A = P from tensor memory (8 columns per K = 16 step): the PV MMA reads only V^T from shared memory, whose
+              // bandwidth (128 B/clk) otherwise caps a 128 x HD x 16 MMA with a 4 KB smem A operand at 2/3 of its rate
+              tc_mma_f16_ts(tS + 128, tS + 128 + HD + t * 8, db + static_cast<uint64_t>(k * 2), idesc_o, (j | t) != 0 ? 1u : 0u);
+            } else {
+              const uint64_t da = make_desc_k128(smem_u32(sP + g * CF::kPBytes + kb * 128 * 128));
+              tc_mma_f16(tS + 128, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc_o, (j | t) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(&o_full[g]);
           tc_commit(&kv_empty[st_p]);
@@ -416,6 +430,7 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
     constexpr int OW = HD / SPLIT;          // O columns (head dims) per warp
     const uint32_t tS = tmem_base + g * CF::kGroupCols + (static_cast<uint32_t>(q4 * 32) << 16) + part * CW;
     const uint32_t tO = tmem_base + g * CF::kGroupCols + 128 + (static_cast<uint32_t>(q4 * 32) << 16) + part * OW;
+    const uint32_t tP = tmem_base + g * CF::kGroupCols + 128 + HD + (static_cast<uint32_t>(q4 * 32) << 16);
     const uint32_t sP_row = smem_u32(sP + g * CF::kPBytes) + row * 128;
     const uint32_t sP_base = smem_u32(sP + g * CF::kPBytes);
     float* xm = xchg + (g * 128 + row) * 4;  // [2 buffers][2 parts] row maxima; the l exchange reuses the slots
@@ -444,14 +459,14 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
       }
       float m = -INFINITY, l = 0.f;
       SmCtx cx;
-      cx.tS = tS; cx.tO = tO; cx.sP_row = sP_row; cx.row = row; cx.part = part; cx.lane = lane; cx.xm = xm; cx.sl2 = sl2;
+      cx.tS = tS; cx.tO = tO; cx.tP = tP; cx.sP_row = sP_row; cx.row = row; cx.part = part; cx.lane = lane; cx.xm = xm; cx.sl2 = sl2;
       cx.s_full = &s_full[g]; cx.s_free = &s_free[g]; cx.p_full = &p_full[g]; cx.o_full = &o_full[g];
       cx.bar_id = 1 + g * 4 + q4;
-      for (int j = 0; j + 1 < J; ++j) softmax_chunk<TT, HD, false, kOne, POLY>(cx, j, 2, 64, m, l, sfull_cnt, ofull_cnt);
+      for (int j = 0; j + 1 < J; ++j) softmax_chunk<TT, HD, false, kOne, POLY, PT>(cx, j, 2, 64, m, l, sfull_cnt, ofull_cnt);
       {
         int ngrp = (tail_n - part * CW + 31) >> 5;             // 32-column groups this warp owns in the last chunk
         ngrp = ngrp < 0 ? 0 : (ngrp > CW / 32 ? CW / 32 : ngrp);
-        softmax_chunk<TT, HD, true, kOne, POLY>(cx, J - 1, ngrp, tail_valid - part * CW, m, l, sfull_cnt, ofull_cnt);
+        softmax_chunk<TT, HD, true, kOne, POLY, PT>(cx, J - 1, ngrp, tail_valid - part * CW, m, l, sfull_cnt, ofull_cnt);
       }
       // ---- last PV retired: read this warp's O slice, release the accumulator for the next item
       mbar_wait(&o_full[g], ofull_cnt & 1);
@@ -509,9 +524,9 @@ __global__ void __launch_bounds__(At3Cfg<HD>::kThreads, 1) attn_tc3_kernel(const
   }
 }
 
-template <typename T, int HD, bool kOne, int POLY>
+template <typename T, int HD, bool kOne, int POLY, bool PT = false>
 static int launch_attn_tc3(const AttnMaps& maps, const AttnArgs& a, cudaStream_t stream) {
-  auto kern = attn_tc3_kernel<T, HD, kOne, POLY>;
+  auto kern = attn_tc3_kernel<T, HD, kOne, POLY, PT>;
   using CF = At3Cfg<HD>;
   static_assert(CF::kSmem <= 227 * 1024, "attention smem budget");
   static bool configured_dev[64] = {};
@@ -528,17 +543,19 @@ static int launch_attn_tc3(const AttnMaps& maps, const AttnArgs& a, cudaStream_t
 }
 
 int attention_tc3_dispatch(const AttnMaps& maps, const AttnArgs& a, int head_dim, int dtype, int variant, cudaStream_t stream) {
-  // variant (b2u_set_option(4, .)): 0 = default, 4 = single-pass softmax, 6 = every exp2 on the MUFU pipe, 7 = every 4th exp2 on the FMA pipe (default: every 3rd; measured: 1/2 and packed-pair polynomials lose)
+  // variant (b2u_set_option(4, .)): 0 = default (P in tensor memory), 8 = P through shared memory (round-2 first version), 4 = single-pass softmax, 6 = every exp2 on the MUFU pipe, 7 = every 4th exp2 on the FMA pipe (default: every 3rd; measured: 1/2 and packed-pair polynomials lose)
   const bool bf = dtype == B2U_BF16;
   if (head_dim == 64) {
     if (variant == 4) return bf ? launch_attn_tc3<__nv_bfloat16, 64, true, 0>(maps, a, stream) : launch_attn_tc3<__half, 64, true, 0>(maps, a, stream);
     if (variant == 6) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 0>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 0>(maps, a, stream);
     if (variant == 7) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 4>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 4>(maps, a, stream);
-    return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 3>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 3>(maps, a, stream);
+    if (variant == 8) return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 3>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 3>(maps, a, stream);
+    return bf ? launch_attn_tc3<__nv_bfloat16, 64, false, 3, true>(maps, a, stream) : launch_attn_tc3<__half, 64, false, 3, true>(maps, a, stream);
   }
   // head_dim 128: 320 threads compile to 168 registers -> the single-pass softmax fits without spills; exp2 is half as
   // dense per flop there, MUFU is not the limiter
-  return bf ? launch_attn_tc3<__nv_bfloat16, 128, true, 0>(maps, a, stream) : launch_attn_tc3<__half, 128, true, 0>(maps, a, stream);
+  if (variant == 8) return bf ? launch_attn_tc3<__nv_bfloat16, 128, true, 0>(maps, a, stream) : launch_attn_tc3<__half, 128, true, 0>(maps, a, stream);
+  return bf ? launch_attn_tc3<__nv_bfloat16, 128, true, 0, true>(maps, a, stream) : launch_attn_tc3<__half, 128, true, 0, true>(maps, a, stream);
 }
 
 }  // namespace b2u

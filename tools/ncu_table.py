@@ -84,4 +84,11 @@ for f, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
                f"{gbs / peaks['hbm_gbs']:.2f} | {a['tens'] / a['ns']:.1f} | {a['xu'] / a['ns']:.1f} | {a['issue'] / a['ns']:.1f} |")
 out.append(f"\nSum of kernel durations: {tot / 1e6:.2f} ms (CUDA-event step of the same build, graph replay: {event_ms} ms).")
 open(dst, "w").write("\n".join(out) + "\n")
+# per-launch DRAM traffic of the roofline kernels (bench.py reads this file for its `traffic` fields)
+per = {f: (a["rd"] + a["wr"]) / a["n"] for f, a in agg.items()}
+vit = [per[k] for k in ("vit.qkv", "vit.proj", "vit.fc1", "vit.fc2") if k in per]
+traffic = {"per_launch_dram_bytes": {k: per[k] for k in ("vit.fc1", "vit.fc2", "vit.proj", "vit.qkv", "vit.attn", "d2.conv0", "d2.conv1") if k in per},
+           "vit_gemm_family_avg_per_launch": sum(vit) / max(len(vit), 1),
+           "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu pass over one eager step with the final binaries (" + src + ")"}
+json.dump(traffic, open(dst.replace("kernel_table.md", "traffic.json"), "w"), indent=1)
 print("\n".join(out[:16]))
