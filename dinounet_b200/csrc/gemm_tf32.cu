@@ -1,0 +1,195 @@
+// tcgen05 kind::tf32 GEMM for the TRAINING path: same parameter block, addressing modes and epilogue as b2u_f32_gemm
+// (csrc/fp32_tier.cu) - plain / transposed rows, the 3x3 window of an NHWC image on the A side (conv forward, conv data
+// gradient) or on the W side (conv weight gradient, K = output pixels), row remap, 2x2 pixel shuffle, split-K atomics -
+// but the products run on the 5th-generation tensor cores: fp32 operands rounded to TF32 (cvt.rna: 10 mantissa bits, the
+// mantissa width of the fp16 autocast the reference trains under, nnUNetTrainer.py:899-929, with fp32's exponent range),
+// fp32 accumulation in tensor memory.  The fp32 SIMT kernel stays the parity tier (1e-5); this one is the fast tier of
+// the train step (the SIMT GEMM was 87 % of it, profiles/r02_train_step_kernels_dinounet_b_b64.md).
+//
+// Why register-path loaders instead of TMA: five of the eight operand modes are gathers that no tensor map expresses
+// without a transposed copy in HBM (A[k][m], W[k][n], flipped 3x3 weights, the per-pixel window with K = pixel index).
+// Every mode is therefore loaded with ordinary (vector where the mode is K-contiguous) global loads, rounded to TF32
+// in registers and written to shared memory in exactly the layout a SWIZZLE_128B K-major tensor map would produce
+// (row r of a k-block = 128 B = 32 floats; 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)), so the
+// UMMA descriptors are byte-identical to the 16-bit GEMM's (make_desc_k128; +32 B per K = 8 step).
+//
+// CTA = one 128 x BN output tile of one K slice (grid = m tiles x n tiles x ksplit), 256 threads, 3-stage smem ring:
+//   all threads: wait stage free (tcgen05.commit -> mbarrier) -> st.shared the k-block fetched one iteration earlier ->
+//   fence.proxy.async -> issue the global loads of the NEXT k-block (in flight across the barrier) -> __syncthreads ->
+//   one elected thread issues 4 x tcgen05.mma (M128, N = BN, K8) + commit.  Epilogue: tcgen05.ld, thread = row.
+// 2-3 CTAs per SM (60-96 KB smem, BN TMEM columns each) hide the load latency of one another.
+#include <math.h>
+
+#include "common.cuh"
+#include "../../include/dinounet_b200.h"
+#include "gemm_tf32_addr.h"
+#include "host_util.h"
+
+namespace b2u {
+namespace {
+
+using namespace tf32;
+
+template <int BN> struct TfCfg {
+  static constexpr int kABytes = kTM * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kBarOff = kTStages * kStage;
+  static constexpr int kSmem = kBarOff + 64 + 1024;   // + barriers / TMEM slot + alignment slack
+  static constexpr int kWChunks = BN / 32;            // 16-byte chunks of the W tile per thread and k-block
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void st_shared_tf32x4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(to_tf32(v.x)), "r"(to_tf32(v.y)), "r"(to_tf32(v.z)),
+               "r"(to_tf32(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTThreads, 2) gemm_tf32_kernel(const b2u_f32_gemm_params p) {
+  using C = TfCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  int k_lo, k_hi;
+  k_slice(p, static_cast<int>(blockIdx.z), k_lo, k_hi);
+  if (k_lo >= k_hi) return;                            // empty K slice (uniform per CTA): nothing to add
+  const int nkb = (k_hi - k_lo + kTK - 1) / kTK;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + C::kBarOff);   // [kTStages]
+  uint64_t* done_bar = empty_bar + kTStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kTM;
+  const int n0 = static_cast<int>(blockIdx.y) * BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTStages; ++s) mbar_init(&empty_bar[s], 1);
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const Roles R = make_roles(p, tid, m0, n0, BN);      // this thread's A-tile row / W-tile row and chunk runs
+  constexpr int kWC = C::kWChunks;
+  constexpr uint32_t idesc = make_idesc_f16(2 /* TF32 */, kTM, BN);
+
+  float4 ra[4], rw[kWC];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ra[j] = load_a(p, R, k_lo + (R.a_c0 + j) * 4, k_hi);
+#pragma unroll
+  for (int j = 0; j < kWC; ++j) rw[j] = load_w(p, R, k_lo + (R.w_c0 + j) * 4, k_hi);
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % kTStages;
+    if (kb >= kTStages) mbar_wait(&empty_bar[s], static_cast<uint32_t>((kb / kTStages - 1) & 1));   // MMAs of k-block kb - 3 have read the stage
+    const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * C::kStage;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st_shared_tf32x4(sbase + smem_off(R.a_r, R.a_c0 + j), ra[j]);
+#pragma unroll
+    for (int j = 0; j < kWC; ++j) st_shared_tf32x4(sbase + C::kABytes + smem_off(R.w_r, R.w_c0 + j), rw[j]);
+    fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core's async proxy
+    if (kb + 1 < nkb) {                                // next k-block's loads fly across the barrier and the MMA issue
+      const int kn = k_lo + (kb + 1) * kTK;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ra[j] = load_a(p, R, kn + (R.a_c0 + j) * 4, k_hi);
+#pragma unroll
+      for (int j = 0; j < kWC; ++j) rw[j] = load_w(p, R, kn + (R.w_c0 + j) * 4, k_hi);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint64_t da = make_desc_k128(sbase);
+        const uint64_t db = make_desc_k128(sbase + C::kABytes);
+#pragma unroll
+        for (int k = 0; k < kTK / 8; ++k)
+          tc_mma_tf32(tmem_base, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+        tc_commit(&empty_bar[s]);
+        if (kb == nkb - 1) tc_commit(done_bar);        // everything issued so far has completed when this one arrives
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---------------------------------------------------------------- epilogue: thread = accumulator row
+  mbar_wait(done_bar, 0);
+  tc_fence_after();
+  {
+    const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter (fixed by warp % 4), column half
+    constexpr int kCols = BN / 2;
+    const EpiRow e = make_epi_row(p, m0 + q * 32 + lane);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * kCols);
+#pragma unroll 1
+    for (int c0 = 0; c0 < kCols; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + static_cast<uint32_t>(c0), v);   // .sync.aligned: every lane, also rows beyond M
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float acc[4] = {__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])};
+        emit4(p, e, n0 + half * kCols + c0 + g * 4, acc);
+      }
+      __syncwarp();                                      // reconverge before the next warp-collective tcgen05.ld
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN>
+int launch_tf32(const b2u_f32_gemm_params& p, cudaStream_t stream) {
+  auto kern = gemm_tf32_kernel<BN>;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[current_device_index()];
+  constexpr int kSmem = TfCfg<BN>::kSmem;
+  static_assert(kSmem <= 113 * 1024, "two CTAs per SM must fit");
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(gemm_tf32): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long m_tiles = (p.M + kTM - 1) / kTM;
+  if (m_tiles > 0x7fffffffLL) return set_error(-1, "b2u_tf32_gemm: too many row tiles");
+  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>((p.N + BN - 1) / BN), p.ksplit > 1 ? p.ksplit : 1);
+  kern<<<grid, kTThreads, kSmem, stream>>>(p);
+  return check_launch("tf32_gemm");
+}
+
+}  // namespace
+
+extern "C" int b2u_tf32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (const char* why = tf32::validate(p)) return set_error(-1, "b2u_tf32_gemm: %s", why);
+  switch (tf32::pick_bn(p->N)) {
+    case 32: return launch_tf32<32>(*p, stream);
+    case 64: return launch_tf32<64>(*p, stream);
+    default: return launch_tf32<128>(*p, stream);
+  }
+}
+
+}  // namespace b2u

@@ -108,6 +108,7 @@ SIGNATURES = {
     "b2u_seg_head": [vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "b2u_zero": [vp, i64, vp],
     "b2u_f32_gemm": [C.POINTER(F32GemmParams), vp],
+    "b2u_tf32_gemm": [C.POINTER(F32GemmParams), vp],
     "b2u_f32_layernorm": [vp, vp, vp, vp, i64, i32, f32, i32, i32, i32, vp],
     "b2u_f32_patchify": [vp, vp, i32, i32, vp],
     "b2u_f32_nchw_to_nhwc": [vp, vp, i32, i32, i64, vp],

@@ -500,6 +500,10 @@ class DinoUNet(nn.Module):
     #: "16" = the bf16/fp16 tensor-core kernels (default, benchmarked); "fp32" = the fp32 parity tier (plain SIMT kernels,
     #: within 1e-5 of the reference's fp32 forward; set before the first forward or call repack())
     precision = "16"
+    #: matrix products of the TRAINING step's trainable part: "tf32" = tcgen05 tensor cores, TF32-rounded operands, fp32
+    #: accumulation (default; the reference trains under fp16 autocast = the same mantissa); "fp32" = IEEE-fp32 SIMT kernels
+    #: (the tier the gradient goldens are held to at 2e-3)
+    train_gemm = "tf32"
 
     def __init__(self, network_config: dict = None, input_channels: int = None, num_classes: int = None,
                  dinov3_pretrained_path: str = "dinounet/checkpoints/dinov3_vits16_pretrain_lvd1689m-08c60483.pth",
@@ -652,7 +656,7 @@ class DinoUNet(nn.Module):
         with torch.no_grad():
             taps = self._get_engine(x.device).extract_vit_features(x)
         P = self.state_dict(keep_vars=True)
-        return trainable_forward(P, self.dinov3_model_name, x, taps, self.num_classes)
+        return trainable_forward(P, self.dinov3_model_name, x, taps, self.num_classes, getattr(self, "train_gemm", "tf32"))
 
     @torch.no_grad()
     def predict_labels(self, x: torch.Tensor) -> torch.Tensor:

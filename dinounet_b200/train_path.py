@@ -7,10 +7,14 @@ head (289 tensors).  Here:
 
   * the frozen ViT runs on the 16-bit tensor-core engine (`ForwardEngine.extract_vit_features`) or, with
     `vit_precision="fp32"`, on the fp32 tier - no gradient flows into it;
-  * every differentiable operator is a `torch.autograd.Function` whose forward AND backward call hand-written fp32
-    kernels through the C-ABI (csrc/fp32_tier.cu, csrc/train_bwd.cu, msda.cu, loss.cu).  torch.autograd is used as the
-    tape only: what it executes itself is data movement (views, cat, contiguous) and gradient accumulation for tensors
-    with several consumers;
+  * every differentiable operator is a `torch.autograd.Function` whose forward AND backward call hand-written
+    kernels through the C-ABI (csrc/gemm_tf32.cu, csrc/fp32_tier.cu, csrc/train_bwd.cu, msda.cu, loss.cu).  torch.autograd
+    is used as the tape only: what it executes itself is data movement (views, cat, contiguous) and gradient accumulation
+    for tensors with several consumers;
+  * the matrix products (F.linear / Conv2d / ConvTranspose2d: forward, data gradient, weight gradient) have two tiers
+    with ONE parameter block: `gemm="tf32"` (default) = `b2u_tf32_gemm`, tcgen05 tensor cores with TF32-rounded operands
+    and fp32 accumulation (the mantissa of the fp16 autocast the reference trains under); `gemm="fp32"` = `b2u_f32_gemm`,
+    the IEEE-fp32 SIMT kernel the gradient goldens are held to at 2e-3.  Everything else is fp32 in both tiers;
   * semantics = the gradient oracle's (oracle/grad_oracle.py, pinned to autograd through the REAL reference): eval-mode
     BatchNorm (running statistics), DropPath off, fp32.
 
@@ -32,8 +36,13 @@ def _s(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+#: matrix-product tier of the Functions created from now on ("tf32" | "fp32"); `trainable_forward` sets it for the duration
+#: of its forward and every Function remembers it for its backward
+_GEMM_TIER = "tf32"
+
+
 def _gemm(A, W, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, residual=None, conv=0, img=(0, 0, 0), cpad=0,
-          ps=None, a_trans=0, w_mode=0, w_cpad=0, ksplit=0, col_off=0):
+          ps=None, a_trans=0, w_mode=0, w_cpad=0, ksplit=0, col_off=0, tier=None):
     p = L.F32GemmParams()
     p.M, p.N, p.K = int(M), int(N), int(K)
     p.A, p.lda = A.data_ptr(), int(lda if lda is not None else A.shape[-1])
@@ -49,8 +58,9 @@ def _gemm(A, W, out, M, N, K, *, lda=None, ldw=None, ldc=None, bias=None, residu
     if residual is not None:
         p.residual, p.ldres = residual.data_ptr(), int(residual.shape[-1])
     p.a_trans, p.w_mode, p.w_cpad, p.ksplit = int(a_trans), int(w_mode), int(w_cpad), int(ksplit)
+    fn = "b2u_tf32_gemm" if (tier or _GEMM_TIER) == "tf32" else "b2u_f32_gemm"
     with torch.cuda.device(out.device):
-        L.check(L.load().b2u_f32_gemm(C.byref(p), C.c_void_p(_s(out))), "b2u_f32_gemm")
+        L.check(getattr(L.load(), fn)(C.byref(p), C.c_void_p(_s(out))), fn)
 
 
 def _ksplit(rows: int) -> int:
@@ -81,7 +91,7 @@ class LinearF(Function):
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         _gemm(x, W, y, M, N, K, bias=b, residual=residual)
         ctx.save_for_backward(x, W)
-        ctx.has_b, ctx.has_r = b is not None, residual is not None
+        ctx.has_b, ctx.has_r, ctx.tier = b is not None, residual is not None, _GEMM_TIER
         return y
 
     @staticmethod
@@ -92,10 +102,10 @@ class LinearF(Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _gemm(dy, W, dx, M, K, N, w_mode=1)                       # dx[m,k] = sum_n dy[m,n] W[n,k]
+            _gemm(dy, W, dx, M, K, N, w_mode=1, tier=ctx.tier)        # dx[m,k] = sum_n dy[m,n] W[n,k]
         if ctx.needs_input_grad[1]:
             dW = torch.zeros_like(W)
-            _gemm(dy, x, dW, N, K, M, a_trans=1, w_mode=1, ksplit=_ksplit(M))   # dW[n,k] = sum_m dy[m,n] x[m,k]
+            _gemm(dy, x, dW, N, K, M, a_trans=1, w_mode=1, ksplit=_ksplit(M), tier=ctx.tier)   # dW[n,k] = sum_m dy[m,n] x[m,k]
         if ctx.has_b and ctx.needs_input_grad[2]:
             db = _colsum(dy, N)
         return dx, dW, db, (dy if ctx.has_r else None)
@@ -114,7 +124,7 @@ class Conv3x3F(Function):
         _gemm(x, Wp, y, B * Ho * Wo, N, 9 * Cc, bias=b, conv=L.CONV3X3_S2 if stride == 2 else L.CONV3X3_S1, img=(H, Wd, Cc), cpad=Cc)
         ctx.save_for_backward(x, Wp)
         ctx.geo = (B, H, Wd, Cc, N, stride)
-        ctx.has_b = b is not None
+        ctx.has_b, ctx.tier = b is not None, _GEMM_TIER
         return y
 
     @staticmethod
@@ -127,7 +137,8 @@ class Conv3x3F(Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if stride == 1:   # correlation of dy with the flipped, transposed weights: the GEMM kernel's conv data-gradient mode
-                _gemm(dy, Wp, dx, B * H * Wd, Cc, 9 * N, conv=L.CONV3X3_S1, img=(H, Wd, N), cpad=N, w_mode=2, w_cpad=Cc, ldw=9 * Cc)
+                _gemm(dy, Wp, dx, B * H * Wd, Cc, 9 * N, conv=L.CONV3X3_S1, img=(H, Wd, N), cpad=N, w_mode=2, w_cpad=Cc, ldw=9 * Cc,
+                      tier=ctx.tier)
             else:
                 _call("b2u_f32_conv3x3_dgrad", dy, Wp, dx, B, H, Wd, Cc, Cc, N, stride)
         if ctx.needs_input_grad[1]:
@@ -135,7 +146,7 @@ class Conv3x3F(Function):
             dWp = torch.zeros_like(Wp)
             npix = B * Ho * Wo
             _gemm(dy, x, dWp, N, 9 * Cc, npix, a_trans=1, lda=N, w_mode=3, conv=L.CONV3X3_S2 if stride == 2 else L.CONV3X3_S1,
-                  img=(H, Wd, Cc), cpad=Cc, ksplit=max(1, min(256, npix // 4096)))
+                  img=(H, Wd, Cc), cpad=Cc, ksplit=max(1, min(256, npix // 4096)), tier=ctx.tier)
             dW = dWp.view(N, 3, 3, Cc).permute(0, 3, 1, 2).contiguous()
         if ctx.has_b and ctx.needs_input_grad[2]:
             db = _colsum(dy, N)
@@ -154,6 +165,7 @@ class ConvT2x2F(Function):
         _gemm(x, Wp, y, B * h * w, 4 * Cout, Cin, bias=b.repeat(4).contiguous(), ps=(Cout, h, w))
         ctx.save_for_backward(x, Wp)
         ctx.geo = (B, h, w, Cin, Cout)
+        ctx.tier = _GEMM_TIER
         return y
 
     @staticmethod
@@ -167,10 +179,10 @@ class ConvT2x2F(Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _gemm(dyu, Wp, dx, M, Cin, 4 * Cout, w_mode=1)
+            _gemm(dyu, Wp, dx, M, Cin, 4 * Cout, w_mode=1, tier=ctx.tier)
         if ctx.needs_input_grad[1]:
             dWp = torch.zeros_like(Wp)
-            _gemm(dyu, x, dWp, 4 * Cout, Cin, M, a_trans=1, w_mode=1, ksplit=_ksplit(M))
+            _gemm(dyu, x, dWp, 4 * Cout, Cin, M, a_trans=1, w_mode=1, ksplit=_ksplit(M), tier=ctx.tier)
             dW = dWp.view(2, 2, Cout, Cin).permute(3, 2, 0, 1).contiguous()
         if ctx.needs_input_grad[2]:
             db = _colsum(dy, Cout)
@@ -417,9 +429,22 @@ class TailAddF(Function):
 
 
 # ------------------------------------------------------------------------------------------------------------ the network
-def trainable_forward(P: Dict[str, torch.Tensor], variant: str, x: torch.Tensor, taps: List[torch.Tensor], num_classes: int) -> torch.Tensor:
+def trainable_forward(P: Dict[str, torch.Tensor], variant: str, x: torch.Tensor, taps: List[torch.Tensor], num_classes: int,
+                      gemm: str = "tf32") -> torch.Tensor:
     """Differentiable forward of everything outside the frozen backbone.  P: reference-keyed parameters / buffers
-    (`net.state_dict(keep_vars=True)`), x [B,3,S,S] fp32, taps: 4 x [B, P, D] fp32 (frozen ViT outputs) -> logits [B,C,S,S]."""
+    (`net.state_dict(keep_vars=True)`), x [B,3,S,S] fp32, taps: 4 x [B, P, D] fp32 (frozen ViT outputs) -> logits [B,C,S,S].
+    gemm: matrix-product tier, "tf32" (tensor cores) or "fp32" (SIMT parity tier); the backward uses the same tier."""
+    global _GEMM_TIER
+    if gemm not in ("tf32", "fp32"):
+        raise ValueError(f"gemm tier must be 'tf32' or 'fp32', got {gemm!r}")
+    prev, _GEMM_TIER = _GEMM_TIER, gemm
+    try:
+        return _trainable_forward(P, variant, x, taps, num_classes)
+    finally:
+        _GEMM_TIER = prev
+
+
+def _trainable_forward(P, variant, x, taps, num_classes):
     v = cfg.VARIANTS[variant]
     D = v.embed_dim
     B, _, S, _ = x.shape

@@ -311,6 +311,12 @@ typedef struct b2u_f32_gemm_params {
   int32_t a_trans, w_mode, w_cpad, ksplit, accumulate;
 } b2u_f32_gemm_params;
 int b2u_f32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream);   /* F.linear / Conv2d 1x1, 3x3 / ConvTranspose2d k2 s2 */
+/* Same parameter block, addressing modes and epilogue on the tensor cores (csrc/gemm_tf32.cu): operands rounded to TF32
+ * (round-to-nearest, 10 mantissa bits = the fp16 autocast the reference trains under, nnUNetTrainer.py:899-929, with fp32's
+ * exponent range), fp32 accumulation in tensor memory (tcgen05.mma kind::tf32).  The fast tier of the TRAINING step's
+ * matrix products (forward, data gradient, weight gradient of F.linear / Conv2d / ConvTranspose2d); not bit-comparable
+ * with b2u_f32_gemm (about 1e-3 relative per product). */
+int b2u_tf32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream);
 /* F.layer_norm; input row = (r / out_per_b) * in_per_b + in_off + r % out_per_b when in_per_b > 0 (ViT taps drop the prefix) */
 int b2u_f32_layernorm(const float* in, float* out, const float* w, const float* b, int64_t rows, int32_t D, float eps,
                       int32_t in_per_b, int32_t out_per_b, int32_t in_off, b2u_stream_t stream);
