@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--rest-dtype", default="fp16")
     ap.add_argument("--query-dtype", default="fp32", choices=["16", "fp32"],
                     help="adapter query stream storage: fp32 = the reference's dtype (default), 16 = opt-in reduced storage")
+    ap.add_argument("--train-gemm", default="tf32", choices=["tf32", "fp32"],
+                    help="--mode train: matrix products of the trainable part on tcgen05 kind::tf32 (default) or the fp32 SIMT tier")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--gemm-pair", default="on", choices=["on", "off"], help="CTA-pair (cta_group::2) GEMM tiles (A/B switch)")
     ap.add_argument("--pdl", default="off", choices=["on", "off"], help="programmatic dependent launch across the plan (A/B switch; measured slower, default off)")
@@ -231,7 +233,8 @@ def eager_cuda_patches_per_s(model, B, S, steps, warmup, dev):
 def run_train(a):
     """BASELINE.json configs[2]: `dinounet_b random-init, batch 64x512x512x3 synthetic, 1xB200 fwd+bwd (Dice+CE loss)`.
     One step = nnUNetTrainer.train_step: frozen ViT on the 16-bit tensor-core engine, trainable part forward + backward on the
-    fp32 kernels of train_path.py, Dice+CE, (N > 1: one NCCL all-reduce of the gradients), clip + SGD-nesterov."""
+    kernels of train_path.py (matrix products: tcgen05 kind::tf32 by default, --train-gemm fp32 = the SIMT parity tier), Dice+CE,
+    (N > 1: one NCCL all-reduce of the gradients), clip + SGD-nesterov."""
     import torch
     import torch.distributed as dist
     os.environ.setdefault("DINOUNET_B200_ALLOW_RANDOM_BACKBONE", "1")
@@ -250,6 +253,7 @@ def run_train(a):
     sd = O.make_state_dict(a.model, 2, seed=0)
     net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, 2, None, a.model)
     net.load_state_dict(sd, strict=True)
+    net.train_gemm = a.train_gemm
     net = net.to(dev).train()
     crit = DC_and_CE_loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": False}, {}, weight_ce=1, weight_dice=1)
     opt = FusedSGD(net.parameters(), lr=1e-2, weight_decay=3e-5)
@@ -284,20 +288,30 @@ def run_train(a):
         flops = fwd + 2 * (fwd - vit)                       # backward of the trainable (non-ViT) part = 2x its forward
         value = world * B * K / (ms / 1e3)
         pk = peaks()
+        tf32 = a.train_gemm == "tf32"
         print(json.dumps({
             "metric": "2D patches/sec (512x512) fwd+bwd (Dice+CE) + SGD step", "value": value, "unit": "patches/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16/fp16 frozen ViT (tcgen05) + fp32 trainable part (SIMT forward/backward kernels)", "data": "synthetic",
+            "dtype": ("bf16/fp16 frozen ViT (tcgen05) + trainable part: tf32 tensor-core matrix products (tcgen05 kind::tf32, fp32 "
+                      "accumulate), fp32 everything else" if tf32 else
+                      "bf16/fp16 frozen ViT (tcgen05) + fp32 trainable part (SIMT forward/backward kernels)"), "data": "synthetic",
             "impl": "b200", "mode": "train",
             "config": {"workload": f"{a.model} train step, {S}x{S}x3, per-GPU batch {B}, Dice+CE, SGD-nesterov + clip 12",
                        "global_batch": B * world, "l2": "two resident batches alternated; the per-step working set is >> 126 MB L2",
+                       "train_gemm": a.train_gemm,
                        "parallelism": f"dp{world} + 1 NCCL all-reduce of the gradients" if world > 1 else "single GPU"},
             "gpu_launches": K * launches_per_step, "kernels_per_step": launches_per_step, "loss": float(loss),
             "clocks": clk.summary(t0, t1),
-            "roofline": {"bound": "fp32-simt", "achieved": value / world * flops / 1e12, "unit": "TFLOP/s",
-                         "algorithmic_gflop_per_patch": flops / 1e9,
-                         "note": "fp32 FMA peak of a B200 is ~72 TF/s (148 SMs x 128 lanes x 2 x 1.9 GHz); the trainable part runs "
-                                 "on plain fp32 SIMT kernels (gradient parity first), not on tensor cores"},
+            "roofline": ({"bound": "tensor", "achieved": value / world * flops / 1e12, "peak": pk["tflops"] / 2, "unit": "TFLOP/s",
+                          "frac": value / world * flops / 1e12 / (pk["tflops"] / 2), "algorithmic_gflop_per_patch": flops / 1e9,
+                          "peak_source": "half of the measured sustained bf16 peak (TF32 dense = 0.5 x bf16 on B200; no measured TF32 entry)",
+                          "note": "whole step (frozen ViT + trainable forward/backward + loss + SGD) over the algorithmic FLOPs; the "
+                                  "tf32 GEMM's operands go through registers (gathers no tensor map expresses), so it is bound by "
+                                  "L2->SM operand traffic and LSU issue, not by the tensor pipe"} if tf32 else
+                         {"bound": "fp32-simt", "achieved": value / world * flops / 1e12, "unit": "TFLOP/s",
+                          "algorithmic_gflop_per_patch": flops / 1e9,
+                          "note": "fp32 FMA peak of a B200 is ~72 TF/s (148 SMs x 128 lanes x 2 x 1.9 GHz); --train-gemm fp32 runs the "
+                                  "trainable part on plain fp32 SIMT kernels (the gradient-parity tier)"}),
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:
         dist.destroy_process_group()

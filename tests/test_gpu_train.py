@@ -1,5 +1,5 @@
-"""-m gpu: the training path (dinounet_b200/train_path.py: autograd Functions over hand-written fp32 forward / backward
-kernels) against the gradient oracle's goldens (tests/golden/grads_*.npz = autograd through the oracle forward + loss
+"""-m gpu: the training path (dinounet_b200/train_path.py: autograd Functions over hand-written forward / backward
+kernels; matrix products on the fp32 SIMT tier here unless a test says tf32) against the gradient oracle's goldens (tests/golden/grads_*.npz = autograd through the oracle forward + loss
 oracle, itself pinned to autograd through the REAL reference, tests/test_grad_oracle_cpu.py).  BASELINE.json config 3.
 
 Tolerance: fp32 with different summation orders (split-K atomics): loss 1e-5 rel; per-tensor gradient norm 2e-3 rel
@@ -22,11 +22,12 @@ from oracle import grad_oracle as G
 pytestmark = pytest.mark.gpu
 
 
-def _net(model, sd, ncls):
+def _net(model, sd, ncls, gemm="fp32"):
     os.environ["DINOUNET_B200_ALLOW_RANDOM_BACKBONE"] = "1"
     net = dinounet_b200.DinoUNet.from_config({"architecture": dict(config.DEFAULT_ARCHITECTURE)}, 3, ncls, None, model)
     net.load_state_dict(sd, strict=True)
     net.precision = "fp32"          # frozen ViT on the fp32 tier: the goldens are fp32 end to end
+    net.train_gemm = gemm           # "fp32": SIMT matrix products (the 2e-3 bar); "tf32": the tensor-core tier
     return net.to("cuda").train()
 
 
@@ -72,6 +73,50 @@ def test_gradients_match_the_reference_autograd_goldens():
         assert not bad, bad[:8]
         # no gradient reaches the frozen backbone
         assert all(p.grad is None for n, p in net.named_parameters() if n.startswith("encoder.dinov3_adapter.backbone."))
+
+
+def test_tensor_core_tier_gradients_stay_within_tf32_of_the_goldens():
+    """The same goldens through the tcgen05 kind::tf32 matrix products (train_gemm = "tf32", the default of the train step):
+    operands carry 10 mantissa bits like the fp16 autocast the reference trains under, so the bar is TF32's, not fp32's:
+    loss 2e-3, every gradient tensor's norm within 3e-2 (tensors above 1e-4 of the largest), samples within 3e-2 of the
+    tensor's largest sample."""
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "grads_*.npz")))
+    assert files
+    for f in files:
+        model, b, s, c, w = os.path.basename(f)[len("grads_"):-4].rsplit("_", 4)
+        B, S, ncls, seed = int(b[1:]), int(s[1:]), int(c[1:]), int(w[1:])
+        g = np.load(f)
+        sd = O.make_state_dict(model, ncls, seed=seed)
+        x = O.make_input(B, S, seed)
+        target = torch.randint(0, ncls, (B, 1, S, S), generator=torch.Generator().manual_seed(seed + 7)).float()
+        net = _net(model, sd, ncls, gemm="tf32")
+        crit = DC_and_CE_loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": False}, {}, weight_ce=1, weight_dice=1)
+        loss = crit(net(x.cuda()), target.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - float(g["loss"])) <= 2e-3 * max(1.0, abs(float(g["loss"]))), (loss.item(), float(g["loss"]))
+        names = [str(n) for n in g["names"]]
+        params = dict(net.named_parameters())
+        top = float(np.max(g["norms"]))
+        bad, worst_n, worst_s = [], 0.0, 0.0
+        for i, k in enumerate(names):
+            p = params[k] if k in params else net.state_dict(keep_vars=True)[k]
+            want = float(g["norms"][i])
+            if p.grad is None or want <= 1e-4 * top:
+                continue
+            gr = p.grad.detach().float().cpu()
+            assert torch.isfinite(gr).all(), k
+            rel = abs(gr.double().norm().item() - want) / want
+            fl = gr.reshape(-1)
+            samp = fl[:: max(1, fl.numel() // 16)][:16].numpy()
+            ws = g[f"s{i}"]
+            serr = float(np.abs(samp - ws).max() / max(np.abs(ws).max(), 1e-12))
+            worst_n, worst_s = max(worst_n, rel), max(worst_s, serr)
+            if rel > 3e-2 or serr > 3e-2:
+                bad.append((k, rel, serr))
+        print(f"{os.path.basename(f)} [tf32 tier]: loss {loss.item():.6f} (golden {float(g['loss']):.6f}), worst norm rel err {worst_n:.2e}, "
+              f"worst sample err {worst_s:.2e}")
+        assert not bad, bad[:8]
 
 
 def test_fused_sgd_step_matches_torch_sgd():
