@@ -13,11 +13,11 @@
 // (row r of a k-block = 128 B = 32 floats; 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)), so the
 // UMMA descriptors are byte-identical to the 16-bit GEMM's (make_desc_k128; +32 B per K = 8 step).
 //
-// CTA = one 128 x BN output tile of one K slice (grid = m tiles x n tiles x ksplit), 256 threads, 3-stage smem ring:
-//   all threads: wait stage free (tcgen05.commit -> mbarrier) -> st.shared the k-block fetched one iteration earlier ->
-//   fence.proxy.async -> issue the global loads of the NEXT k-block (in flight across the barrier) -> __syncthreads ->
-//   one elected thread issues 4 x tcgen05.mma (M128, N = BN, K8) + commit.  Epilogue: tcgen05.ld, thread = row.
-// 2-3 CTAs per SM (60-96 KB smem, BN TMEM columns each) hide the load latency of one another.
+// CTA = one 128 x BN output tile of one K slice (grid = tiles (n fastest) x ksplit), 256 threads, 3-stage smem ring:
+//   all threads: wait stage free (tcgen05.commit -> mbarrier) -> st.shared the k-block fetched kPF iterations earlier ->
+//   fence.proxy.async -> issue the global loads of k-block kb + kPF into the freed register set (in flight across kPF
+//   barriers) -> __syncthreads -> one elected thread issues 4 x tcgen05.mma (M128, N = BN, K8) + commit.
+// Epilogue: tcgen05.ld, thread = accumulator row.  Two CTAs fit an SM's shared memory (60-96 KB each, BN TMEM columns).
 #include <math.h>
 
 #include "common.cuh"
@@ -30,13 +30,22 @@ namespace {
 
 using namespace tf32;
 
+// A/B knobs (python csrc/build.py with B2U_EXTRA_FLAGS): register prefetch depth in k-blocks, resident CTAs per SM
+#ifndef B2U_TF32_PF
+#define B2U_TF32_PF 1
+#endif
+#ifndef B2U_TF32_MINB
+#define B2U_TF32_MINB 2
+#endif
+constexpr int kPF = B2U_TF32_PF;
+static_assert(kPF >= 1 && kPF <= kTStages, "a k-block is stored into the ring before its register set is refilled");
+
 template <int BN> struct TfCfg {
   static constexpr int kABytes = kTM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStage = kABytes + kBBytes;
   static constexpr int kBarOff = kTStages * kStage;
   static constexpr int kSmem = kBarOff + 64 + 1024;   // + barriers / TMEM slot + alignment slack
-  static constexpr int kWChunks = BN / 32;            // 16-byte chunks of the W tile per thread and k-block
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float v) {
@@ -44,11 +53,14 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return r;
 }
-__device__ __forceinline__ void st_shared_tf32x4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(to_tf32(v.x)), "r"(to_tf32(v.y)), "r"(to_tf32(v.z)),
-               "r"(to_tf32(v.w))
-               : "memory");
-}
+struct SmemPut {            // tf32::stage's sink: round to TF32, one 16-byte shared-memory store
+  uint32_t base;
+  __device__ __forceinline__ void operator()(uint32_t off, float4 v) const {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + off), "r"(to_tf32(v.x)), "r"(to_tf32(v.y)), "r"(to_tf32(v.z)),
+                 "r"(to_tf32(v.w))
+                 : "memory");
+  }
+};
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -61,7 +73,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kTThreads, 2) gemm_tf32_kernel(const b2u_f32_gemm_params p) {
+__global__ void __launch_bounds__(kTThreads, B2U_TF32_MINB) gemm_tf32_kernel(const b2u_f32_gemm_params p) {
   using C = TfCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   int k_lo, k_hi;
@@ -76,8 +88,9 @@ __global__ void __launch_bounds__(kTThreads, 2) gemm_tf32_kernel(const b2u_f32_g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long m0 = static_cast<long long>(blockIdx.x) * kTM;
-  const int n0 = static_cast<int>(blockIdx.y) * BN;
+  long long m0;
+  int n0;
+  tile_origin(p, BN, static_cast<long long>(blockIdx.x), m0, n0);
 
   if (tid == 0) {
     for (int s = 0; s < kTStages; ++s) mbar_init(&empty_bar[s], 1);
@@ -91,44 +104,49 @@ __global__ void __launch_bounds__(kTThreads, 2) gemm_tf32_kernel(const b2u_f32_g
   const uint32_t tmem_base = *tmem_slot;
 
   const Roles R = make_roles(p, tid, m0, n0, BN);      // this thread's A-tile row / W-tile row and chunk runs
-  constexpr int kWC = C::kWChunks;
   constexpr uint32_t idesc = make_idesc_f16(2 /* TF32 */, kTM, BN);
 
-  float4 ra[4], rw[kWC];
+  // kPF register sets: k-block kb lives in set kb % kPF from the moment its loads are issued (kPF iterations ahead) until it
+  // is stored to the ring.  MEASURED (same box, 15 shapes, profiles/r02_tf32_gemm_micro.md): kPF 1 / 2 / 3 at two CTAs per SM
+  // = 32.9 / 37.4 / 42.6 ms in total - deeper prefetch LOSES: the kernel is bound by L2->SM operand bytes (3.7 TB/s at the
+  // 768-wide linears = 32 FLOP per operand byte of a 128 x 128 fp32 tile), not by load latency; default 1.
+  float4 ra[kPF][4], rw[kPF][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) ra[j] = load_a(p, R, k_lo + (R.a_c0 + j) * 4, k_hi);
-#pragma unroll
-  for (int j = 0; j < kWC; ++j) rw[j] = load_w(p, R, k_lo + (R.w_c0 + j) * 4, k_hi);
+  for (int u = 0; u < kPF; ++u) {
+    const int kh = u < nkb ? k_hi : 0;                 // beyond the slice: fetch_* return zeros without touching memory
+    fetch_a(p, R, k_lo + u * kTK, kh, ra[u]);
+    fetch_w(p, R, k_lo + u * kTK, kh, rw[u]);
+  }
 
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % kTStages;
-    if (kb >= kTStages) mbar_wait(&empty_bar[s], static_cast<uint32_t>((kb / kTStages - 1) & 1));   // MMAs of k-block kb - 3 have read the stage
-    const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * C::kStage;
+  for (int kb0 = 0; kb0 < nkb; kb0 += kPF) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) st_shared_tf32x4(sbase + smem_off(R.a_r, R.a_c0 + j), ra[j]);
-#pragma unroll
-    for (int j = 0; j < kWC; ++j) st_shared_tf32x4(sbase + C::kABytes + smem_off(R.w_r, R.w_c0 + j), rw[j]);
-    fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core's async proxy
-    if (kb + 1 < nkb) {                                // next k-block's loads fly across the barrier and the MMA issue
-      const int kn = k_lo + (kb + 1) * kTK;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ra[j] = load_a(p, R, kn + (R.a_c0 + j) * 4, k_hi);
-#pragma unroll
-      for (int j = 0; j < kWC; ++j) rw[j] = load_w(p, R, kn + (R.w_c0 + j) * 4, k_hi);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        tc_fence_after();
-        const uint64_t da = make_desc_k128(sbase);
-        const uint64_t db = make_desc_k128(sbase + C::kABytes);
-#pragma unroll
-        for (int k = 0; k < kTK / 8; ++k)
-          tc_mma_tf32(tmem_base, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-        tc_commit(&empty_bar[s]);
-        if (kb == nkb - 1) tc_commit(done_bar);        // everything issued so far has completed when this one arrives
+    for (int u = 0; u < kPF; ++u) {
+      const int kb = kb0 + u;
+      if (kb >= nkb) break;                            // uniform over the CTA
+      const int s = kb % kTStages;
+      if (kb >= kTStages) mbar_wait(&empty_bar[s], static_cast<uint32_t>((kb / kTStages - 1) & 1));   // MMAs of k-block kb - 3 have read the stage
+      const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * C::kStage;
+      stage(R.a_blk, R.a_r, R.a_c0, 4, ra[u], SmemPut{sbase});
+      stage(R.w_blk, R.w_r, R.w_c0, R.w_n, rw[u], SmemPut{sbase + C::kABytes});
+      fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core's async proxy
+      if (kb + kPF < nkb) {                            // refill this register set: in flight across kPF barriers / MMA issues
+        fetch_a(p, R, k_lo + (kb + kPF) * kTK, k_hi, ra[u]);
+        fetch_w(p, R, k_lo + (kb + kPF) * kTK, k_hi, rw[u]);
       }
-      __syncwarp();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint64_t da = make_desc_k128(sbase);
+          const uint64_t db = make_desc_k128(sbase + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < kTK / 8; ++k)
+            tc_mma_tf32(tmem_base, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+          if (kb == nkb - 1) tc_commit(done_bar);      // everything issued so far has completed when this one arrives
+        }
+        __syncwarp();
+      }
     }
   }
 
@@ -167,15 +185,15 @@ int launch_tf32(const b2u_f32_gemm_params& p, cudaStream_t stream) {
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[current_device_index()];
   constexpr int kSmem = TfCfg<BN>::kSmem;
-  static_assert(kSmem <= 113 * 1024, "two CTAs per SM must fit");
+  static_assert(kSmem <= 113 * 1024, "two CTAs per SM must fit in shared memory");
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return set_error(-2, "cudaFuncSetAttribute(gemm_tf32): %s", cudaGetErrorString(e));
     configured = true;
   }
-  const long long m_tiles = (p.M + kTM - 1) / kTM;
-  if (m_tiles > 0x7fffffffLL) return set_error(-1, "b2u_tf32_gemm: too many row tiles");
-  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>((p.N + BN - 1) / BN), p.ksplit > 1 ? p.ksplit : 1);
+  const long long tiles = ((p.M + kTM - 1) / kTM) * ((p.N + BN - 1) / BN);
+  if (tiles > 0x7fffffffLL) return set_error(-1, "b2u_tf32_gemm: too many output tiles");
+  dim3 grid(static_cast<unsigned>(tiles), 1, p.ksplit > 1 ? p.ksplit : 1);
   kern<<<grid, kTThreads, kSmem, stream>>>(p);
   return check_launch("tf32_gemm");
 }

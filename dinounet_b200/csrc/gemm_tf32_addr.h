@@ -40,16 +40,35 @@ struct Row {              // what one loader thread knows about "its" operand ro
   int tap, c;             // W window mode (w_mode 3): window element of this row
 };
 
-struct Roles {            // loader role of one thread: one A-tile row and one W-tile row, a run of 16-byte chunks in each
+// Loader role of one thread, per operand one of two shapes:
+//   row mode   (operand contiguous along K, or no alignment guarantees): ONE tile row, a run of 16-byte chunks of it
+//              (A: row tid / 2, 4 chunks; W: BN / 32 chunks) - each chunk is 4 consecutive k's, one LDG.128 where allowed;
+//   block mode (operand contiguous along its ROW index: A[k][m], W[k][n], the flipped 3x3 weights, the pixel-indexed window
+//              of a weight gradient): a 4 x 4 block = 4 consecutive rows x one chunk, fetched as four LDG.128 ALONG THE ROWS
+//              (one per k) and transposed in registers into the four 16-byte chunks the K-major tile wants.  Row mode needs
+//              16 scalar loads with 16 address computations for the same 16 elements: the weight-gradient GEMMs were bound
+//              by exactly that integer work (15 TF/s at 1.3 TB/s of L2->SM traffic, profiles/r02_tf32_gemm_micro.md).
+struct Roles {
   int amode, stride, Ho, Wo;
-  int a_r, a_c0;          // A tile: row tid / 2, chunks a_c0 .. a_c0 + 3 of the 8 chunks of a k-block
-  int w_r, w_c0, w_n;     // W tile: BN rows x 8 chunks over 256 threads = w_n = BN / 32 chunks per thread
-  Row ar, wr;
-  bool a_vec, w_vec;      // 16-byte global loads allowed (K-contiguous mode, aligned base and leading dimension)
+  bool a_blk, w_blk;
+  int a_r, a_c0;          // row mode: row tid / 2, chunks a_c0 .. a_c0 + 3; block mode: first row 4 * (tid / 8), chunk tid % 8
+  int w_r, w_c0, w_n;     // row mode: BN / 32 = w_n chunks of one row; block mode: first row, chunk, w_n = 4 loads (0: idle thread)
+  Row ar, wr;             // block mode: the FIRST row of the group
+  bool a_vec, w_vec;      // row mode: 16-byte global loads allowed (K-contiguous, aligned base and leading dimension)
 };
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a K-major SWIZZLE_128B tile whose base is 1024-aligned
 TF_HD uint32_t smem_off(int row, int chunk) { return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4); }
+
+// output tile of linear block index `tile` (grid.x): the n tiles of one row tile are NEIGHBOURS in launch order, so the CTAs
+// that share an A row tile run together and A streams from HBM once (the other order re-read A once per n tile: measured
+// 1.65 TB/s of DRAM traffic on the 768-wide linears); W' (weights, or the small dy^T / x slices of a weight gradient) is
+// L2-resident either way
+TF_HD void tile_origin(const b2u_f32_gemm_params& p, int BN, long long tile, long long& m0, int& n0) {
+  const int n_tiles = (p.N + BN - 1) / BN;
+  m0 = (tile / n_tiles) * kTM;
+  n0 = static_cast<int>(tile % n_tiles) * BN;
+}
 
 // K slice [k_lo, k_hi) of grid.z index z: whole k-blocks, so every chunk of four k's stays 16-byte aligned; may be empty
 TF_HD void k_slice(const b2u_f32_gemm_params& p, int z, int& k_lo, int& k_hi) {
@@ -84,8 +103,14 @@ TF_HD Roles make_roles(const b2u_f32_gemm_params& p, int tid, long long m0, int 
   r.Ho = p.conv ? p.Hin / r.stride : 0;
   r.Wo = p.conv ? p.Win / r.stride : 0;
   r.amode = p.a_trans ? kATrans : ((!p.conv || p.w_mode == 3) ? kAPlain : kAWindow);
-  r.a_r = tid >> 1;
-  r.a_c0 = (tid & 1) * 4;
+  const bool a_al = (reinterpret_cast<uintptr_t>(p.A) & 15) == 0, w_al = (reinterpret_cast<uintptr_t>(p.W) & 15) == 0;
+  // ---- A operand
+  r.a_blk = r.amode == kATrans && a_al && (p.lda & 3) == 0 && (p.M & 3) == 0;
+  // block mode: chunk = tid % 8, row group = tid / 8: the 8 lanes of a shared-memory store phase hold the 8 chunks of ONE row,
+  // which the swizzle spreads over all 32 banks (conflict-free STS.128); a warp-wide load covers 16 consecutive rows (64
+  // contiguous bytes) at 8 different k
+  if (r.a_blk) { r.a_r = 4 * (tid >> 3); r.a_c0 = tid & 7; }
+  else { r.a_r = tid >> 1; r.a_c0 = (tid & 1) * 4; }
   const long long am = m0 + r.a_r;
   r.ar.ok = am < p.M;
   r.ar.idx = am;
@@ -98,15 +123,24 @@ TF_HD Roles make_roles(const b2u_f32_gemm_params& p, int tid, long long m0, int 
     r.ar.cx = rem - r.ar.cy * r.Wo;
   }
   if (r.ar.ok && r.amode == kAPlain && p.a_rows_in > 0) r.ar.idx = (am / p.a_rows_in) * p.a_rows_out + p.a_row_off + am % p.a_rows_in;
-  r.w_n = BN / 32;
-  r.w_r = (tid * r.w_n) >> 3;
-  r.w_c0 = (tid * r.w_n) & 7;
+  // ---- W operand
+  r.w_blk = w_al && ((p.w_mode == 1 && (p.ldw & 3) == 0 && (p.N & 3) == 0) ||
+                     (p.w_mode == 2 && (p.ldw & 3) == 0 && (p.w_cpad & 3) == 0 && (p.N & 3) == 0) ||
+                     (p.w_mode == 3 && (p.Cpad & 3) == 0 && (p.C & 3) == 0));
+  if (r.w_blk) {
+    r.w_r = 4 * (tid >> 3);                          // BN / 4 row groups x 8 chunks = 2 * BN block slots, the other threads idle
+    r.w_c0 = tid & 7;
+    r.w_n = (tid >> 3) < BN / 4 ? 4 : 0;
+  } else {
+    r.w_n = BN / 32;
+    r.w_r = (tid * r.w_n) >> 3;
+    r.w_c0 = (tid * r.w_n) & 7;
+  }
   const int wn = n0 + r.w_r;
   r.wr.ok = wn < p.N;
   r.wr.idx = wn;
   r.wr.cb = r.wr.cy = r.wr.cx = r.wr.tap = r.wr.c = 0;
   if (p.w_mode == 3) { r.wr.tap = wn / p.Cpad; r.wr.c = wn - r.wr.tap * p.Cpad; }
-  const bool a_al = (reinterpret_cast<uintptr_t>(p.A) & 15) == 0, w_al = (reinterpret_cast<uintptr_t>(p.W) & 15) == 0;
   r.a_vec = r.amode == kAPlain ? ((p.lda & 3) == 0 && a_al) : (r.amode == kAWindow && (p.C & 3) == 0 && a_al);
   r.w_vec = p.w_mode == 0 && (p.ldw & 3) == 0 && w_al;
   return r;
@@ -202,6 +236,85 @@ TF_HD float4 load_w(const b2u_f32_gemm_params& p, const Roles& R, int k, int k_h
     v = make_float4(t[0], t[1], t[2], t[3]);
   }
   return v;
+}
+
+TF_HD float4 ldg4(const float* src) { return TF_LDG(reinterpret_cast<const float4*>(src)); }
+
+// this thread's share of the A' k-block that starts at kbase, as up to four float4:
+//   row mode: v[j] = chunk a_c0 + j of the thread's row (four consecutive k's);
+//   block mode: v[i] = rows a_r .. a_r + 3 at k = kbase + 4 * a_c0 + i (four consecutive ROWS: the memory-contiguous direction)
+TF_HD void fetch_a(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int k_hi, float4 (&v)[4]) {
+  if (!R.a_blk) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = load_a(p, R, kbase + (R.a_c0 + j) * 4, k_hi);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = kbase + R.a_c0 * 4 + i;
+    v[i] = (R.ar.ok && k < k_hi) ? ldg4(p.A + static_cast<long long>(k) * p.lda + R.ar.idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+TF_HD void fetch_w(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int k_hi, float4 (&v)[4]) {
+  if (!R.w_blk) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < R.w_n) v[j] = load_w(p, R, kbase + (R.w_c0 + j) * 4, k_hi);
+    return;
+  }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = zero;
+  if (R.w_n == 0 || !R.wr.ok) return;
+  const int k0 = kbase + R.w_c0 * 4;
+  if (p.w_mode == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (k0 + i < k_hi) v[i] = ldg4(p.W + static_cast<long long>(k0 + i) * p.ldw + R.wr.idx);          // W'(n, k) = W[k][n]
+  } else if (p.w_mode == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = k0 + i;
+      if (kk < k_hi) {
+        const int tap = kk / p.Cpad, nn = kk - tap * p.Cpad;                                              // W'(c, (tap', n)) = W[n][(8 - tap') w_cpad + c]
+        if (nn < p.C) v[i] = ldg4(p.W + static_cast<long long>(nn) * p.ldw + (8 - tap) * p.w_cpad + R.wr.idx);
+      }
+    }
+  } else {
+    const int hw = R.Ho * R.Wo;
+    int cb = k0 / hw;
+    const int rem = k0 - cb * hw;
+    int cy = rem / R.Wo, cx = rem - cy * R.Wo;
+    const int dy = R.wr.tap / 3, dx = R.wr.tap - dy * 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (k0 + i < k_hi) {
+        const int iy = cy * R.stride + dy - 1, ix = cx * R.stride + dx - 1;
+        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
+          v[i] = ldg4(p.W + ((static_cast<long long>(cb) * p.Hin + iy) * p.Win + ix) * p.C + R.wr.c);    // channels c .. c + 3 of that pixel
+      }
+      if (++cx == R.Wo) { cx = 0; if (++cy == R.Ho) { cy = 0; ++cb; } }
+    }
+  }
+}
+
+// write the fetched values into the k-block tile: put(byte offset inside the operand's tile, 16 bytes)
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class Put> TF_HD void stage(bool blk, int row, int c0, int n, const float4 (&v)[4], Put put) {
+  if (!blk) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < n) put(smem_off(row, c0 + j), v[j]);
+    return;
+  }
+  if (n == 0) return;
+  put(smem_off(row, c0), make_float4(v[0].x, v[1].x, v[2].x, v[3].x));          // the 4 x 4 register transpose
+  put(smem_off(row + 1, c0), make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
+  put(smem_off(row + 2, c0), make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
+  put(smem_off(row + 3, c0), make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
 }
 
 struct EpiRow {           // epilogue state of one thread = one accumulator row

@@ -24,10 +24,13 @@ static float round_tf32(float v) {   // cvt.rna.tf32.f32
   return v;
 }
 
-static void put4(uint8_t* tile, uint32_t off, float4 v) {
-  const float t[4] = {round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)};
-  memcpy(tile + off, t, 16);
-}
+struct HostPut {             // tf32::stage's sink on the host: round to TF32, 16 bytes into the modelled shared memory
+  uint8_t* tile;
+  void operator()(uint32_t off, float4 v) const {
+    const float t[4] = {round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)};
+    memcpy(tile + off, t, 16);
+  }
+};
 
 // element (row, k) of a K-major SWIZZLE_128B tile with a 1024-byte aligned base, as the tensor core addresses it
 static float get(const uint8_t* tile, int row, int k) {
@@ -38,32 +41,43 @@ static float get(const uint8_t* tile, int row, int k) {
   return v;
 }
 
+static int g_modes = 0;   // bit 0 / 1: A / W operand staged in row mode, bit 2 / 3: in block mode (since the last reset)
+extern "C" int tf32_hostsim_modes(int reset) {
+  const int m = g_modes;
+  if (reset) g_modes = 0;
+  return m;
+}
+
 extern "C" const char* tf32_hostsim_gemm(const b2u_f32_gemm_params* pp) {
   if (const char* why = validate(pp)) return why;
   const b2u_f32_gemm_params& p = *pp;
   const int BN = pick_bn(p.N);
-  const long long m_tiles = (p.M + kTM - 1) / kTM;
-  const int n_tiles = (p.N + BN - 1) / BN, nz = p.ksplit > 1 ? p.ksplit : 1;
+  const long long tiles = ((p.M + kTM - 1) / kTM) * ((p.N + BN - 1) / BN);
+  const int nz = p.ksplit > 1 ? p.ksplit : 1;
   const int a_bytes = kTM * 128, w_bytes = BN * 128;
   std::vector<uint8_t> tile(a_bytes + w_bytes);
   std::vector<double> acc(static_cast<size_t>(kTM) * BN);
   for (int bz = 0; bz < nz; ++bz)
-    for (int by = 0; by < n_tiles; ++by)
-      for (long long bx = 0; bx < m_tiles; ++bx) {
+      for (long long bx = 0; bx < tiles; ++bx) {
         int k_lo, k_hi;
         k_slice(p, bz, k_lo, k_hi);
         if (k_lo >= k_hi) continue;
         const int nkb = (k_hi - k_lo + kTK - 1) / kTK;
-        const long long m0 = bx * kTM;
-        const int n0 = by * BN;
+        long long m0;
+        int n0;
+        tile_origin(p, BN, bx, m0, n0);
         std::fill(acc.begin(), acc.end(), 0.0);
         for (int kb = 0; kb < nkb; ++kb) {
           memset(tile.data(), 0xff, tile.size());                 // NaN pattern: an unwritten chunk poisons the tile
           const int k0 = k_lo + kb * kTK;
           for (int tid = 0; tid < kTThreads; ++tid) {
             const Roles R = make_roles(p, tid, m0, n0, BN);
-            for (int j = 0; j < 4; ++j) put4(tile.data(), smem_off(R.a_r, R.a_c0 + j), load_a(p, R, k0 + (R.a_c0 + j) * 4, k_hi));
-            for (int j = 0; j < R.w_n; ++j) put4(tile.data() + a_bytes, smem_off(R.w_r, R.w_c0 + j), load_w(p, R, k0 + (R.w_c0 + j) * 4, k_hi));
+            g_modes |= (R.a_blk ? 4 : 1) | (R.w_blk ? 8 : 2);
+            float4 va[4], vw[4];
+            fetch_a(p, R, k0, k_hi, va);
+            fetch_w(p, R, k0, k_hi, vw);
+            stage(R.a_blk, R.a_r, R.a_c0, 4, va, HostPut{tile.data()});
+            stage(R.w_blk, R.w_r, R.w_c0, R.w_n, vw, HostPut{tile.data() + a_bytes});
           }
           for (int r = 0; r < kTM; ++r)
             for (int n = 0; n < BN; ++n) {

@@ -35,6 +35,7 @@ def hostsim():
             setattr(p, k, v.data_ptr() if isinstance(v, torch.Tensor) else int(v))
         why = lib.tf32_hostsim_gemm(C.byref(p))
         assert why is None, why
+    raw_gemm.modes = lambda reset=1: lib.tf32_hostsim_modes(reset)
     return raw_gemm
 
 
@@ -43,6 +44,7 @@ def test_kernel_addressing_on_the_host_model_all_modes(hostsim, monkeypatch):
     monkeypatch.setattr(G, "raw_gemm", hostsim)
     monkeypatch.setattr(G, "TOL", 1e-5)
     ran = 0
+    hostsim.modes()
     for fn in (G.test_plain_rows_bias_activation_residual, G.test_unaligned_leading_dimensions_take_the_scalar_paths,
                G.test_transposed_operands_and_split_k, G.test_conv3x3_forward_data_gradient_weight_gradient,
                G.test_pixel_shuffle_and_row_remap_epilogues):
@@ -50,6 +52,7 @@ def test_kernel_addressing_on_the_host_model_all_modes(hostsim, monkeypatch):
             fn(**kw)
             ran += 1
     assert ran >= 20
+    assert hostsim.modes() == 15, "row AND block staging of both operands must have been exercised"
 
 
 def test_host_model_rejects_what_the_entry_point_rejects(hostsim):
