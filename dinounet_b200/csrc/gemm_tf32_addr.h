@@ -291,7 +291,7 @@ TF_HD void fetch_w(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int 
     for (int i = 0; i < 4; ++i) {
       if (k0 + i < k_hi) {
         const int iy = cy * R.stride + dy - 1, ix = cx * R.stride + dx - 1;
-        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
+        if (R.wr.c < p.C && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)                               // c >= C: channel padding rows
           v[i] = ldg4(p.W + ((static_cast<long long>(cb) * p.Hin + iy) * p.Win + ix) * p.C + R.wr.c);    // channels c .. c + 3 of that pixel
       }
       if (++cx == R.Wo) { cx = 0; if (++cy == R.Ho) { cy = 0; ++cb; } }

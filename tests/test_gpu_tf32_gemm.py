@@ -138,6 +138,26 @@ def test_conv3x3_forward_data_gradient_weight_gradient(B, H, Wd, Cin, Cout, stri
         check(dWp, rdW, what=f"conv weight gradient ksplit {ksplit}")
 
 
+def test_conv3x3_channel_padding_rows_are_zero():
+    """Cpad > C (k = tap * Cpad + c with padded weight columns): forward ignores the padding, the weight gradient writes 0 there."""
+    B, H, Wd, Cin, Cpad, Cout = 2, 16, 24, 20, 24, 12
+    x, Wt, dy = rnd(B * H * Wd, Cin, seed=1), rnd(Cout, Cin, 3, 3, seed=2, scale=0.2), rnd(B * H * Wd, Cout, seed=3)
+    Wp = torch.zeros((Cout, 9, Cpad), device=DEV)
+    Wp[:, :, :Cin] = Wt.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    Wp = Wp.reshape(Cout, 9 * Cpad).contiguous()
+    y = torch.full((B * H * Wd, Cout), float("nan"), device=DEV)
+    gemm(x, Wp, y, B * H * Wd, Cout, 9 * Cpad, conv=L.CONV3X3_S1, Hin=H, Win=Wd, C=Cin, Cpad=Cpad)
+    xi = tf32(x).view(B, H, Wd, Cin).permute(0, 3, 1, 2)
+    check(y, F.conv2d(xi, tf32(Wt), None, padding=1).permute(0, 2, 3, 1).reshape(B * H * Wd, Cout), what="padded forward")
+    dWp = torch.zeros((Cout, 9 * Cpad), device=DEV)
+    gemm(dy, x, dWp, Cout, 9 * Cpad, B * H * Wd, a_trans=1, lda=Cout, w_mode=3, conv=L.CONV3X3_S1, Hin=H, Win=Wd, C=Cin, Cpad=Cpad, ksplit=3)
+    dyi = tf32(dy).view(B, H, Wd, Cout).permute(0, 3, 1, 2)
+    rdW = torch.nn.grad.conv2d_weight(xi, (Cout, Cin, 3, 3), dyi, padding=1).permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    got = dWp.view(Cout, 9, Cpad)
+    check(got[:, :, :Cin], rdW, what="padded weight gradient")
+    assert (got[:, :, Cin:] == 0).all()
+
+
 def test_pixel_shuffle_and_row_remap_epilogues():
     """ConvTranspose2d(k2, s2) = GEMM + 2x2 pixel shuffle (ps_*); row remaps on both sides (a_rows_*, rows_*)."""
     B, h, w, Cin, Cout = 2, 12, 20, 48, 24

@@ -46,7 +46,7 @@ def test_kernel_addressing_on_the_host_model_all_modes(hostsim, monkeypatch):
     ran = 0
     hostsim.modes()
     for fn in (G.test_plain_rows_bias_activation_residual, G.test_unaligned_leading_dimensions_take_the_scalar_paths,
-               G.test_transposed_operands_and_split_k, G.test_conv3x3_forward_data_gradient_weight_gradient,
+               G.test_transposed_operands_and_split_k, G.test_conv3x3_forward_data_gradient_weight_gradient, G.test_conv3x3_channel_padding_rows_are_zero,
                G.test_pixel_shuffle_and_row_remap_epilogues):
         for kw in _cases(fn):
             fn(**kw)

@@ -106,7 +106,7 @@ def test_reference_formulas_of_the_gpu_test_agree_with_the_parameter_block_seman
     monkeypatch.setattr(G, "TOL", 1e-5)
     ran = 0
     for fn in (G.test_plain_rows_bias_activation_residual, G.test_unaligned_leading_dimensions_take_the_scalar_paths,
-               G.test_transposed_operands_and_split_k, G.test_conv3x3_forward_data_gradient_weight_gradient,
+               G.test_transposed_operands_and_split_k, G.test_conv3x3_forward_data_gradient_weight_gradient, G.test_conv3x3_channel_padding_rows_are_zero,
                G.test_pixel_shuffle_and_row_remap_epilogues):
         for kw in _cases(fn):
             if kw.get("M", 0) * kw.get("N", 0) * kw.get("K", 0) > 2e9:      # keep the CPU suite short
