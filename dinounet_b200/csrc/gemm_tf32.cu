@@ -72,7 +72,9 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
-template <int BN>
+// ABLK / WBLK: staging shape of the two operands (tf32::pick_modes), compile-time so that each instantiation carries only
+// its own loader (a runtime switch cost the row-mode shapes 6-15 %)
+template <int BN, bool ABLK, bool WBLK>
 __global__ void __launch_bounds__(kTThreads, B2U_TF32_MINB) gemm_tf32_kernel(const b2u_f32_gemm_params p) {
   using C = TfCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -103,7 +105,8 @@ __global__ void __launch_bounds__(kTThreads, B2U_TF32_MINB) gemm_tf32_kernel(con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const Roles R = make_roles(p, tid, m0, n0, BN);      // this thread's A-tile row / W-tile row and chunk runs
+  const Roles R = make_roles(p, tid, m0, n0, BN, ABLK, WBLK);   // this thread's rows / chunks of the two operand tiles
+  constexpr int kWN = BN / 32;
   constexpr uint32_t idesc = make_idesc_f16(2 /* TF32 */, kTM, BN);
 
   // kPF register sets: k-block kb lives in set kb % kPF from the moment its loads are issued (kPF iterations ahead) until it
@@ -114,8 +117,8 @@ __global__ void __launch_bounds__(kTThreads, B2U_TF32_MINB) gemm_tf32_kernel(con
 #pragma unroll
   for (int u = 0; u < kPF; ++u) {
     const int kh = u < nkb ? k_hi : 0;                 // beyond the slice: fetch_* return zeros without touching memory
-    fetch_a(p, R, k_lo + u * kTK, kh, ra[u]);
-    fetch_w(p, R, k_lo + u * kTK, kh, rw[u]);
+    fetch_a<ABLK>(p, R, k_lo + u * kTK, kh, ra[u]);
+    fetch_w<WBLK, kWN>(p, R, k_lo + u * kTK, kh, rw[u]);
   }
 
   for (int kb0 = 0; kb0 < nkb; kb0 += kPF) {
@@ -126,12 +129,12 @@ __global__ void __launch_bounds__(kTThreads, B2U_TF32_MINB) gemm_tf32_kernel(con
       const int s = kb % kTStages;
       if (kb >= kTStages) mbar_wait(&empty_bar[s], static_cast<uint32_t>((kb / kTStages - 1) & 1));   // MMAs of k-block kb - 3 have read the stage
       const uint32_t sbase = smem_base + static_cast<uint32_t>(s) * C::kStage;
-      stage(R.a_blk, R.a_r, R.a_c0, 4, ra[u], SmemPut{sbase});
-      stage(R.w_blk, R.w_r, R.w_c0, R.w_n, rw[u], SmemPut{sbase + C::kABytes});
+      stage<ABLK, 4>(R.a_r, R.a_c0, true, ra[u], SmemPut{sbase});
+      stage<WBLK, kWN>(R.w_r, R.w_c0, R.w_n != 0, rw[u], SmemPut{sbase + C::kABytes});
       fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core's async proxy
       if (kb + kPF < nkb) {                            // refill this register set: in flight across kPF barriers / MMA issues
-        fetch_a(p, R, k_lo + (kb + kPF) * kTK, k_hi, ra[u]);
-        fetch_w(p, R, k_lo + (kb + kPF) * kTK, k_hi, rw[u]);
+        fetch_a<ABLK>(p, R, k_lo + (kb + kPF) * kTK, k_hi, ra[u]);
+        fetch_w<WBLK, kWN>(p, R, k_lo + (kb + kPF) * kTK, k_hi, rw[u]);
       }
       __syncthreads();
       if (warp == 0) {
@@ -179,9 +182,9 @@ __global__ void __launch_bounds__(kTThreads, B2U_TF32_MINB) gemm_tf32_kernel(con
   }
 }
 
-template <int BN>
+template <int BN, bool ABLK, bool WBLK>
 int launch_tf32(const b2u_f32_gemm_params& p, cudaStream_t stream) {
-  auto kern = gemm_tf32_kernel<BN>;
+  auto kern = gemm_tf32_kernel<BN, ABLK, WBLK>;
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[current_device_index()];
   constexpr int kSmem = TfCfg<BN>::kSmem;
@@ -203,10 +206,19 @@ int launch_tf32(const b2u_f32_gemm_params& p, cudaStream_t stream) {
 extern "C" int b2u_tf32_gemm(const b2u_f32_gemm_params* p, b2u_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (const char* why = tf32::validate(p)) return set_error(-1, "b2u_tf32_gemm: %s", why);
-  switch (tf32::pick_bn(p->N)) {
-    case 32: return launch_tf32<32>(*p, stream);
-    case 64: return launch_tf32<64>(*p, stream);
-    default: return launch_tf32<128>(*p, stream);
+  bool a_blk, w_blk;
+  tf32::pick_modes(*p, a_blk, w_blk);
+  const int mode = a_blk ? 2 : (w_blk ? 1 : 0);        // a_blk implies w_blk
+  switch (tf32::pick_bn(p->N) + mode) {
+    case 32: return launch_tf32<32, false, false>(*p, stream);
+    case 33: return launch_tf32<32, false, true>(*p, stream);
+    case 34: return launch_tf32<32, true, true>(*p, stream);
+    case 64: return launch_tf32<64, false, false>(*p, stream);
+    case 65: return launch_tf32<64, false, true>(*p, stream);
+    case 66: return launch_tf32<64, true, true>(*p, stream);
+    case 128: return launch_tf32<128, false, false>(*p, stream);
+    case 129: return launch_tf32<128, false, true>(*p, stream);
+    default: return launch_tf32<128, true, true>(*p, stream);
   }
 }
 

@@ -97,19 +97,32 @@ TF_HD float window(const float* img, int Hin, int Win, int Cc, int stride, int c
   return 0.f;
 }
 
-TF_HD Roles make_roles(const b2u_f32_gemm_params& p, int tid, long long m0, int n0, int BN) {
+// Which staging shape each operand gets.  Block mode needs the row-contiguous addressing AND 16-byte alignment of every row
+// group; it is used for the CONVOLUTION gradients only (weight gradient: both operands; data gradient: the flipped weights):
+// measured on B200 (profiles/r02_tf32_gemm_micro.md) it doubles the 3x3 weight gradients (4.9 -> 2.6 ms at 512^2 64->32,
+// B = 8) and speeds up the data gradients by 7-30 %, while the plain linears' transposed operands (small, L2-resident
+// weight / dy^T slices) ran 10-30 % slower in block mode than with scalar row-mode loads.
+TF_HD void pick_modes(const b2u_f32_gemm_params& p, bool& a_blk, bool& w_blk) {
+  const bool a_al = (reinterpret_cast<uintptr_t>(p.A) & 15) == 0, w_al = (reinterpret_cast<uintptr_t>(p.W) & 15) == 0;
+  w_blk = p.conv != 0 && w_al &&
+          ((p.w_mode == 2 && (p.ldw & 3) == 0 && (p.w_cpad & 3) == 0 && (p.N & 3) == 0) || (p.w_mode == 3 && (p.Cpad & 3) == 0 && (p.C & 3) == 0));
+  a_blk = w_blk && p.a_trans && a_al && (p.lda & 3) == 0 && (p.M & 3) == 0;
+}
+
+TF_HD Roles make_roles(const b2u_f32_gemm_params& p, int tid, long long m0, int n0, int BN, bool a_blk, bool w_blk) {
   Roles r;
   r.stride = p.conv == B2U_CONV3X3_S2 ? 2 : 1;
   r.Ho = p.conv ? p.Hin / r.stride : 0;
   r.Wo = p.conv ? p.Win / r.stride : 0;
   r.amode = p.a_trans ? kATrans : ((!p.conv || p.w_mode == 3) ? kAPlain : kAWindow);
   const bool a_al = (reinterpret_cast<uintptr_t>(p.A) & 15) == 0, w_al = (reinterpret_cast<uintptr_t>(p.W) & 15) == 0;
+  r.a_blk = a_blk;
+  r.w_blk = w_blk;
   // ---- A operand
-  r.a_blk = r.amode == kATrans && a_al && (p.lda & 3) == 0 && (p.M & 3) == 0;
   // block mode: chunk = tid % 8, row group = tid / 8: the 8 lanes of a shared-memory store phase hold the 8 chunks of ONE row,
   // which the swizzle spreads over all 32 banks (conflict-free STS.128); a warp-wide load covers 16 consecutive rows (64
   // contiguous bytes) at 8 different k
-  if (r.a_blk) { r.a_r = 4 * (tid >> 3); r.a_c0 = tid & 7; }
+  if (a_blk) { r.a_r = 4 * (tid >> 3); r.a_c0 = tid & 7; }
   else { r.a_r = tid >> 1; r.a_c0 = (tid & 1) * 4; }
   const long long am = m0 + r.a_r;
   r.ar.ok = am < p.M;
@@ -124,10 +137,7 @@ TF_HD Roles make_roles(const b2u_f32_gemm_params& p, int tid, long long m0, int 
   }
   if (r.ar.ok && r.amode == kAPlain && p.a_rows_in > 0) r.ar.idx = (am / p.a_rows_in) * p.a_rows_out + p.a_row_off + am % p.a_rows_in;
   // ---- W operand
-  r.w_blk = w_al && ((p.w_mode == 1 && (p.ldw & 3) == 0 && (p.N & 3) == 0) ||
-                     (p.w_mode == 2 && (p.ldw & 3) == 0 && (p.w_cpad & 3) == 0 && (p.N & 3) == 0) ||
-                     (p.w_mode == 3 && (p.Cpad & 3) == 0 && (p.C & 3) == 0));
-  if (r.w_blk) {
+  if (w_blk) {
     r.w_r = 4 * (tid >> 3);                          // BN / 4 row groups x 8 chunks = 2 * BN block slots, the other threads idle
     r.w_c0 = tid & 7;
     r.w_n = (tid >> 3) < BN / 4 ? 4 : 0;
@@ -139,7 +149,9 @@ TF_HD Roles make_roles(const b2u_f32_gemm_params& p, int tid, long long m0, int 
   const int wn = n0 + r.w_r;
   r.wr.ok = wn < p.N;
   r.wr.idx = wn;
-  r.wr.cb = r.wr.cy = r.wr.cx = r.wr.tap = r.wr.c = 0;
+  r.wr.cb = r.wr.cy = r.wr.cx = 0;
+  r.wr.tap = 0;
+  r.wr.c = 0;
   if (p.w_mode == 3) { r.wr.tap = wn / p.Cpad; r.wr.c = wn - r.wr.tap * p.Cpad; }
   r.a_vec = r.amode == kAPlain ? ((p.lda & 3) == 0 && a_al) : (r.amode == kAWindow && (p.C & 3) == 0 && a_al);
   r.w_vec = p.w_mode == 0 && (p.ldw & 3) == 0 && w_al;
@@ -243,24 +255,24 @@ TF_HD float4 ldg4(const float* src) { return TF_LDG(reinterpret_cast<const float
 // this thread's share of the A' k-block that starts at kbase, as up to four float4:
 //   row mode: v[j] = chunk a_c0 + j of the thread's row (four consecutive k's);
 //   block mode: v[i] = rows a_r .. a_r + 3 at k = kbase + 4 * a_c0 + i (four consecutive ROWS: the memory-contiguous direction)
-TF_HD void fetch_a(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int k_hi, float4 (&v)[4]) {
-  if (!R.a_blk) {
+template <bool BLK> TF_HD void fetch_a(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int k_hi, float4 (&v)[4]) {
+  if constexpr (!BLK) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = load_a(p, R, kbase + (R.a_c0 + j) * 4, k_hi);
-    return;
-  }
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = kbase + R.a_c0 * 4 + i;
-    v[i] = (R.ar.ok && k < k_hi) ? ldg4(p.A + static_cast<long long>(k) * p.lda + R.ar.idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) {
+      const int k = kbase + R.a_c0 * 4 + i;
+      v[i] = (R.ar.ok && k < k_hi) ? ldg4(p.A + static_cast<long long>(k) * p.lda + R.ar.idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
-TF_HD void fetch_w(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int k_hi, float4 (&v)[4]) {
-  if (!R.w_blk) {
+// WN: float4 per thread in row mode (BN / 32, a compile-time constant in the kernel)
+template <bool BLK, int WN> TF_HD void fetch_w(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int k_hi, float4 (&v)[4]) {
+  if constexpr (!BLK) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < R.w_n) v[j] = load_w(p, R, kbase + (R.w_c0 + j) * 4, k_hi);
+    for (int j = 0; j < WN; ++j) v[j] = load_w(p, R, kbase + (R.w_c0 + j) * 4, k_hi);
     return;
   }
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -303,14 +315,14 @@ TF_HD void fetch_w(const b2u_f32_gemm_params& p, const Roles& R, int kbase, int 
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
-template <class Put> TF_HD void stage(bool blk, int row, int c0, int n, const float4 (&v)[4], Put put) {
-  if (!blk) {
+// row mode: N chunks of one row (compile-time); block mode: `active` threads write the 4 x 4 transpose
+template <bool BLK, int N, class Put> TF_HD void stage(int row, int c0, bool active, const float4 (&v)[4], Put put) {
+  if constexpr (!BLK) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < n) put(smem_off(row, c0 + j), v[j]);
+    for (int j = 0; j < N; ++j) put(smem_off(row, c0 + j), v[j]);
     return;
   }
-  if (n == 0) return;
+  if (!active) return;
   put(smem_off(row, c0), make_float4(v[0].x, v[1].x, v[2].x, v[3].x));          // the 4 x 4 register transpose
   put(smem_off(row + 1, c0), make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
   put(smem_off(row + 2, c0), make_float4(v[0].z, v[1].z, v[2].z, v[3].z));

@@ -48,10 +48,28 @@ extern "C" int tf32_hostsim_modes(int reset) {
   return m;
 }
 
+template <int BN, bool ABLK, bool WBLK> static void run(const b2u_f32_gemm_params& p);
+
 extern "C" const char* tf32_hostsim_gemm(const b2u_f32_gemm_params* pp) {
   if (const char* why = validate(pp)) return why;
-  const b2u_f32_gemm_params& p = *pp;
-  const int BN = pick_bn(p.N);
+  bool a_blk, w_blk;
+  pick_modes(*pp, a_blk, w_blk);
+  const int mode = a_blk ? 2 : (w_blk ? 1 : 0);        // the same dispatch as b2u_tf32_gemm
+  switch (pick_bn(pp->N) + mode) {
+    case 32: run<32, false, false>(*pp); break;
+    case 33: run<32, false, true>(*pp); break;
+    case 34: run<32, true, true>(*pp); break;
+    case 64: run<64, false, false>(*pp); break;
+    case 65: run<64, false, true>(*pp); break;
+    case 66: run<64, true, true>(*pp); break;
+    case 128: run<128, false, false>(*pp); break;
+    case 129: run<128, false, true>(*pp); break;
+    default: run<128, true, true>(*pp); break;
+  }
+  return nullptr;
+}
+
+template <int BN, bool ABLK, bool WBLK> static void run(const b2u_f32_gemm_params& p) {
   const long long tiles = ((p.M + kTM - 1) / kTM) * ((p.N + BN - 1) / BN);
   const int nz = p.ksplit > 1 ? p.ksplit : 1;
   const int a_bytes = kTM * 128, w_bytes = BN * 128;
@@ -71,13 +89,13 @@ extern "C" const char* tf32_hostsim_gemm(const b2u_f32_gemm_params* pp) {
           memset(tile.data(), 0xff, tile.size());                 // NaN pattern: an unwritten chunk poisons the tile
           const int k0 = k_lo + kb * kTK;
           for (int tid = 0; tid < kTThreads; ++tid) {
-            const Roles R = make_roles(p, tid, m0, n0, BN);
+            const Roles R = make_roles(p, tid, m0, n0, BN, ABLK, WBLK);
             g_modes |= (R.a_blk ? 4 : 1) | (R.w_blk ? 8 : 2);
             float4 va[4], vw[4];
-            fetch_a(p, R, k0, k_hi, va);
-            fetch_w(p, R, k0, k_hi, vw);
-            stage(R.a_blk, R.a_r, R.a_c0, 4, va, HostPut{tile.data()});
-            stage(R.w_blk, R.w_r, R.w_c0, R.w_n, vw, HostPut{tile.data() + a_bytes});
+            fetch_a<ABLK>(p, R, k0, k_hi, va);
+            fetch_w<WBLK, BN / 32>(p, R, k0, k_hi, vw);
+            stage<ABLK, 4>(R.a_r, R.a_c0, true, va, HostPut{tile.data()});
+            stage<WBLK, BN / 32>(R.w_r, R.w_c0, R.w_n != 0, vw, HostPut{tile.data() + a_bytes});
           }
           for (int r = 0; r < kTM; ++r)
             for (int n = 0; n < BN; ++n) {
@@ -101,5 +119,4 @@ extern "C" const char* tf32_hostsim_gemm(const b2u_f32_gemm_params* pp) {
               }
           }
       }
-  return nullptr;
 }
