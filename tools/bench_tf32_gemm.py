@@ -1,6 +1,6 @@
 """Microbenchmark: the training path's matrix products on both tiers (b2u_tf32_gemm = tcgen05 kind::tf32, b2u_f32_gemm =
 fp32 SIMT) at the shapes that dominate the dinounet_b train step.  CUDA events, 1 warm-up + 3 timed launches each.
-usage: python tools/bench_tf32_gemm.py [B]   (B = images for the conv shapes, default 8)"""
+usage: python tools/bench_tf32_gemm.py [B] [tiers]   (B = images for the conv shapes, default 8; tiers = "tf32,fp32")"""
 import json
 import os
 import sys
@@ -26,16 +26,18 @@ def timeit(fn, reps=3):
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    tiers = tuple(sys.argv[2].split(",")) if len(sys.argv) > 2 else ("tf32", "fp32")
     dev = "cuda"
     rows = []
 
     def run(name, flops, call):
         r = {"shape": name, "gflop": flops / 1e9}
-        for tier in ("tf32", "fp32"):
+        for tier in tiers:
             ms = timeit(lambda: call(tier))
             r[tier + "_ms"] = round(ms, 3)
             r[tier + "_tflops"] = round(flops / ms / 1e9, 1)
-        r["speedup"] = round(r["fp32_ms"] / r["tf32_ms"], 2)
+        if "fp32_ms" in r and "tf32_ms" in r:
+            r["speedup"] = round(r["fp32_ms"] / r["tf32_ms"], 2)
         rows.append(r)
         print(json.dumps(r), flush=True)
 
