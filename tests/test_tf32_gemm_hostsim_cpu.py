@@ -7,6 +7,7 @@ bodies of tests/test_gpu_tf32_gemm.py (all modes, tails, split-K, remaps) run ag
 the GPU run is the tcgen05 / mbarrier plumbing, not the arithmetic of addresses."""
 import ctypes as C
 import os
+import shutil
 import subprocess
 import tempfile
 
@@ -22,6 +23,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture(scope="module")
 def hostsim():
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/vector_types.h"):
+        pytest.skip("host model needs g++ and the CUDA headers (vector_types.h)")
     src = os.path.join(HERE, "native", "tf32_hostsim.cpp")
     out = os.path.join(tempfile.mkdtemp(prefix="b2u_hostsim_"), "tf32_hostsim.so")
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include", src, "-o", out], check=True)
