@@ -633,7 +633,7 @@ class DinoUNet(nn.Module):
                                       "(DinoUNetTrainer derives from nnUNetTrainerNoDeepSupervision)")
         if torch.is_grad_enabled() and self.training:
             # training step (nnUNetTrainer.py:899-929): frozen ViT on the engine, everything else differentiable through the
-            # autograd Functions of train_path.py (forward and backward on hand-written fp32 kernels).  Semantics of the
+            # autograd Functions of train_path.py (forward and backward on hand-written kernels; `train_gemm` picks the matrix-product tier).  Semantics of the
             # gradient oracle: BatchNorm uses running statistics and DropPath is off in BOTH module modes (the reference's
             # train-mode stochasticity of the frozen ViT, SURVEY.md fact 8, is deliberately not reproduced).
             return self.train_forward(x)
