@@ -1,3 +1,4 @@
+# ncu --set full of three tf32 GEMM launches (report kept in /tmp on the box; only the exported pages + a small .ncu-rep come back)
 mkdir -p gpurun_out
 rm -f gpurun_out/h_rc.txt
 timeout 85 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 3 -c 3 -o /tmp/tf32_full python tools/ncu_tf32_three.py > gpurun_out/h_ncu_full.log 2>&1; echo "rc ncufull $?" >> gpurun_out/h_rc.txt
