@@ -8,8 +8,9 @@
 //
 // Why register-path loaders instead of TMA: five of the eight operand modes are gathers that no tensor map expresses
 // without a transposed copy in HBM (A[k][m], W[k][n], flipped 3x3 weights, the per-pixel window with K = pixel index).
-// Every mode is therefore loaded with ordinary (vector where the mode is K-contiguous) global loads, rounded to TF32
-// in registers and written to shared memory in exactly the layout a SWIZZLE_128B K-major tensor map would produce
+// Every mode is therefore loaded with ordinary global loads - 16-byte ones where the mode is K-contiguous; for the
+// convolution gradients' row-contiguous operands 4 x 4 blocks (four LDG.128 along the rows, transposed in registers:
+// tf32::Roles in gemm_tf32_addr.h) - rounded to TF32 in registers and written to shared memory in exactly the layout a SWIZZLE_128B K-major tensor map would produce
 // (row r of a k-block = 128 B = 32 floats; 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)), so the
 // UMMA descriptors are byte-identical to the 16-bit GEMM's (make_desc_k128; +32 B per K = 8 step).
 //
